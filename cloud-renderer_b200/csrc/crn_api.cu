@@ -1,0 +1,825 @@
+// crn_api.cu — the C-ABI (include/cloud_renderer_b200.h): context, host-side uniform
+// derivation (what the reference's pass drivers do on the CPU before each draw), buffer
+// management and the stream-ordered orchestration of the kernels in k_*.cu.
+//
+// Reference call sites replaced (src/main.cpp:98-124):
+//   Sun::update(volume)                -> crn_set_sun + derive_sun()          (src/Sun.hpp:26-43)
+//   volume->update()                   -> crn_set_volume/crn_set_billboards   (src/CloudVolume.cpp:84-93,139-164)
+//   voxelizeShader->voxelize(volume)   -> crn_voxelize                        (src/Shaders/VoxelizeShader.cpp:18-31)
+//   coneShader->coneTrace(volume)      -> crn_cone_trace                      (src/Shaders/ConeTraceShader.cpp:15-82)
+// There is no CPU fallback: every entry point that computes needs a CUDA device and fails
+// with CRN_ERR_NO_DEVICE / CRN_ERR_CUDA otherwise.
+#include "crn_internal.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+using namespace crn;
+
+// ------------------------------------------------------------------------------------------
+// host math: the GLM 0.9.8.5 calls the reference's drivers make (RH, -1..1 depth), float32,
+// one rounding per operation, sums left to right.
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct F3 { float v[3]; };
+inline F3 f3(const float *p) { return {{p[0], p[1], p[2]}}; }
+inline F3 sub3(F3 a, F3 b) { return {{a.v[0] - b.v[0], a.v[1] - b.v[1], a.v[2] - b.v[2]}}; }
+inline F3 add3(F3 a, F3 b) { return {{a.v[0] + b.v[0], a.v[1] + b.v[1], a.v[2] + b.v[2]}}; }
+inline F3 scale3(F3 a, float s) { return {{a.v[0] * s, a.v[1] * s, a.v[2] * s}}; }
+inline float dot3(F3 a, F3 b) { float t0 = a.v[0] * b.v[0], t1 = a.v[1] * b.v[1], t2 = a.v[2] * b.v[2]; return (t0 + t1) + t2; }
+inline float len3(F3 a) { return sqrtf(dot3(a, a)); }
+inline F3 norm3(F3 a) { return scale3(a, 1.0f / sqrtf(dot3(a, a))); }
+inline F3 cross3(F3 x, F3 y) {
+    return {{x.v[1] * y.v[2] - y.v[1] * x.v[2], x.v[2] * y.v[0] - y.v[2] * x.v[0], x.v[0] * y.v[1] - y.v[0] * x.v[1]}};
+}
+
+void look_at(F3 eye, F3 center, F3 up, float *m) {
+    const F3 f = norm3(sub3(center, eye));
+    const F3 s = norm3(cross3(f, up));
+    const F3 u = cross3(s, f);
+    for (int i = 0; i < 16; i++) m[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+    for (int c = 0; c < 3; c++) { m[c * 4 + 0] = s.v[c]; m[c * 4 + 1] = u.v[c]; m[c * 4 + 2] = -f.v[c]; }
+    m[12] = -dot3(s, eye); m[13] = -dot3(u, eye); m[14] = dot3(f, eye);
+}
+
+void ortho(float l, float r, float b, float t, float n, float f, float *m) {
+    for (int i = 0; i < 16; i++) m[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+    m[0] = 2.0f / (r - l); m[5] = 2.0f / (t - b); m[10] = -2.0f / (f - n);
+    m[12] = -(r + l) / (r - l); m[13] = -(t + b) / (t - b); m[14] = -(f + n) / (f - n);
+}
+
+void perspective(float fovy, float aspect, float n, float f, float *m) {
+    const float th = tanf(fovy / 2.0f);
+    for (int i = 0; i < 16; i++) m[i] = 0.0f;
+    m[0] = 1.0f / (aspect * th); m[5] = 1.0f / th; m[11] = -1.0f;
+    m[10] = -(f + n) / (f - n); m[14] = -(2.0f * f * n) / (f - n);
+}
+
+void derive_sun(const crn_volume_desc &vol, const crn_sun &sun, crn_sun_derived *out) {     // src/Sun.hpp:26-43
+    const F3 mn = {{vol.xBounds[0], vol.yBounds[0], vol.zBounds[0]}}, mx = {{vol.xBounds[1], vol.yBounds[1], vol.zBounds[1]}};
+    const F3 vp = f3(vol.position);
+    const F3 lookDir = norm3(sub3(vp, f3(sun.position)));
+    const float L = fmaxf(len3(mn), len3(mx));
+    const F3 lookPos = sub3(vp, scale3(lookDir, L));
+    const F3 upv = {{0.0f, 1.0f, 0.0f}};
+    look_at(lookPos, vp, upv, out->V);
+    const float minmin = 2.0f * fminf(mn.v[0], fminf(mn.v[1], mn.v[2]));
+    const float maxmax = 2.0f * fmaxf(mx.v[0], fmaxf(mx.v[1], mx.v[2]));
+    const F3 nearP = add3(lookPos, scale3(lookDir, 0.01f));
+    const F3 farP = add3(lookPos, scale3(scale3(lookDir, 2.0f), L));
+    for (int k = 0; k < 3; k++) { out->nearPlane[k] = nearP.v[k]; out->farPlane[k] = farP.v[k]; }
+    out->clipDistance = len3(sub3(farP, nearP));
+    ortho(minmin, maxmax, minmin, maxmax, 0.01f, 0.01f + out->clipDistance, out->P);
+}
+
+ViewParams make_view(const float *P, const float *V, int W, int H) {
+    ViewParams v;
+    for (int k = 0; k < 3; k++) { v.right[k] = V[4 * k + 0]; v.up[k] = V[4 * k + 1]; v.back[k] = V[4 * k + 2]; }
+    const F3 n = norm3(f3(v.back));
+    for (int k = 0; k < 3; k++) v.nrm[k] = n.v[k];
+    std::memcpy(v.V, V, 64); std::memcpy(v.P, P, 64);
+    v.ortho = (P[15] == 1.0f) ? 1 : 0;
+    v.W = W; v.H = H;
+    return v;
+}
+
+// host twin of k_prep_sort.cu's quad_rect, for the one sun quad
+void host_quad(const ViewParams &vp, const float c[3], float scale, BoardRec *rec, BoardRect *q) {
+    float cv[4];
+    for (int r = 0; r < 4; r++) cv[r] = ((vp.V[r] * c[0] + vp.V[4 + r] * c[1]) + vp.V[8 + r] * c[2]) + vp.V[12 + r];
+    *rec = {c[0], c[1], c[2], scale, cv[0], cv[1], cv[2], -1};
+    const float zv = cv[2];
+    const float zc = vp.P[10] * zv + vp.P[14] * 1.0f, wc = vp.P[11] * zv + vp.P[15] * 1.0f;
+    if (!(zc >= -wc && zc <= wc) || !(wc > 0.0f)) { *q = {0, -1, 0, -1}; return; }
+    const float W = (float)vp.W, H = (float)vp.H;
+    float x0 = (vp.P[0] * (cv[0] - scale) + vp.P[12] * 1.0f) / wc, x1 = (vp.P[0] * (cv[0] + scale) + vp.P[12] * 1.0f) / wc;
+    float y0 = (vp.P[5] * (cv[1] - scale) + vp.P[13] * 1.0f) / wc, y1 = (vp.P[5] * (cv[1] + scale) + vp.P[13] * 1.0f) / wc;
+    float fx0 = (x0 + 1.0f) * 0.5f * W, fx1 = (x1 + 1.0f) * 0.5f * W, fy0 = (y0 + 1.0f) * 0.5f * H, fy1 = (y1 + 1.0f) * 0.5f * H;
+    fx0 = fminf(fmaxf(fx0, -2.0f), W + 2.0f); fx1 = fminf(fmaxf(fx1, -2.0f), W + 2.0f);
+    fy0 = fminf(fmaxf(fy0, -2.0f), H + 2.0f); fy1 = fminf(fmaxf(fy1, -2.0f), H + 2.0f);
+    q->i0 = (int16_t)std::max(0, (int)floorf(fx0) - 1); q->i1 = (int16_t)std::min(vp.W - 1, (int)floorf(fx1) + 1);
+    q->j0 = (int16_t)std::max(0, (int)floorf(fy0) - 1); q->j1 = (int16_t)std::min(vp.H - 1, (int)floorf(fy1) + 1);
+}
+
+std::mutex g_err_mutex;
+std::string g_create_error;
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct crn_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool ownStream = false;
+    std::string err;
+    uint64_t launches = 0;
+
+    bool haveVol = false, haveSun = false, haveCam = false, haveNoise = false, haveWindow = false;
+    crn_volume_desc vol{};
+    crn_sun sun{};
+    crn_camera cam{};
+    crn_trace_params tp{};
+    int W = 0, H = 0;
+    int nBoards = 0;
+    int noiseDim = 0;
+    int row0 = 0, row1 = 1 << 30;
+    int z0 = 0, z1 = -1;                 // -1: whole volume
+    bool keepPosmap = false, statsOn = false, timingOn = false;
+    bool voxelized = false, traced = false;
+
+    VolumeParams vparams{};
+    size_t chainBytes = 0;
+
+    DevBuf pos, scale, keyL, keyC, rankL, rankC, recTmpL, recTmpC, rectTmpL, rectTmpC, lbTmp, recL, recC, rectL, rectC,
+        lbSorted, drawOrder, bits, chain, noise, posmap, image, misc;
+    Bins binsL, binsC;
+    uint32_t *hCursors = nullptr;        // pinned: [0..1] light cursors, [2..3] camera cursors
+    unsigned long long *hStats = nullptr;
+
+    cudaEvent_t evV[5] = {}, evT[4] = {};
+    bool evVValid = false, evTValid = false;
+};
+
+namespace {
+
+int fail(crn_ctx *c, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    else { std::lock_guard<std::mutex> g(g_err_mutex); g_create_error = buf; }
+    return code;
+}
+
+#define CRN_CUDA(c, call)                                                                              \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) return fail((c), CRN_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+int reserve(crn_ctx *c, DevBuf &b, size_t bytes) {
+    if (bytes <= b.cap) return CRN_OK;
+    CRN_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (b.p) CRN_CUDA(c, cudaFree(b.p));
+    b.p = nullptr; b.cap = 0;
+    const size_t want = bytes + bytes / 4 + 256;
+    CRN_CUDA(c, cudaMalloc(&b.p, want));
+    CRN_CUDA(c, cudaMemsetAsync(b.p, 0, want, c->stream));      // tickets / counters start at zero
+    b.cap = want;
+    return CRN_OK;
+}
+
+int alloc_u32(crn_ctx *c, uint32_t *&p, size_t &have, size_t want) {
+    if (want <= have) return CRN_OK;
+    CRN_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (p) CRN_CUDA(c, cudaFree(p));
+    p = nullptr; have = 0;
+    CRN_CUDA(c, cudaMalloc(&p, want * sizeof(uint32_t)));
+    have = want;
+    return CRN_OK;
+}
+
+int ensure_bins(crn_ctx *c, Bins &b, int W, int H, int n) {
+    b.tilesX = (W + kTile - 1) / kTile; b.tilesY = (H + kTile - 1) / kTile;
+    b.coarseX = (b.tilesX + kCoarse - 1) / kCoarse; b.coarseY = (b.tilesY + kCoarse - 1) / kCoarse;
+    const size_t tiles = (size_t)b.tilesX * b.tilesY, coarse = (size_t)b.coarseX * b.coarseY;
+    if (tiles > b.tilesAlloc) {
+        size_t h1 = b.tilesAlloc, h2 = b.tilesAlloc;
+        int r = alloc_u32(c, b.tileOff, h1, tiles); if (r) return r;
+        r = alloc_u32(c, b.tileCnt, h2, tiles); if (r) return r;
+        b.tilesAlloc = tiles;
+    }
+    if (coarse > b.coarseAlloc) {
+        size_t h1 = b.coarseAlloc, h2 = b.coarseAlloc;
+        int r = alloc_u32(c, b.coarseOff, h1, coarse); if (r) return r;
+        r = alloc_u32(c, b.coarseCnt, h2, coarse); if (r) return r;
+        b.coarseAlloc = coarse;
+    }
+    if (!b.cursors) CRN_CUDA(c, cudaMalloc(&b.cursors, 2 * sizeof(uint32_t)));
+    int r = alloc_u32(c, b.coarseList, b.coarseCap, std::max<size_t>((size_t)1 << 16, (size_t)n * 8)); if (r) return r;
+    r = alloc_u32(c, b.tileList, b.tileCap, std::max<size_t>((size_t)1 << 20, (size_t)n * 96)); if (r) return r;
+    return CRN_OK;
+}
+
+void free_bins(Bins &b) {
+    cudaFree(b.coarseOff); cudaFree(b.coarseCnt); cudaFree(b.coarseList);
+    cudaFree(b.tileOff); cudaFree(b.tileCnt); cudaFree(b.tileList); cudaFree(b.cursors);
+    b = Bins();
+}
+
+// grow a pool whose cursor ran past its capacity; returns true if anything grew
+int grow_if_overflowed(crn_ctx *c, Bins &b, const uint32_t *cur, bool *grew) {
+    *grew = false;
+    if (cur[0] > b.coarseCap) {
+        int r = alloc_u32(c, b.coarseList, b.coarseCap, (size_t)cur[0] + cur[0] / 2); if (r) return r;
+        *grew = true;
+    }
+    if (cur[1] > b.tileCap) {
+        int r = alloc_u32(c, b.tileList, b.tileCap, (size_t)cur[1] + cur[1] / 2); if (r) return r;
+        *grew = true;
+    }
+    return CRN_OK;
+}
+
+int check_volume(crn_ctx *c, const crn_volume_desc *d) {
+    const int D = d->dimension;
+    if (D < 32 || D > 2048 || (D & (D - 1))) return fail(c, CRN_ERR_UNSUPPORTED, "dimension %d: need a power of two in [32, 2048]", D);
+    int maxL = 1; for (int s = D; s > 1; s >>= 1) maxL++;
+    if (d->levels < 1 || d->levels > maxL || d->levels > kMaxLevels) return fail(c, CRN_ERR_INVALID_ARG, "levels %d out of range [1,%d]", d->levels, maxL);
+    if (!(d->xBounds[1] > d->xBounds[0] && d->yBounds[1] > d->yBounds[0] && d->zBounds[1] > d->zBounds[0]))
+        return fail(c, CRN_ERR_INVALID_ARG, "bounds must satisfy min < max on every axis");
+    if (d->format != CRN_VOLUME_R8) return fail(c, CRN_ERR_UNSUPPORTED, "volume format %d: the render path is R8 (the shipped reference format)", d->format);
+    return CRN_OK;
+}
+
+void fill_vparams(crn_ctx *c) {
+    VolumeParams &v = c->vparams;
+    const crn_volume_desc &d = c->vol;
+    for (int k = 0; k < 2; k++) {
+        v.xB[k] = d.position[0] + d.xBounds[k]; v.yB[k] = d.position[1] + d.yBounds[k]; v.zB[k] = d.position[2] + d.zBounds[k];
+    }
+    v.dim = d.dimension; v.levels = d.levels;
+    const float fd = (float)d.dimension;
+    const float rx = d.xBounds[1] - d.xBounds[0], ry = d.yBounds[1] - d.yBounds[0], rz = d.zBounds[1] - d.zBounds[0];
+    v.stepSize = fminf(rx / fd, fminf(ry / fd, rz / fd));          // src/Shaders/VoxelizeShader.cpp:128
+    size_t off = 0; int s = d.dimension;
+    for (int l = 0; l < kMaxLevels; l++) { v.levelOff[l] = 0; v.levelSize[l] = 0; }
+    for (int l = 0; l < d.levels; l++) {
+        v.levelOff[l] = (uint32_t)off; v.levelSize[l] = s;
+        off += ((size_t)s * s * s + 255) / 256 * 256;
+        s = std::max(1, s / 2);
+    }
+    c->chainBytes = off;
+    v.z0 = c->z1 < 0 ? 0 : c->z0;
+    v.z1 = c->z1 < 0 ? d.dimension : c->z1;
+}
+
+int require(crn_ctx *c, bool ok, const char *what) {
+    return ok ? CRN_OK : fail(c, CRN_ERR_STATE, "%s has not been set", what);
+}
+
+int enqueue_voxelize(crn_ctx *c) {
+    const int n = c->nBoards;
+    crn_sun_derived sd;
+    derive_sun(c->vol, c->sun, &sd);
+    const ViewParams light = make_view(sd.P, sd.V, c->W, c->H);
+    const ViewParams dummy = light;
+    fill_vparams(c);
+    int r;
+    const size_t nn = std::max(n, 1);
+    if ((r = reserve(c, c->keyL, nn * 8))) return r;
+    if ((r = reserve(c, c->rankL, nn * 4))) return r;
+    if ((r = reserve(c, c->recTmpL, nn * sizeof(BoardRec)))) return r;
+    if ((r = reserve(c, c->rectTmpL, nn * sizeof(BoardRect)))) return r;
+    if ((r = reserve(c, c->lbTmp, nn * 4))) return r;
+    if ((r = reserve(c, c->recL, nn * sizeof(BoardRec)))) return r;
+    if ((r = reserve(c, c->rectL, nn * sizeof(BoardRect)))) return r;
+    if ((r = reserve(c, c->lbSorted, nn * 4))) return r;
+    const size_t D = c->vol.dimension;
+    if ((r = reserve(c, c->bits, D * D * D / 8))) return r;
+    if ((r = reserve(c, c->chain, c->chainBytes))) return r;
+    if ((r = reserve(c, c->misc, 256))) return r;
+    if (c->keepPosmap && (r = reserve(c, c->posmap, (size_t)c->W * c->H * 16))) return r;
+    if ((r = ensure_bins(c, c->binsL, c->W, c->H, n))) return r;
+
+    cudaStream_t st = c->stream;
+    if (c->timingOn) cudaEventRecord(c->evV[0], st);
+    const float zero3[3] = {0, 0, 0};
+    c->launches += launch_prep_sort(st, (const float *)c->pos.p, (const float *)c->scale.p, n, c->vol.fluffiness, c->vol.position,
+                                    light, sd.nearPlane, sd.clipDistance, dummy, zero3, true, false, (uint32_t *)c->rankL.p, nullptr,
+                                    (uint64_t *)c->keyL.p, nullptr, (BoardRec *)c->recTmpL.p, nullptr, (BoardRect *)c->rectTmpL.p,
+                                    nullptr, (float *)c->lbTmp.p, (BoardRec *)c->recL.p, nullptr, (BoardRect *)c->rectL.p, nullptr,
+                                    (float *)c->lbSorted.p, nullptr);
+    if (c->timingOn) cudaEventRecord(c->evV[1], st);
+    c->launches += launch_bin(st, (const BoardRect *)c->rectL.p, n, c->W, c->H, c->binsL);
+    cudaMemcpyAsync(c->hCursors, c->binsL.cursors, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    if (c->timingOn) cudaEventRecord(c->evV[2], st);
+    c->launches += launch_voxelize(st, light, c->vparams, sd.nearPlane, sd.clipDistance, (const BoardRec *)c->recL.p,
+                                   (const float *)c->lbSorted.p, c->binsL, (uint32_t *)c->bits.p,
+                                   c->keepPosmap ? (float4 *)c->posmap.p : nullptr);
+    if (c->timingOn) cudaEventRecord(c->evV[3], st);
+    c->launches += launch_mips(st, c->vparams, (const uint32_t *)c->bits.p, (uint8_t *)c->chain.p, (uint32_t *)c->misc.p, true);
+    if (c->timingOn) { cudaEventRecord(c->evV[4], st); c->evVValid = true; }
+    CRN_CUDA(c, cudaGetLastError());
+    c->voxelized = true;
+    return CRN_OK;
+}
+
+void build_trace_params(crn_ctx *c, const ViewParams &cam, TraceParams *tp) {
+    std::memset(tp, 0, sizeof *tp);
+    tp->p = c->tp;
+    for (int k = 0; k < 3; k++) { tp->lightPos[k] = c->sun.position[k]; tp->octaveOffsets[k] = c->tp.windVel[k] * c->tp.runTime; }
+    tp->octaveOffsets[3] = 0.0f;
+    for (int k = 0; k < 4; k++) tp->bg[k] = c->tp.clearColor[k];
+    tp->sun = c->sun;
+    host_quad(cam, c->sun.position, c->sun.outerRadius, &tp->sunRec, &tp->sunRect);
+    tp->nSteps = c->tp.vctSteps;
+    tp->noiseDim = c->noiseDim;
+    tp->row0 = std::max(0, c->row0); tp->row1 = std::min(c->H, c->row1);
+    tp->active = (c->tp.doConeTrace || c->tp.doNoiseSample || c->tp.showQuad) ? 1 : 0;   // ConeTraceShader.cpp:16-18
+    tp->stats = c->statsOn ? 1 : 0;
+    // traceCone (res/conetrace_frag.glsl:64-79): per-step constants, float ops as written
+    float coneHeight = c->tp.vctConeInitialHeight;
+    const float tanHalf = tanf(c->tp.vctConeAngle / 2.0f);
+    const int L = c->vol.levels;
+    for (int i = 1; i <= c->tp.vctSteps; i++) {
+        const float coneRadius = coneHeight * tanHalf;
+        const float lod = log2f(fmaxf(1.0f, 2.0f * coneRadius)) + c->tp.vctLodOffset;
+        ConeStep &s = tp->steps[i - 1];
+        s.height = coneHeight;
+        s.weight = (float)i / ((float)c->tp.vctSteps * c->tp.vctDownScaling);
+        if (!(lod > 0.0f)) { s.level0 = 0; s.frac = 0.0f; }
+        else if (lod >= (float)(L - 1)) { s.level0 = L - 1; s.frac = 0.0f; }
+        else { const float fl = floorf(lod); s.level0 = (int)fl; s.frac = lod - fl; }
+        coneHeight += coneRadius;
+    }
+}
+
+int enqueue_trace(crn_ctx *c, int format) {
+    const int n = c->nBoards;
+    const ViewParams cam = make_view(c->cam.P, c->cam.V, c->W, c->H);
+    fill_vparams(c);
+    int r;
+    const size_t nn = std::max(n, 1);
+    if ((r = reserve(c, c->keyC, nn * 8))) return r;
+    if ((r = reserve(c, c->rankC, nn * 4))) return r;
+    if ((r = reserve(c, c->recTmpC, nn * sizeof(BoardRec)))) return r;
+    if ((r = reserve(c, c->rectTmpC, nn * sizeof(BoardRect)))) return r;
+    if ((r = reserve(c, c->recC, nn * sizeof(BoardRec)))) return r;
+    if ((r = reserve(c, c->rectC, nn * sizeof(BoardRect)))) return r;
+    if ((r = reserve(c, c->drawOrder, nn * 4))) return r;
+    if ((r = reserve(c, c->misc, 256))) return r;
+    const size_t texel = format == CRN_IMAGE_RGBA32F ? 16 : 4;
+    if ((r = reserve(c, c->image, (size_t)c->W * c->H * texel))) return r;
+    if ((r = ensure_bins(c, c->binsC, c->W, c->H, n))) return r;
+
+    TraceParams tp;
+    build_trace_params(c, cam, &tp);
+    cudaStream_t st = c->stream;
+    unsigned long long *dStats = (unsigned long long *)((char *)c->misc.p + 64);
+    if (c->statsOn) cudaMemsetAsync(dStats, 0, 4 * sizeof(unsigned long long), st);
+    if (c->timingOn) cudaEventRecord(c->evT[0], st);
+    const float zero3[3] = {0, 0, 0};
+    c->launches += launch_prep_sort(st, (const float *)c->pos.p, (const float *)c->scale.p, n, c->vol.fluffiness, c->vol.position, cam,
+                                    zero3, 1.0f, cam, c->cam.position, false, true, nullptr, (uint32_t *)c->rankC.p, nullptr,
+                                    (uint64_t *)c->keyC.p, nullptr, (BoardRec *)c->recTmpC.p, nullptr, (BoardRect *)c->rectTmpC.p,
+                                    nullptr, nullptr, (BoardRec *)c->recC.p, nullptr, (BoardRect *)c->rectC.p, nullptr,
+                                    (int32_t *)c->drawOrder.p);
+    if (c->timingOn) cudaEventRecord(c->evT[1], st);
+    c->launches += launch_bin(st, (const BoardRect *)c->rectC.p, n, c->W, c->H, c->binsC);
+    cudaMemcpyAsync(c->hCursors + 2, c->binsC.cursors, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    if (c->timingOn) cudaEventRecord(c->evT[2], st);
+    c->launches += launch_trace(st, cam, c->vparams, tp, (const BoardRec *)c->recC.p, c->binsC, (const uint32_t *)c->bits.p,
+                                (const uint8_t *)c->chain.p, (const int8_t *)c->noise.p, c->image.p, format, dStats);
+    if (c->timingOn) { cudaEventRecord(c->evT[3], st); c->evTValid = true; }
+    if (c->statsOn) cudaMemcpyAsync(c->hStats, dStats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+    CRN_CUDA(c, cudaGetLastError());
+    return CRN_OK;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------
+// exported
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *crn_version(void) { return "cloud-renderer_b200 0.1.0 sm_100a"; }
+
+const char *crn_last_error(const crn_ctx *ctx) {
+    if (ctx) return ctx->err.c_str();
+    std::lock_guard<std::mutex> g(g_err_mutex);
+    return g_create_error.c_str();
+}
+
+int crn_create(int device, void *stream, crn_ctx **out) {
+    if (!out) return fail(nullptr, CRN_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, CRN_ERR_NO_DEVICE, "no CUDA device (%s); this library has no CPU path", e == cudaSuccess ? "count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(nullptr, CRN_ERR_INVALID_ARG, "device %d out of range [0,%d)", device, count);
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(nullptr, CRN_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    crn_ctx *c = new crn_ctx();
+    c->device = device;
+    if (stream) c->stream = (cudaStream_t)stream;
+    else {
+        if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+            delete c;
+            return fail(nullptr, CRN_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+        }
+        c->ownStream = true;
+    }
+    cudaMallocHost(&c->hCursors, 4 * sizeof(uint32_t));
+    cudaMallocHost(&c->hStats, 4 * sizeof(unsigned long long));
+    std::memset(c->hCursors, 0, 4 * sizeof(uint32_t));
+    std::memset(c->hStats, 0, 4 * sizeof(unsigned long long));
+    for (auto &ev : c->evV) cudaEventCreate(&ev);
+    for (auto &ev : c->evT) cudaEventCreate(&ev);
+    crn_default_trace_params(&c->tp);
+    if ((e = cudaGetLastError()) != cudaSuccess) {
+        crn_destroy(c);
+        return fail(nullptr, CRN_ERR_CUDA, "context set-up: %s", cudaGetErrorString(e));
+    }
+    *out = c;
+    return CRN_OK;
+}
+
+void crn_destroy(crn_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf *bufs[] = {&c->pos, &c->scale, &c->keyL, &c->keyC, &c->rankL, &c->rankC, &c->recTmpL, &c->recTmpC, &c->rectTmpL,
+                      &c->rectTmpC, &c->lbTmp, &c->recL, &c->recC, &c->rectL, &c->rectC, &c->lbSorted, &c->drawOrder, &c->bits,
+                      &c->chain, &c->noise, &c->posmap, &c->image, &c->misc};
+    for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+    free_bins(c->binsL); free_bins(c->binsC);
+    if (c->hCursors) cudaFreeHost(c->hCursors);
+    if (c->hStats) cudaFreeHost(c->hStats);
+    for (auto &ev : c->evV) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : c->evT) if (ev) cudaEventDestroy(ev);
+    if (c->ownStream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int crn_sync(crn_ctx *c) {
+    if (!c) return CRN_ERR_INVALID_ARG;
+    CRN_CUDA(c, cudaSetDevice(c->device));
+    CRN_CUDA(c, cudaStreamSynchronize(c->stream));
+    return CRN_OK;
+}
+
+void crn_default_trace_params(crn_trace_params *p) {          // src/Shaders/ConeTraceShader.hpp:15-36
+    if (!p) return;
+    std::memset(p, 0, sizeof *p);
+    p->stepSize = 0.01f; p->noiseOpacity = 4.0f; p->numOctaves = 4; p->freqStep = 3.0f; p->persStep = 0.5f;
+    p->adjustSize = 40.0f; p->minNoiseSteps = 2; p->maxNoiseSteps = 8; p->minNoiseColor = 0.2f; p->noiseColorScale = 0.45f;
+    p->windVel[0] = 0.01f; p->windVel[1] = 0.0f; p->windVel[2] = 0.0f;
+    p->vctSteps = 16; p->vctConeAngle = 0.9f; p->vctConeInitialHeight = 0.1f; p->vctLodOffset = 0.0f; p->vctDownScaling = 1.0f;
+    p->showQuad = 0; p->doConeTrace = 1; p->doNoiseSample = 1;
+    p->runTime = 0.0f;
+    p->clearColor[0] = 0.2f; p->clearColor[1] = 0.3f; p->clearColor[2] = 0.5f; p->clearColor[3] = 1.0f;   // src/main.cpp:112
+    p->drawSun = 1;
+    p->transmittanceCutoff = 0.0f;
+}
+
+int crn_set_volume(crn_ctx *c, const crn_volume_desc *d) {
+    if (!c || !d) return CRN_ERR_INVALID_ARG;
+    int r = check_volume(c, d); if (r) return r;
+    if (c->haveVol && (c->vol.dimension != d->dimension || c->vol.levels != d->levels)) { c->voxelized = false; c->z1 = -1; c->z0 = 0; }
+    c->vol = *d; c->haveVol = true;
+    return CRN_OK;
+}
+
+int crn_set_billboards(crn_ctx *c, const float *positions3, const float *scales, int32_t count, int32_t mem) {
+    if (!c || count < 0 || (count > 0 && (!positions3 || !scales))) return fail(c, CRN_ERR_INVALID_ARG, "bad billboard arrays");
+    if (mem != CRN_MEM_HOST && mem != CRN_MEM_DEVICE) return fail(c, CRN_ERR_INVALID_ARG, "mem must be CRN_MEM_HOST or CRN_MEM_DEVICE");
+    CRN_CUDA(c, cudaSetDevice(c->device));
+    int r;
+    if ((r = reserve(c, c->pos, (size_t)std::max(count, 1) * 12))) return r;
+    if ((r = reserve(c, c->scale, (size_t)std::max(count, 1) * 4))) return r;
+    if (count) {
+        const cudaMemcpyKind kind = mem == CRN_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+        CRN_CUDA(c, cudaMemcpyAsync(c->pos.p, positions3, (size_t)count * 12, kind, c->stream));
+        CRN_CUDA(c, cudaMemcpyAsync(c->scale.p, scales, (size_t)count * 4, kind, c->stream));
+    }
+    c->nBoards = count;
+    return CRN_OK;
+}
+
+int crn_set_sun(crn_ctx *c, const crn_sun *sun) {
+    if (!c || !sun) return CRN_ERR_INVALID_ARG;
+    c->sun = *sun; c->haveSun = true;
+    return CRN_OK;
+}
+
+int crn_sun_update(const crn_volume_desc *vol, const crn_sun *sun, crn_sun_derived *out) {
+    if (!vol || !sun || !out) return CRN_ERR_INVALID_ARG;
+    derive_sun(*vol, *sun, out);
+    return CRN_OK;
+}
+
+int crn_set_camera(crn_ctx *c, const crn_camera *cam) {
+    if (!c || !cam) return CRN_ERR_INVALID_ARG;
+    const float *P = cam->P;
+    const bool persp = P[15] == 0.0f && P[11] == -1.0f, orth = P[15] == 1.0f && P[11] == 0.0f;
+    if (!(persp || orth) || P[1] != 0.0f || P[4] != 0.0f || P[8] != 0.0f || P[9] != 0.0f || P[0] == 0.0f || P[5] == 0.0f)
+        return fail(c, CRN_ERR_UNSUPPORTED, "P must be a glm::perspective or glm::ortho matrix (no skew, symmetric frustum)");
+    c->cam = *cam; c->haveCam = true;
+    return CRN_OK;
+}
+
+int crn_camera_update(int32_t width, int32_t height, const float eye[3], const float lookAt[3], crn_camera *out) {   // src/Camera.cpp:59-60
+    if (!eye || !lookAt || !out || width <= 0 || height <= 0) return CRN_ERR_INVALID_ARG;
+    const float aspect = (float)(width / height);             // integer division, as in the reference
+    perspective(45.0f, aspect, 0.01f, 2500.0f, out->P);       // 45 *radians* under GLM 0.9.8.5
+    const F3 upv = {{0.0f, 1.0f, 0.0f}};
+    look_at(f3(eye), f3(lookAt), upv, out->V);
+    for (int k = 0; k < 3; k++) out->position[k] = eye[k];
+    return CRN_OK;
+}
+
+int crn_set_window(crn_ctx *c, int32_t width, int32_t height) {
+    if (!c) return CRN_ERR_INVALID_ARG;
+    if (width <= 0 || height <= 0 || width > 32767 || height > 32767) return fail(c, CRN_ERR_INVALID_ARG, "window %dx%d out of range", width, height);
+    c->W = width; c->H = height; c->haveWindow = true;
+    return CRN_OK;
+}
+
+int crn_set_trace_params(crn_ctx *c, const crn_trace_params *p) {
+    if (!c || !p) return CRN_ERR_INVALID_ARG;
+    if (p->vctSteps < 0 || p->vctSteps > kMaxConeSteps) return fail(c, CRN_ERR_UNSUPPORTED, "vctSteps %d > %d", p->vctSteps, kMaxConeSteps);
+    if (p->numOctaves < 0 || p->numOctaves > kMaxOctaves) return fail(c, CRN_ERR_UNSUPPORTED, "numOctaves %d > %d", p->numOctaves, kMaxOctaves);
+    if (!(p->transmittanceCutoff >= 0.0f && p->transmittanceCutoff < 1.0f)) return fail(c, CRN_ERR_INVALID_ARG, "transmittanceCutoff must be in [0,1)");
+    c->tp = *p;
+    return CRN_OK;
+}
+
+int crn_build_noise(const int8_t *alpha, int32_t dim, int8_t *rgba) {      // src/Shaders/ConeTraceShader.cpp:100-151
+    if (!alpha || !rgba || dim <= 0) return CRN_ERR_INVALID_ARG;
+    auto wrap = [dim](int v) { if (v < 0) v += dim; return v % dim; };
+    auto at = [&](int x, int y, int z) { return wrap(x) + wrap(y) * dim + wrap(z) * dim * dim; };
+    auto rho = [&](int i) { return (float)alpha[i] / 128.0f; };
+    auto pack = [](float f) -> int8_t {
+        if (f != f) return 0;
+        const float v = fminf(fmaxf(f * 128.0f, -128.0f), 127.0f);
+        return (int8_t)(int)v;
+    };
+    for (int z = 0; z < dim; z++)
+        for (int y = 0; y < dim; y++)
+            for (int x = 0; x < dim; x++) {
+                F3 g;      // precedence quirk kept: only the second density is divided by heightAdjust (0.5)
+                g.v[0] = rho(at(x + 1, y, z)) - rho(at(x - 1, y, z)) / 0.5f;
+                g.v[1] = rho(at(x, y + 1, z)) - rho(at(x, y - 1, z)) / 0.5f;
+                g.v[2] = rho(at(x, y, z + 1)) - rho(at(x, y, z - 1)) / 0.5f;
+                const F3 nrm = norm3(g);
+                const int i = at(x, y, z);
+                rgba[4 * i + 0] = pack(nrm.v[0]); rgba[4 * i + 1] = pack(nrm.v[1]); rgba[4 * i + 2] = pack(nrm.v[2]);
+                rgba[4 * i + 3] = alpha[i];
+            }
+    return CRN_OK;
+}
+
+int crn_set_noise(crn_ctx *c, const int8_t *rgba, int32_t dim) {
+    if (!c || !rgba || dim <= 0 || dim > 512) return fail(c, CRN_ERR_INVALID_ARG, "bad noise texture");
+    CRN_CUDA(c, cudaSetDevice(c->device));
+    const size_t n = (size_t)dim * dim * dim;
+    // the fragment stage reads only .g and .a of the SNORM8 texel: decode them once, here
+    std::vector<float> ga(n * 2);
+    for (size_t i = 0; i < n; i++) {
+        ga[2 * i + 0] = fmaxf((float)rgba[4 * i + 1] / 127.0f, -1.0f);
+        ga[2 * i + 1] = fmaxf((float)rgba[4 * i + 3] / 127.0f, -1.0f);
+    }
+    int r = reserve(c, c->noise, n * 8); if (r) return r;
+    CRN_CUDA(c, cudaMemcpyAsync(c->noise.p, ga.data(), n * 8, cudaMemcpyHostToDevice, c->stream));
+    CRN_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->noiseDim = dim; c->haveNoise = true;
+    return CRN_OK;
+}
+
+int crn_voxelize(crn_ctx *c) {
+    if (!c) return CRN_ERR_INVALID_ARG;
+    int r;
+    if ((r = require(c, c->haveVol, "volume")) || (r = require(c, c->haveSun, "sun")) || (r = require(c, c->haveWindow, "window"))) return r;
+    CRN_CUDA(c, cudaSetDevice(c->device));
+    if ((r = enqueue_voxelize(c))) return r;
+    return CRN_OK;
+}
+
+// make sure neither pass ran with a truncated bin pool; re-run what did
+static int settle(crn_ctx *c, bool haveTrace, int format) {
+    for (int attempt = 0; attempt < 4; attempt++) {
+        CRN_CUDA(c, cudaStreamSynchronize(c->stream));
+        bool grewL = false, grewC = false;
+        int r;
+        if (c->voxelized && (r = grow_if_overflowed(c, c->binsL, c->hCursors, &grewL))) return r;
+        if (haveTrace && (r = grow_if_overflowed(c, c->binsC, c->hCursors + 2, &grewC))) return r;
+        if (!grewL && !grewC) return CRN_OK;
+        if (grewL && (r = enqueue_voxelize(c))) return r;
+        if (haveTrace && (r = enqueue_trace(c, format))) return r;
+    }
+    return fail(c, CRN_ERR_STATE, "bin pools did not settle");
+}
+
+int crn_cone_trace(crn_ctx *c, void *out, int32_t mem, int32_t format) {
+    if (!c || !out) return fail(c, CRN_ERR_INVALID_ARG, "out is NULL");
+    if (format != CRN_IMAGE_RGBA8 && format != CRN_IMAGE_RGBA32F) return fail(c, CRN_ERR_INVALID_ARG, "unknown image format %d", format);
+    if (mem != CRN_MEM_HOST && mem != CRN_MEM_DEVICE) return fail(c, CRN_ERR_INVALID_ARG, "mem must be CRN_MEM_HOST or CRN_MEM_DEVICE");
+    int r;
+    if ((r = require(c, c->haveVol, "volume")) || (r = require(c, c->haveSun, "sun")) || (r = require(c, c->haveCam, "camera")) ||
+        (r = require(c, c->haveWindow, "window")) || (r = require(c, c->haveNoise, "noise texture")))
+        return r;
+    if (!c->voxelized) return fail(c, CRN_ERR_STATE, "crn_voxelize has not produced a volume yet");
+    CRN_CUDA(c, cudaSetDevice(c->device));
+    if ((r = enqueue_trace(c, format))) return r;
+    if ((r = settle(c, true, format))) return r;
+    c->traced = true;
+    const size_t texel = format == CRN_IMAGE_RGBA32F ? 16 : 4;
+    const int r0 = std::max(0, c->row0), r1 = std::min(c->H, c->row1);
+    if (r1 > r0) {
+        const size_t offB = (size_t)r0 * c->W * texel, bytes = (size_t)(r1 - r0) * c->W * texel;
+        const cudaMemcpyKind kind = mem == CRN_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+        CRN_CUDA(c, cudaMemcpyAsync((char *)out + offB, (char *)c->image.p + offB, bytes, kind, c->stream));
+    }
+    if (mem == CRN_MEM_HOST) CRN_CUDA(c, cudaStreamSynchronize(c->stream));
+    return CRN_OK;
+}
+
+int crn_set_row_range(crn_ctx *c, int32_t row0, int32_t row1) {
+    if (!c || row0 < 0 || row1 < row0) return fail(c, CRN_ERR_INVALID_ARG, "bad row range");
+    c->row0 = row0; c->row1 = row1;
+    return CRN_OK;
+}
+
+int crn_set_z_slab(crn_ctx *c, int32_t z0, int32_t z1) {
+    if (!c) return CRN_ERR_INVALID_ARG;
+    int r = require(c, c->haveVol, "volume"); if (r) return r;
+    if (z0 < 0 || z1 <= z0 || z1 > c->vol.dimension || (z0 % 16) || (z1 % 16))
+        return fail(c, CRN_ERR_INVALID_ARG, "slab [%d,%d) must be non-empty, inside the volume and aligned to 16 slices", z0, z1);
+    c->z0 = z0; c->z1 = z1;
+    return CRN_OK;
+}
+
+int crn_volume_level_ptr(crn_ctx *c, int32_t level, void **dev_ptr, size_t *bytes) {
+    if (!c || !dev_ptr || !bytes) return CRN_ERR_INVALID_ARG;
+    int r = require(c, c->haveVol, "volume"); if (r) return r;
+    if (level < 0 || level >= c->vol.levels) return fail(c, CRN_ERR_INVALID_ARG, "level %d out of range", level);
+    fill_vparams(c);
+    if ((r = reserve(c, c->chain, c->chainBytes))) return r;
+    const size_t s = c->vparams.levelSize[level];
+    *dev_ptr = (char *)c->chain.p + c->vparams.levelOff[level];
+    *bytes = s * s * s;
+    return CRN_OK;
+}
+
+int crn_volume_bits_ptr(crn_ctx *c, void **dev_ptr, size_t *bytes) {
+    if (!c || !dev_ptr || !bytes) return CRN_ERR_INVALID_ARG;
+    int r = require(c, c->haveVol, "volume"); if (r) return r;
+    const size_t D = c->vol.dimension;
+    if ((r = reserve(c, c->bits, D * D * D / 8))) return r;
+    *dev_ptr = c->bits.p; *bytes = D * D * D / 8;
+    return CRN_OK;
+}
+
+int crn_finish_mips(crn_ctx *c, int32_t first_level) {
+    if (!c) return CRN_ERR_INVALID_ARG;
+    int r = require(c, c->haveVol, "volume"); if (r) return r;
+    if (first_level < 1 || first_level > c->vol.levels) return fail(c, CRN_ERR_INVALID_ARG, "first_level %d out of range", first_level);
+    CRN_CUDA(c, cudaSetDevice(c->device));
+    fill_vparams(c);
+    c->launches += launch_finish_mips(c->stream, c->vparams, (uint8_t *)c->chain.p, first_level);
+    CRN_CUDA(c, cudaGetLastError());
+    c->voxelized = true;
+    return CRN_OK;
+}
+
+int crn_read_volume(crn_ctx *c, int32_t level, void *dst) {
+    if (!c || !dst) return CRN_ERR_INVALID_ARG;
+    if (!c->voxelized) return fail(c, CRN_ERR_STATE, "no volume has been produced yet");
+    if (level < 0 || level >= c->vol.levels) return fail(c, CRN_ERR_INVALID_ARG, "level %d out of range", level);
+    CRN_CUDA(c, cudaSetDevice(c->device));
+    int r = settle(c, false, 0); if (r) return r;
+    const size_t s = c->vparams.levelSize[level];
+    CRN_CUDA(c, cudaMemcpyAsync(dst, (char *)c->chain.p + c->vparams.levelOff[level], s * s * s, cudaMemcpyDeviceToHost, c->stream));
+    CRN_CUDA(c, cudaStreamSynchronize(c->stream));
+    return CRN_OK;
+}
+
+int crn_count_active_voxels(crn_ctx *c, uint64_t *count) {
+    if (!c || !count) return CRN_ERR_INVALID_ARG;
+    if (!c->voxelized) return fail(c, CRN_ERR_STATE, "no volume has been produced yet");
+    CRN_CUDA(c, cudaSetDevice(c->device));
+    int r = settle(c, false, 0); if (r) return r;
+    const size_t D = c->vol.dimension;
+    unsigned long long *d = (unsigned long long *)((char *)c->misc.p + 128);
+    c->launches += launch_count_bits(c->stream, (const uint32_t *)c->bits.p, D * D * D / 32, d);
+    unsigned long long h = 0;
+    CRN_CUDA(c, cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CRN_CUDA(c, cudaStreamSynchronize(c->stream));
+    *count = h;
+    return CRN_OK;
+}
+
+int crn_keep_position_map(crn_ctx *c, int32_t enable) {
+    if (!c) return CRN_ERR_INVALID_ARG;
+    c->keepPosmap = enable != 0;
+    return CRN_OK;
+}
+
+int crn_read_position_map(crn_ctx *c, float *dst) {
+    if (!c || !dst) return CRN_ERR_INVALID_ARG;
+    if (!c->keepPosmap || !c->voxelized || !c->posmap.p) return fail(c, CRN_ERR_STATE, "enable crn_keep_position_map before crn_voxelize");
+    CRN_CUDA(c, cudaSetDevice(c->device));
+    int r = settle(c, false, 0); if (r) return r;
+    CRN_CUDA(c, cudaMemcpyAsync(dst, c->posmap.p, (size_t)c->W * c->H * 16, cudaMemcpyDeviceToHost, c->stream));
+    CRN_CUDA(c, cudaStreamSynchronize(c->stream));
+    return CRN_OK;
+}
+
+int crn_read_sorted_order(crn_ctx *c, int32_t *dst) {
+    if (!c || !dst) return CRN_ERR_INVALID_ARG;
+    if (!c->traced) return fail(c, CRN_ERR_STATE, "crn_cone_trace has not run yet");
+    CRN_CUDA(c, cudaSetDevice(c->device));
+    if (c->nBoards) CRN_CUDA(c, cudaMemcpyAsync(dst, c->drawOrder.p, (size_t)c->nBoards * 4, cudaMemcpyDeviceToHost, c->stream));
+    CRN_CUDA(c, cudaStreamSynchronize(c->stream));
+    return CRN_OK;
+}
+
+int crn_read_bins(crn_ctx *c, int32_t which, int32_t *tiles_x, int32_t *tiles_y, int32_t *tile_w, int32_t *tile_h,
+                  int32_t *counts, int32_t *entries, uint64_t *total) {
+    if (!c || (which != 0 && which != 1)) return CRN_ERR_INVALID_ARG;
+    if ((which == 0 && !c->voxelized) || (which == 1 && !c->traced)) return fail(c, CRN_ERR_STATE, "that pass has not run yet");
+    CRN_CUDA(c, cudaSetDevice(c->device));
+    int r = settle(c, false, 0); if (r) return r;
+    const Bins &b = which == 0 ? c->binsL : c->binsC;
+    const DevBuf &recs = which == 0 ? c->recL : c->recC;
+    const size_t tiles = (size_t)b.tilesX * b.tilesY;
+    if (tiles_x) *tiles_x = b.tilesX;
+    if (tiles_y) *tiles_y = b.tilesY;
+    if (tile_w) *tile_w = kTile;
+    if (tile_h) *tile_h = kTile;
+    std::vector<uint32_t> cnt(tiles), off(tiles);
+    CRN_CUDA(c, cudaMemcpy(cnt.data(), b.tileCnt, tiles * 4, cudaMemcpyDeviceToHost));
+    CRN_CUDA(c, cudaMemcpy(off.data(), b.tileOff, tiles * 4, cudaMemcpyDeviceToHost));
+    uint64_t tot = 0;
+    for (size_t t = 0; t < tiles; t++) tot += cnt[t];
+    if (total) *total = tot;
+    if (counts) for (size_t t = 0; t < tiles; t++) counts[t] = (int32_t)cnt[t];
+    if (entries && tot) {
+        const uint32_t cur = c->hCursors[which == 0 ? 1 : 3];
+        std::vector<uint32_t> list(cur);
+        CRN_CUDA(c, cudaMemcpy(list.data(), b.tileList, (size_t)cur * 4, cudaMemcpyDeviceToHost));
+        std::vector<BoardRec> rec(std::max(c->nBoards, 1));
+        CRN_CUDA(c, cudaMemcpy(rec.data(), recs.p, (size_t)c->nBoards * sizeof(BoardRec), cudaMemcpyDeviceToHost));
+        size_t o = 0;
+        for (size_t t = 0; t < tiles; t++)
+            for (uint32_t e = 0; e < cnt[t]; e++) entries[o++] = rec[list[off[t] + e]].idx;
+    }
+    return CRN_OK;
+}
+
+int crn_get_trace_stats(crn_ctx *c, crn_trace_stats *out) {
+    if (!c || !out) return CRN_ERR_INVALID_ARG;
+    if (!c->traced || !c->statsOn) return fail(c, CRN_ERR_STATE, "enable crn_set_stats before crn_cone_trace");
+    CRN_CUDA(c, cudaSetDevice(c->device));
+    CRN_CUDA(c, cudaStreamSynchronize(c->stream));
+    out->fragments = c->hStats[0]; out->coneSamples = c->hStats[1]; out->noiseSamples = c->hStats[2];
+    out->binEntries = c->hCursors[3];
+    return CRN_OK;
+}
+
+int crn_set_stats(crn_ctx *c, int32_t enable) {
+    if (!c) return CRN_ERR_INVALID_ARG;
+    c->statsOn = enable != 0;
+    return CRN_OK;
+}
+
+int crn_set_timing(crn_ctx *c, int32_t enable) {
+    if (!c) return CRN_ERR_INVALID_ARG;
+    c->timingOn = enable != 0;
+    if (!c->timingOn) c->evVValid = c->evTValid = false;
+    return CRN_OK;
+}
+
+int crn_get_timings(crn_ctx *c, crn_timings *out) {
+    if (!c || !out) return CRN_ERR_INVALID_ARG;
+    std::memset(out, 0, sizeof *out);
+    CRN_CUDA(c, cudaSetDevice(c->device));
+    CRN_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->evVValid) {
+        CRN_CUDA(c, cudaEventElapsedTime(&out->prepSortMs, c->evV[0], c->evV[1]));
+        CRN_CUDA(c, cudaEventElapsedTime(&out->lightBinMs, c->evV[1], c->evV[2]));
+        CRN_CUDA(c, cudaEventElapsedTime(&out->voxelizeMs, c->evV[2], c->evV[3]));
+        CRN_CUDA(c, cudaEventElapsedTime(&out->mipMs, c->evV[3], c->evV[4]));
+    }
+    if (c->evTValid) {
+        float t = 0;
+        CRN_CUDA(c, cudaEventElapsedTime(&t, c->evT[0], c->evT[1]));
+        out->prepSortMs += t;
+        CRN_CUDA(c, cudaEventElapsedTime(&out->camBinMs, c->evT[1], c->evT[2]));
+        CRN_CUDA(c, cudaEventElapsedTime(&out->traceMs, c->evT[2], c->evT[3]));
+    }
+    return CRN_OK;
+}
+
+int crn_get_launch_count(crn_ctx *c, uint64_t *count) {
+    if (!c || !count) return CRN_ERR_INVALID_ARG;
+    *count = c->launches;
+    return CRN_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,106 @@
+// crn_internal.cuh — shared declarations of the B200 Cloud-Renderer hot path (host + device).
+// Not part of the public boundary (that is include/cloud_renderer_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/cloud_renderer_b200.h"
+
+namespace crn {
+
+// ----------------------------------------------------------------------------------------
+// geometry of the two tilings
+// ----------------------------------------------------------------------------------------
+constexpr int kTile = 16;            // fine tile edge in pixels: one 256-thread CTA, 8 warps of 8x4
+constexpr int kCoarse = 8;           // coarse tile = kCoarse x kCoarse fine tiles (128 px)
+constexpr int kMaxConeSteps = 128;   // vctSteps upper bound (reference UI slider tops out far lower)
+constexpr int kMaxLevels = 16;
+constexpr int kMaxOctaves = 8;
+
+// One billboard as a pass sees it, stored in that pass's list order (32 B, two 128-bit loads).
+struct BoardRec {
+    float cx, cy, cz, r;     // world-space centre (volumePosition + boardPosition), radius (scale * fluffiness)
+    float xv, yv, zv;        // V * (centre, 1)
+    int32_t idx;             // instance index in the caller's arrays
+};
+
+// inclusive pixel rectangle of the quad (i1 < i0: clipped away)
+struct BoardRect {
+    int16_t i0, i1, j0, j1;
+};
+
+// The slice of a camera (light or user) the device code needs.
+struct ViewParams {
+    float right[3], up[3], back[3];   // rows of V's rotation block
+    float nrm[3];                     // normalize(back) == normalize(fragNor)
+    float V[16], P[16];
+    int32_t ortho;                    // P[15] == 1
+    int32_t W, H;
+};
+
+struct VolumeParams {                 // uniforms of VoxelizeShader::bindVolume / ConeTraceShader::bindVolume
+    float xB[2], yB[2], zB[2];        // absolute bounds (position + relative bounds)
+    int32_t dim, levels;
+    float stepSize;
+    uint32_t levelOff[kMaxLevels];    // byte offset of each level in the chain buffer
+    int32_t levelSize[kMaxLevels];
+    int32_t z0, z1;                   // slab (voxel slices) this context owns
+};
+
+struct ConeStep {                     // traceCone's per-step constants (identical for every fragment)
+    float height;                     // coneHeight at this step, voxels
+    float weight;                     // float(i) / (steps * vctDownScaling)
+    int32_t level0;                   // lower mip level sampled
+    float frac;                       // blend toward level0+1 (0: single level)
+};
+
+struct TraceParams {
+    crn_trace_params p;
+    float lightPos[3];
+    float octaveOffsets[4];
+    float bg[4];                      // clear colour
+    crn_sun sun;
+    BoardRect sunRect;
+    BoardRec sunRec;
+    int32_t nSteps;
+    int32_t noiseDim;
+    int32_t row0, row1;
+    int32_t active;                   // doConeTrace || doNoiseSample || showQuad
+    int32_t stats;
+    ConeStep steps[kMaxConeSteps];
+};
+
+// bins of one pass
+struct Bins {
+    int32_t tilesX = 0, tilesY = 0, coarseX = 0, coarseY = 0;
+    uint32_t *coarseOff = nullptr, *coarseCnt = nullptr;   // per coarse tile
+    uint32_t *coarseList = nullptr; size_t coarseCap = 0;
+    uint32_t *tileOff = nullptr, *tileCnt = nullptr;       // per fine tile
+    uint32_t *tileList = nullptr; size_t tileCap = 0;
+    uint32_t *cursors = nullptr;                            // [0] coarse cursor, [1] fine cursor (device)
+    size_t tilesAlloc = 0, coarseAlloc = 0;
+};
+
+// kernels' launch wrappers (each returns the number of kernels it launched)
+int launch_prep_sort(cudaStream_t st, const float *pos, const float *scale, int n, float fluff, const float volpos[3],
+                     const ViewParams &light, const float nearPlane[3], float clip, const ViewParams &cam,
+                     const float camPos[3], bool doLight, bool doCam, uint32_t *rankL, uint32_t *rankC,
+                     uint64_t *keyL, uint64_t *keyC, BoardRec *recTmpL, BoardRec *recTmpC, BoardRect *rectTmpL,
+                     BoardRect *rectTmpC, float *lbTmp, BoardRec *recL, BoardRec *recC, BoardRect *rectL,
+                     BoardRect *rectC, float *lbSorted, int32_t *drawOrder);
+int launch_bin(cudaStream_t st, const BoardRect *rects, int n, int W, int H, Bins &b);
+int launch_voxelize(cudaStream_t st, const ViewParams &light, const VolumeParams &vol, const float nearPlane[3],
+                    float clip, const BoardRec *recs, const float *lbSorted, const Bins &b, uint32_t *bits,
+                    float4 *posmap);
+int launch_mips(cudaStream_t st, const VolumeParams &vol, const uint32_t *bits, uint8_t *chain, uint32_t *ticket,
+                bool writeLevel0);
+int launch_finish_mips(cudaStream_t st, const VolumeParams &vol, uint8_t *chain, int firstLevel);
+int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol, const TraceParams &tp,
+                 const BoardRec *recs, const Bins &b, const uint32_t *bits, const uint8_t *chain,
+                 const int8_t *noise, void *image, int format, unsigned long long *stats);
+int launch_count_bits(cudaStream_t st, const uint32_t *bits, size_t words, unsigned long long *out);
+
+} // namespace crn

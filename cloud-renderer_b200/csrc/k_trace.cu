@@ -1,0 +1,361 @@
+// k_trace.cu — stage 3: voxel cone tracing of the noise-marched billboards, per pixel.
+//
+// Replaces ConeTraceShader::coneTrace's instanced, alpha-blended draw
+// (src/Shaders/ConeTraceShader.cpp:22-75), its GPU program (res/conetrace_frag.glsl:122-201
+// with helpers :48-120, vertex stage res/billboard_vert_instanced.glsl) and the frame state
+// around it: the clear (src/main.cpp:112-113), the optional sun pass
+// (src/Shaders/SunShader.cpp:7-42, res/sun_frag.glsl:14-28) and the fixed-function
+// SRC_ALPHA / ONE_MINUS_SRC_ALPHA blend (src/main.cpp:94-95).
+//
+// The reference shades one fragment per (billboard, covered pixel) and lets the ROP blend
+// them back to front.  Here one thread owns one pixel, a warp an 8x4 patch, a CTA a 16x16
+// tile, and walks the tile's billboard list (k_bin.cu) FRONT TO BACK carrying the
+// transmittance T of everything already composited:
+//     C += T * a * src;   T *= (1 - a);       final = C + T * background
+// which is the same sum the back-to-front blend produces, re-associated.  A warp stops as
+// soon as every pixel's T is under the caller's cutoff (vote), so the deep interior of the
+// cloud — hundreds of layers of overdraw at 20k billboards — is never shaded.  With
+// cutoff = 0 every fragment is shaded, as in the reference.
+//
+// Sampling is explicit (no texture units): the volume's level 0 is read from the 1-bit
+// occupancy set (2 MB at 256^3), coarser levels from the R8 chain, the 32^3 noise texture from
+// a pre-decoded (g,a) float2 copy; trilinear / mip-linear weights follow GL 4.4 §8.14 in full
+// float precision.  traceCone's per-step height, LOD split and weight are identical for every
+// fragment and are precomputed on the host (TraceParams::steps).
+#include "crn_internal.cuh"
+
+namespace crn {
+
+namespace {
+
+struct TraceArgs {
+    VolumeParams vol;
+    const BoardRec *recs;
+    const uint32_t *tileOff, *tileCnt, *tileList;
+    int tilesX, tilesY;
+    const uint32_t *bits;
+    const uint8_t *chain;
+    const float2 *noise;          // (g, a) decoded, dim^3
+    void *image;
+    int format;
+    unsigned long long *stats;
+    float volScale[3];            // voxelDim / range per axis
+};
+
+__device__ __forceinline__ float saturatef(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
+
+struct Lin {                       // one axis of a linear filter footprint
+    int i0, i1;
+    float a;
+};
+
+__device__ __forceinline__ Lin clamp_axis(float t, int n) {        // CLAMP_TO_EDGE
+    Lin l;
+    t -= 0.5f;
+    const float fl = floorf(t);
+    l.a = t - fl;
+    const float c = fminf(fmaxf(fl, -1.0f), (float)n);              // keeps NaN/inf away from the cast
+    const int i = (int)c;
+    l.i0 = min(max(i, 0), n - 1);
+    l.i1 = min(max(i + 1, 0), n - 1);
+    return l;
+}
+
+__device__ __forceinline__ Lin repeat_axis(float s, int n) {        // REPEAT
+    Lin l;
+    s -= floorf(s);
+    const float t = s * (float)n - 0.5f;
+    const float fl = floorf(t);
+    l.a = t - fl;
+    int i = (int)fl;                                                // [-1, n-1]
+    l.i0 = i < 0 ? i + n : i;
+    l.i1 = l.i0 + 1 == n ? 0 : l.i0 + 1;
+    return l;
+}
+
+__device__ __forceinline__ float lerpf(float a, float b, float t) { return fmaf(t, b - a, a); }
+
+// level 0 from the occupancy bits; returns the filtered UNORM value in [0,1]
+__device__ __forceinline__ float sample_bits(const uint32_t *__restrict__ bits, int D, float px, float py, float pz) {
+    const Lin X = clamp_axis(px, D), Y = clamp_axis(py, D), Z = clamp_axis(pz, D);
+    const int wpr = D >> 5;
+    const int w0 = X.i0 >> 5, w1 = X.i1 >> 5, s0 = X.i0 & 31, s1 = X.i1 & 31;
+    float c[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int y = (k & 1) ? Y.i1 : Y.i0, z = (k & 2) ? Z.i1 : Z.i0;
+        const uint32_t *row = bits + (size_t)(z * D + y) * wpr;
+        const uint32_t a = __ldg(row + w0);
+        const uint32_t b = (w1 == w0) ? a : __ldg(row + w1);
+        const float v0 = (float)((a >> s0) & 1u), v1 = (float)((b >> s1) & 1u);
+        c[k] = lerpf(v0, v1, X.a);
+    }
+    return lerpf(lerpf(c[0], c[1], Y.a), lerpf(c[2], c[3], Y.a), Z.a);
+}
+
+// level >= 1 from the R8 chain; returns the filtered UNORM value in [0,1]
+__device__ __forceinline__ float sample_bytes(const uint8_t *__restrict__ t, int n, float px, float py, float pz) {
+    const Lin X = clamp_axis(px, n), Y = clamp_axis(py, n), Z = clamp_axis(pz, n);
+    float c[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int y = (k & 1) ? Y.i1 : Y.i0, z = (k & 2) ? Z.i1 : Z.i0;
+        const uint8_t *row = t + (size_t)(z * n + y) * n;
+        c[k] = lerpf((float)__ldg(row + X.i0), (float)__ldg(row + X.i1), X.a);
+    }
+    return lerpf(lerpf(c[0], c[1], Y.a), lerpf(c[2], c[3], Y.a), Z.a) * (1.0f / 255.0f);
+}
+
+__device__ __forceinline__ float sample_level(const TraceArgs &a, int l, float px, float py, float pz) {
+    if (l == 0) return sample_bits(a.bits, a.vol.dim, px, py, pz);
+    const float s = 1.0f / (float)(1 << l);
+    return sample_bytes(a.chain + a.vol.levelOff[l], a.vol.levelSize[l], px * s, py * s, pz * s);
+}
+
+// texture(noiseMap, uvw): green and alpha channels only (the shader uses nothing else)
+__device__ __forceinline__ float2 sample_noise(const float2 *__restrict__ nz, int n, float u, float v, float w) {
+    const Lin X = repeat_axis(u, n), Y = repeat_axis(v, n), Z = repeat_axis(w, n);
+    float2 c[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int y = (k & 1) ? Y.i1 : Y.i0, z = (k & 2) ? Z.i1 : Z.i0;
+        const float2 *row = nz + (size_t)(z * n + y) * n;
+        const float2 t0 = __ldg(row + X.i0), t1 = __ldg(row + X.i1);
+        c[k] = make_float2(lerpf(t0.x, t1.x, X.a), lerpf(t0.y, t1.y, X.a));
+    }
+    const float2 c0 = make_float2(lerpf(c[0].x, c[1].x, Y.a), lerpf(c[0].y, c[1].y, Y.a));
+    const float2 c1 = make_float2(lerpf(c[2].x, c[3].x, Y.a), lerpf(c[2].y, c[3].y, Y.a));
+    return make_float2(lerpf(c0.x, c1.x, Z.a), lerpf(c0.y, c1.y, Z.a));
+}
+
+// sun_frag.glsl:14-28 on the sun quad; returns false when the pixel is not covered / discarded
+__device__ __forceinline__ bool sun_fragment(const TraceParams &tp, const ViewParams &cam, float ndcx, float ndcy, int px, int py,
+                                             float col[4]) {
+    const BoardRect r = tp.sunRect;
+    if (!(r.i1 >= r.i0) || px < r.i0 || px > r.i1 || py < r.j0 || py > r.j1) return false;
+    const BoardRec &q = tp.sunRec;
+    const float wz = cam.ortho ? 1.0f : -q.zv;
+    const float xv = cam.ortho ? (ndcx - cam.P[12]) / cam.P[0] : ndcx * wz / cam.P[0];
+    const float yv = cam.ortho ? (ndcy - cam.P[13]) / cam.P[5] : ndcy * wz / cam.P[5];
+    const float u = xv - q.xv, v = yv - q.yv;
+    if (!(fabsf(u) < q.r && fabsf(v) < q.r)) return false;
+    const float dist = sqrtf(u * u + v * v);                 // |fragPos - center| on the quad's plane
+    if (dist < tp.sun.innerRadius) {
+        col[0] = tp.sun.innerColor[0]; col[1] = tp.sun.innerColor[1]; col[2] = tp.sun.innerColor[2]; col[3] = 1.0f;
+        return true;
+    }
+    const float scale = (dist - tp.sun.innerRadius) / (tp.sun.outerRadius - tp.sun.innerRadius);
+    if (scale > 0.99f) return false;
+#pragma unroll
+    for (int k = 0; k < 3; k++) col[k] = tp.sun.outerColor[k] * scale + tp.sun.innerColor[k] * (1.0f - scale);
+    col[3] = 1.0f - scale;
+    return true;
+}
+
+__global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ TraceArgs a, const __grid_constant__ ViewParams cam,
+                                                    const __grid_constant__ TraceParams tp) {
+    const int tile = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tx = tile % a.tilesX, ty = tile / a.tilesX;
+    const int px = tx * kTile + (warp & 1) * 8 + (lane & 7);
+    const int py = ty * kTile + (warp >> 1) * 4 + (lane >> 3);
+    // rows outside [row0,row1) belong to another rank (image-space sharding)
+    const bool valid = px < cam.W && py < cam.H && py >= tp.row0 && py < tp.row1;
+    if (__all_sync(0xFFFFFFFFu, !valid)) return;
+
+    const float ndcx = ((float)px + 0.5f) / (float)cam.W * 2.0f - 1.0f;
+    const float ndcy = ((float)py + 0.5f) / (float)cam.H * 2.0f - 1.0f;
+    const float invP0 = 1.0f / cam.P[0], invP5 = 1.0f / cam.P[5];
+
+    // background = clear colour, then the sun pass blended over it
+    float bg[4] = {tp.bg[0], tp.bg[1], tp.bg[2], tp.bg[3]};
+    if (tp.p.drawSun) {
+        float sc[4];
+        if (sun_fragment(tp, cam, ndcx, ndcy, px, py, sc)) {
+            const float sa = saturatef(sc[3]);
+#pragma unroll
+            for (int k = 0; k < 4; k++) bg[k] = saturatef(sc[k]) * sa + bg[k] * (1.0f - sa);
+        }
+    }
+
+    float C[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    float T = 1.0f;
+    unsigned long long nFrag = 0, nCone = 0, nNoise = 0;
+
+    const uint32_t cnt = tp.active ? a.tileCnt[tile] : 0;
+    const uint32_t off = cnt ? a.tileOff[tile] : 0;
+    const float cutoff = tp.p.transmittanceCutoff;
+    const int D = a.vol.dim;
+    const int nzDim = tp.noiseDim;
+    const float invAdjust = 1.0f / tp.p.adjustSize;
+    const float noiseSpan = (float)(tp.p.maxNoiseSteps - tp.p.minNoiseSteps);
+    // viewRay = normalize(V[0][2], V[1][2], V[2][2]) = cam.nrm (res/conetrace_frag.glsl:138)
+    const float rx = cam.nrm[0], ry = cam.nrm[1], rz = cam.nrm[2];
+
+    for (uint32_t e = 0; e < cnt; e++) {
+        const bool live = valid && T > cutoff;                          // T starts at 1: cutoff 0 keeps everything live
+        if (__all_sync(0xFFFFFFFFu, !live)) break;                      // early ray termination, whole patch
+        const uint32_t k = a.tileList[off + e];
+        const float4 r0 = __ldg(reinterpret_cast<const float4 *>(&a.recs[k].cx));
+        const float4 r1 = __ldg(reinterpret_cast<const float4 *>(&a.recs[k].xv));
+        const float radius = r0.w;
+        // pixel centre on the quad's plane, relative to the quad's centre
+        const float wz = cam.ortho ? 1.0f : -r1.z;
+        const float xv = cam.ortho ? (ndcx - cam.P[12]) * invP0 : ndcx * wz * invP0;
+        const float yv = cam.ortho ? (ndcy - cam.P[13]) * invP5 : ndcy * wz * invP5;
+        const float u = xv - r1.x, v = yv - r1.y;
+        const float d2 = u * u + v * v, r2 = radius * radius;
+        const float h2 = r2 - d2;                                       // half chord squared
+
+        float col[4];
+        bool shade = live && fabsf(u) < radius && fabsf(v) < radius;    // inside the quad
+        if (tp.p.showQuad) {                                            // conetrace_frag.glsl:124-134
+            if (shade) {
+                const float q = sqrtf(d2) / radius;
+                const float sc = sqrtf(fmaxf(0.0f, 1.0f - q * q));
+                const float ftx = (u / radius + 1.0f) * 0.5f, fty = (v / radius + 1.0f) * 0.5f;
+                const bool border = ftx < 0.01f || fty < 0.01f || ftx > 0.99f || fty > 0.99f;
+                col[0] = col[1] = col[2] = col[3] = border ? 1.0f : sc;
+            }
+        } else {
+            // discards: raySphereIntersect's disc = 4*(r^2 - d^2) < 0.01 (noise on), and
+            // sphereContrib = sqrt(1 - d^2/r^2) < 0.01 (cone trace on)
+            if (tp.p.doNoiseSample) shade = shade && !(4.0f * h2 < 0.01f);
+            if (tp.p.doConeTrace) shade = shade && !(sqrtf(fmaxf(0.0f, 1.0f - d2 / r2)) < 0.01f);
+            if (!__any_sync(0xFFFFFFFFu, shade)) continue;
+            const float h = sqrtf(fmaxf(h2, 0.0f));
+            // fragPos - center, and the two sphere hits along the view ray: near = -h, far = +h
+            const float ox = u * cam.right[0] + v * cam.up[0];
+            const float oy = u * cam.right[1] + v * cam.up[1];
+            const float oz = u * cam.right[2] + v * cam.up[2];
+            col[0] = col[1] = col[2] = col[3] = 0.0f;
+
+            if (tp.p.doNoiseSample) {                                   // conetrace_frag.glsl:137-174
+                float ux = (ox - rx * h) / radius, uy = (oy - ry * h) / radius, uz = (oz - rz * h) / radius;   // unitTex
+                float tx = (r0.x + ox - rx * h) * invAdjust, tyy = (r0.y + oy - ry * h) * invAdjust,
+                      tz = (r0.z + oz - rz * h) * invAdjust;                                                // localTexNear
+                const float len = 2.0f * h * invAdjust;
+                float iSteps = fminf(len / tp.p.stepSize, noiseSpan) + (float)tp.p.minNoiseSteps;
+                const float inv = 1.0f / (iSteps - 1.0f);
+                const float dxs = rx * len * inv, dys = ry * len * inv, dzs = rz * len * inv;              // localTexDelta
+                float opacity = 0.0f, light = 0.0f;
+                const int nIter = shade ? (int)ceilf(iSteps) : 0;
+                const int nMax = __reduce_max_sync(0xFFFFFFFFu, nIter);
+                for (int i = 0; i < nMax; i++) {
+                    if (i < nIter) {
+                        float ng = 0.0f, na = 0.0f, freq = 1.0f, pers = 1.0f;
+                        for (int o = 0; o < tp.p.numOctaves; o++) {     // noise3D, :103-120
+                            const float offs = o < 3 ? tp.octaveOffsets[o] : 0.0f;
+                            const float2 s = sample_noise(a.noise, nzDim, (tx + offs) * freq, (tyy + offs) * freq, (tz + offs) * freq);
+                            ng = fmaf(pers, s.x, ng);
+                            na = fmaf(pers, s.y, na);
+                            freq *= tp.p.freqStep;
+                            pers *= tp.p.persStep;
+                        }
+                        na = fabsf(na);
+                        const float uu = ux * ux + uy * uy + uz * uz;
+                        ng += uy * rsqrtf(uu);                          // noiseCell.xyz += normalize(unitTex)
+                        opacity = fmaf(na, 1.0f - uu, opacity);
+                        light += saturatef(ng * 0.5f + 0.5f);
+                        tx += dxs; tyy += dys; tz += dzs;
+                        ux += dxs; uy += dys; uz += dzs;                // (sic) tex-space delta on the unit-sphere coord
+                        if (tp.stats) nNoise += tp.p.numOctaves;
+                    }
+                }
+                const float c = tp.p.minNoiseColor + tp.p.noiseColorScale * light * inv;
+                const float ftx = (u / radius + 1.0f) * 0.5f - 0.5f, fty = (v / radius + 1.0f) * 0.5f - 0.5f;
+                const float alpha = 1.0f - sqrtf(ftx * ftx + fty * fty) * 2.0f;
+                col[0] = col[1] = col[2] = c;
+                col[3] = saturatef(opacity * tp.p.noiseOpacity * inv) * alpha;
+            }
+
+            if (tp.p.doConeTrace) {                                     // conetrace_frag.glsl:176-200, traceCone :64-79
+                // start on the camera-facing sphere surface: fragPos + n * r * sphereContrib = center + o + n*h
+                const float wx3 = r0.x + ox + rx * h, wy3 = r0.y + oy + ry * h, wz3 = r0.z + oz + rz * h;
+                const float vx = (wx3 - a.vol.xB[0]) * a.volScale[0];   // calculateVoxelLerp
+                const float vy = (wy3 - a.vol.yB[0]) * a.volScale[1];
+                const float vz = (wz3 - a.vol.zB[0]) * a.volScale[2];
+                float dx = tp.lightPos[0] - wx3, dy = tp.lightPos[1] - wy3, dz = tp.lightPos[2] - wz3;
+                const float il = rsqrtf(dx * dx + dy * dy + dz * dz);
+                dx *= il; dy *= il; dz *= il;
+                float indirect = 0.0f;
+                if (shade) {
+                    for (int i = 0; i < tp.nSteps; i++) {
+                        const ConeStep st = tp.steps[i];
+                        const float sx = fmaf(st.height, dx, vx), sy = fmaf(st.height, dy, vy), sz = fmaf(st.height, dz, vz);
+                        float s = sample_level(a, st.level0, sx, sy, sz);
+                        if (st.frac != 0.0f) s = lerpf(s, sample_level(a, st.level0 + 1, sx, sy, sz), st.frac);
+                        indirect = fmaf(s, st.weight, indirect);
+                    }
+                }
+                if (tp.stats && shade) nCone += tp.nSteps;
+                if (tp.p.doNoiseSample) { col[0] *= indirect; col[1] *= indirect; col[2] *= indirect; }
+                else col[0] = col[1] = col[2] = col[3] = indirect;
+            }
+        }
+
+        if (shade) {                                                    // blend, front to back
+            const float sa = saturatef(col[3]);
+            const float w = T * sa;
+            C[0] = fmaf(w, saturatef(col[0]), C[0]);
+            C[1] = fmaf(w, saturatef(col[1]), C[1]);
+            C[2] = fmaf(w, saturatef(col[2]), C[2]);
+            C[3] = fmaf(w, sa, C[3]);
+            T *= (1.0f - sa);
+            nFrag++;
+        }
+    }
+
+    if (valid) {
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) o[k] = fmaf(T, bg[k], C[k]);
+        const size_t p = (size_t)py * cam.W + px;
+        if (a.format == CRN_IMAGE_RGBA32F) {
+            reinterpret_cast<float4 *>(a.image)[p] = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+            uchar4 q;
+            q.x = (unsigned char)floorf(saturatef(o[0]) * 255.0f + 0.5f);
+            q.y = (unsigned char)floorf(saturatef(o[1]) * 255.0f + 0.5f);
+            q.z = (unsigned char)floorf(saturatef(o[2]) * 255.0f + 0.5f);
+            q.w = (unsigned char)floorf(saturatef(o[3]) * 255.0f + 0.5f);
+            reinterpret_cast<uchar4 *>(a.image)[p] = q;
+        }
+    }
+
+    if (tp.stats) {
+        for (int s = 16; s > 0; s >>= 1) {
+            nFrag += __shfl_down_sync(0xFFFFFFFFu, nFrag, s);
+            nCone += __shfl_down_sync(0xFFFFFFFFu, nCone, s);
+            nNoise += __shfl_down_sync(0xFFFFFFFFu, nNoise, s);
+        }
+        if (lane == 0) {
+            if (nFrag) atomicAdd(&a.stats[0], nFrag);
+            if (nCone) atomicAdd(&a.stats[1], nCone);
+            if (nNoise) atomicAdd(&a.stats[2], nNoise);
+        }
+    }
+}
+
+} // namespace
+
+int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol, const TraceParams &tp,
+                 const BoardRec *recs, const Bins &b, const uint32_t *bits, const uint8_t *chain,
+                 const int8_t *noise, void *image, int format, unsigned long long *stats) {
+    TraceArgs a;
+    a.vol = vol;
+    a.recs = recs;
+    a.tileOff = b.tileOff; a.tileCnt = b.tileCnt; a.tileList = b.tileList;
+    a.tilesX = b.tilesX; a.tilesY = b.tilesY;
+    a.bits = bits; a.chain = chain;
+    a.noise = reinterpret_cast<const float2 *>(noise);
+    a.image = image; a.format = format; a.stats = stats;
+    const float fd = (float)vol.dim;
+    a.volScale[0] = fd / (vol.xB[1] - vol.xB[0]);
+    a.volScale[1] = fd / (vol.yB[1] - vol.yB[0]);
+    a.volScale[2] = fd / (vol.zB[1] - vol.zB[0]);
+    trace_kernel<<<b.tilesX * b.tilesY, 256, 0, st>>>(a, cam, tp);
+    return 1;
+}
+
+} // namespace crn
