@@ -18,6 +18,7 @@ CRN_OK, CRN_ERR_INVALID_ARG, CRN_ERR_CUDA, CRN_ERR_STATE, CRN_ERR_UNSUPPORTED, C
 MEM_HOST, MEM_DEVICE = 0, 1
 IMAGE_RGBA8, IMAGE_RGBA32F = 0, 1
 VOLUME_R8, VOLUME_R32F = 0, 1
+SAMPLER_EXPLICIT, SAMPLER_TEXTURE = 0, 1
 
 f32, i32, u64 = C.c_float, C.c_int32, C.c_uint64
 
@@ -47,7 +48,7 @@ class TraceParams(C.Structure):
                 ("vctDownScaling", f32),
                 ("showQuad", i32), ("doConeTrace", i32), ("doNoiseSample", i32),
                 ("runTime", f32),
-                ("clearColor", f32 * 4), ("drawSun", i32), ("transmittanceCutoff", f32)]
+                ("clearColor", f32 * 4), ("drawSun", i32), ("transmittanceCutoff", f32), ("sampler", i32)]
 
 
 class TraceStats(C.Structure):
@@ -66,6 +67,7 @@ EXPORTS = [
     "crn_set_z_slab", "crn_volume_level_ptr", "crn_volume_bits_ptr", "crn_finish_mips", "crn_read_volume",
     "crn_count_active_voxels", "crn_keep_position_map", "crn_read_position_map", "crn_read_sorted_order", "crn_read_bins",
     "crn_get_trace_stats", "crn_set_stats", "crn_set_timing", "crn_get_timings", "crn_get_launch_count", "crn_version",
+    "crn_microbench",
 ]
 
 _lib = None
@@ -118,6 +120,7 @@ def load_library():
     lib.crn_set_timing.argtypes = [vp, i32]
     lib.crn_get_timings.argtypes = [vp, C.POINTER(Timings)]
     lib.crn_get_launch_count.argtypes = [vp, C.POINTER(u64)]
+    lib.crn_microbench.argtypes = [C.c_int, i32, C.POINTER(C.c_double)]
     _lib = lib
     return lib
 
@@ -328,3 +331,16 @@ class Renderer:
         n = u64()
         self._ck(self.lib.crn_get_launch_count(self.h, C.byref(n)))
         return n.value
+
+
+MICROBENCH = {0: "tex3D trilinear RGBA8_SNORM 32^3 (L1)", 1: "tex3D trilinear R8 256^3 (L2)", 2: "LDG.32 L1-hit",
+              3: "global atomicOr (RED), 2 MB set", 4: "shared atomicOr", 5: "FFMA"}
+
+
+def microbench(which, device=0):
+    """giga lane-operations per second of one hardware ceiling (see crn_microbench)"""
+    g = C.c_double()
+    rc = load_library().crn_microbench(device, which, C.byref(g))
+    if rc:
+        raise CrnError(rc, "crn_microbench")
+    return g.value

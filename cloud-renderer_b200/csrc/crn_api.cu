@@ -147,6 +147,13 @@ struct crn_ctx {
     uint32_t *hCursors = nullptr;        // pinned: [0..1] light cursors, [2..3] camera cursors
     unsigned long long *hStats = nullptr;
 
+    // texture-unit copies (CRN_SAMPLER_TEXTURE)
+    cudaMipmappedArray_t volArray = nullptr;
+    int volArrayDim = 0, volArrayLevels = 0;
+    cudaArray_t noiseArray = nullptr;
+    TexSet ts{};
+    bool texCurrent = false;             // the arrays hold the chain of the last voxelize
+
     cudaEvent_t evV[5] = {}, evT[4] = {};
     bool evVValid = false, evTValid = false;
 };
@@ -234,6 +241,40 @@ int grow_if_overflowed(crn_ctx *c, Bins &b, const uint32_t *cur, bool *grew) {
     return CRN_OK;
 }
 
+void free_vol_textures(crn_ctx *c) {
+    for (int l = 0; l < kMaxLevels; l++) {
+        if (c->ts.tex[l]) cudaDestroyTextureObject(c->ts.tex[l]);
+        if (c->ts.surf[l]) cudaDestroySurfaceObject(c->ts.surf[l]);
+        c->ts.tex[l] = 0; c->ts.surf[l] = 0;
+    }
+    if (c->volArray) cudaFreeMipmappedArray(c->volArray);
+    c->volArray = nullptr; c->volArrayDim = c->volArrayLevels = 0; c->ts.enabled = 0; c->texCurrent = false;
+}
+
+// the R8 immutable 3D texture with `levels` mips of the reference (src/CloudVolume.cpp:18-23):
+// LINEAR within a level, CLAMP_TO_EDGE x3; the mip-linear blend is done in the kernel.
+int ensure_vol_textures(crn_ctx *c) {
+    const int D = c->vol.dimension, L = c->vol.levels;
+    if (c->volArray && c->volArrayDim == D && c->volArrayLevels == L) return CRN_OK;
+    CRN_CUDA(c, cudaStreamSynchronize(c->stream));
+    free_vol_textures(c);
+    cudaChannelFormatDesc cd = cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned);
+    CRN_CUDA(c, cudaMallocMipmappedArray(&c->volArray, &cd, make_cudaExtent(D, D, D), L, cudaArraySurfaceLoadStore));
+    for (int l = 0; l < L; l++) {
+        cudaArray_t lvl = nullptr;
+        CRN_CUDA(c, cudaGetMipmappedArrayLevel(&lvl, c->volArray, l));
+        cudaResourceDesc rd{};
+        rd.resType = cudaResourceTypeArray; rd.res.array.array = lvl;
+        CRN_CUDA(c, cudaCreateSurfaceObject(&c->ts.surf[l], &rd));
+        cudaTextureDesc td{};
+        td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModeLinear; td.readMode = cudaReadModeNormalizedFloat; td.normalizedCoords = 1;
+        CRN_CUDA(c, cudaCreateTextureObject(&c->ts.tex[l], &rd, &td, nullptr));
+    }
+    c->volArrayDim = D; c->volArrayLevels = L; c->ts.enabled = 1; c->texCurrent = false;
+    return CRN_OK;
+}
+
 int check_volume(crn_ctx *c, const crn_volume_desc *d) {
     const int D = d->dimension;
     if (D < 32 || D > 2048 || (D & (D - 1))) return fail(c, CRN_ERR_UNSUPPORTED, "dimension %d: need a power of two in [32, 2048]", D);
@@ -294,6 +335,8 @@ int enqueue_voxelize(crn_ctx *c) {
     if ((r = reserve(c, c->misc, 256))) return r;
     if (c->keepPosmap && (r = reserve(c, c->posmap, (size_t)c->W * c->H * 16))) return r;
     if ((r = ensure_bins(c, c->binsL, c->W, c->H, n))) return r;
+    const bool toTex = c->tp.sampler == CRN_SAMPLER_TEXTURE;
+    if (toTex && (r = ensure_vol_textures(c))) return r;
 
     cudaStream_t st = c->stream;
     if (c->timingOn) cudaEventRecord(c->evV[0], st);
@@ -311,7 +354,9 @@ int enqueue_voxelize(crn_ctx *c) {
                                    (const float *)c->lbSorted.p, c->binsL, (uint32_t *)c->bits.p,
                                    c->keepPosmap ? (float4 *)c->posmap.p : nullptr);
     if (c->timingOn) cudaEventRecord(c->evV[3], st);
-    c->launches += launch_mips(st, c->vparams, (const uint32_t *)c->bits.p, (uint8_t *)c->chain.p, (uint32_t *)c->misc.p, true);
+    c->launches += launch_mips(st, c->vparams, (const uint32_t *)c->bits.p, (uint8_t *)c->chain.p, (uint32_t *)c->misc.p, true,
+                               toTex ? &c->ts : nullptr);
+    c->texCurrent = toTex && c->vparams.z0 == 0 && c->vparams.z1 == c->vol.dimension;
     if (c->timingOn) { cudaEventRecord(c->evV[4], st); c->evVValid = true; }
     CRN_CUDA(c, cudaGetLastError());
     c->voxelized = true;
@@ -369,6 +414,14 @@ int enqueue_trace(crn_ctx *c, int format) {
     TraceParams tp;
     build_trace_params(c, cam, &tp);
     cudaStream_t st = c->stream;
+    const bool useTex = c->tp.sampler == CRN_SAMPLER_TEXTURE;
+    if (useTex) {
+        if ((r = ensure_vol_textures(c))) return r;
+        if (!c->texCurrent) {           // sampler switched after voxelize, or the chain came from an exchange
+            c->launches += launch_chain_to_surfaces(st, c->vparams, (const uint8_t *)c->chain.p, c->ts, 0);
+            c->texCurrent = true;
+        }
+    }
     unsigned long long *dStats = (unsigned long long *)((char *)c->misc.p + 64);
     if (c->statsOn) cudaMemsetAsync(dStats, 0, 4 * sizeof(unsigned long long), st);
     if (c->timingOn) cudaEventRecord(c->evT[0], st);
@@ -383,7 +436,8 @@ int enqueue_trace(crn_ctx *c, int format) {
     cudaMemcpyAsync(c->hCursors + 2, c->binsC.cursors, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
     if (c->timingOn) cudaEventRecord(c->evT[2], st);
     c->launches += launch_trace(st, cam, c->vparams, tp, (const BoardRec *)c->recC.p, c->binsC, (const uint32_t *)c->bits.p,
-                                (const uint8_t *)c->chain.p, (const int8_t *)c->noise.p, c->image.p, format, dStats);
+                                (const uint8_t *)c->chain.p, (const int8_t *)c->noise.p, useTex ? &c->ts : nullptr, c->image.p, format,
+                                dStats);
     if (c->timingOn) { cudaEventRecord(c->evT[3], st); c->evTValid = true; }
     if (c->statsOn) cudaMemcpyAsync(c->hStats, dStats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
     CRN_CUDA(c, cudaGetLastError());
@@ -448,6 +502,9 @@ void crn_destroy(crn_ctx *c) {
                       &c->chain, &c->noise, &c->posmap, &c->image, &c->misc};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     free_bins(c->binsL); free_bins(c->binsC);
+    free_vol_textures(c);
+    if (c->ts.noise) cudaDestroyTextureObject(c->ts.noise);
+    if (c->noiseArray) cudaFreeArray(c->noiseArray);
     if (c->hCursors) cudaFreeHost(c->hCursors);
     if (c->hStats) cudaFreeHost(c->hStats);
     for (auto &ev : c->evV) if (ev) cudaEventDestroy(ev);
@@ -475,6 +532,7 @@ void crn_default_trace_params(crn_trace_params *p) {          // src/Shaders/Con
     p->clearColor[0] = 0.2f; p->clearColor[1] = 0.3f; p->clearColor[2] = 0.5f; p->clearColor[3] = 1.0f;   // src/main.cpp:112
     p->drawSun = 1;
     p->transmittanceCutoff = 0.0f;
+    p->sampler = CRN_SAMPLER_EXPLICIT;
 }
 
 int crn_set_volume(crn_ctx *c, const crn_volume_desc *d) {
@@ -545,6 +603,7 @@ int crn_set_trace_params(crn_ctx *c, const crn_trace_params *p) {
     if (p->vctSteps < 0 || p->vctSteps > kMaxConeSteps) return fail(c, CRN_ERR_UNSUPPORTED, "vctSteps %d > %d", p->vctSteps, kMaxConeSteps);
     if (p->numOctaves < 0 || p->numOctaves > kMaxOctaves) return fail(c, CRN_ERR_UNSUPPORTED, "numOctaves %d > %d", p->numOctaves, kMaxOctaves);
     if (!(p->transmittanceCutoff >= 0.0f && p->transmittanceCutoff < 1.0f)) return fail(c, CRN_ERR_INVALID_ARG, "transmittanceCutoff must be in [0,1)");
+    if (p->sampler != CRN_SAMPLER_EXPLICIT && p->sampler != CRN_SAMPLER_TEXTURE) return fail(c, CRN_ERR_INVALID_ARG, "unknown sampler %d", p->sampler);
     c->tp = *p;
     return CRN_OK;
 }
@@ -587,6 +646,21 @@ int crn_set_noise(crn_ctx *c, const int8_t *rgba, int32_t dim) {
     int r = reserve(c, c->noise, n * 8); if (r) return r;
     CRN_CUDA(c, cudaMemcpyAsync(c->noise.p, ga.data(), n * 8, cudaMemcpyHostToDevice, c->stream));
     CRN_CUDA(c, cudaStreamSynchronize(c->stream));
+    // texture-unit copy: GL_RGBA8_SNORM, REPEAT x3, LINEAR, no mips (src/Shaders/ConeTraceShader.cpp:152-158)
+    if (c->ts.noise) { cudaDestroyTextureObject(c->ts.noise); c->ts.noise = 0; }
+    if (c->noiseArray) { cudaFreeArray(c->noiseArray); c->noiseArray = nullptr; }
+    cudaChannelFormatDesc cd = cudaCreateChannelDesc(8, 8, 8, 8, cudaChannelFormatKindSigned);
+    CRN_CUDA(c, cudaMalloc3DArray(&c->noiseArray, &cd, make_cudaExtent(dim, dim, dim)));
+    cudaMemcpy3DParms cp{};
+    cp.srcPtr = make_cudaPitchedPtr((void *)rgba, (size_t)dim * 4, dim, dim);
+    cp.dstArray = c->noiseArray; cp.extent = make_cudaExtent(dim, dim, dim); cp.kind = cudaMemcpyHostToDevice;
+    CRN_CUDA(c, cudaMemcpy3D(&cp));
+    cudaResourceDesc rd{};
+    rd.resType = cudaResourceTypeArray; rd.res.array.array = c->noiseArray;
+    cudaTextureDesc td{};
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeWrap;
+    td.filterMode = cudaFilterModeLinear; td.readMode = cudaReadModeNormalizedFloat; td.normalizedCoords = 1;
+    CRN_CUDA(c, cudaCreateTextureObject(&c->ts.noise, &rd, &td, nullptr));
     c->noiseDim = dim; c->haveNoise = true;
     return CRN_OK;
 }
@@ -684,6 +758,7 @@ int crn_finish_mips(crn_ctx *c, int32_t first_level) {
     c->launches += launch_finish_mips(c->stream, c->vparams, (uint8_t *)c->chain.p, first_level);
     CRN_CUDA(c, cudaGetLastError());
     c->voxelized = true;
+    c->texCurrent = false;              // the texture-unit copy is refreshed from the chain at the next trace
     return CRN_OK;
 }
 

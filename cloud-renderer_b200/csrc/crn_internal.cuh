@@ -95,12 +95,21 @@ int launch_bin(cudaStream_t st, const BoardRect *rects, int n, int W, int H, Bin
 int launch_voxelize(cudaStream_t st, const ViewParams &light, const VolumeParams &vol, const float nearPlane[3],
                     float clip, const BoardRec *recs, const float *lbSorted, const Bins &b, uint32_t *bits,
                     float4 *posmap);
+// texture-unit view of the chain + noise (CRN_SAMPLER_TEXTURE)
+struct TexSet {
+    cudaSurfaceObject_t surf[kMaxLevels];   // one per level, written by the mip kernel
+    cudaTextureObject_t tex[kMaxLevels];    // one per level: LINEAR, CLAMP, normalized coords, UNORM8 -> float
+    cudaTextureObject_t noise;              // RGBA8_SNORM, LINEAR, REPEAT
+    int32_t enabled;
+};
+
 int launch_mips(cudaStream_t st, const VolumeParams &vol, const uint32_t *bits, uint8_t *chain, uint32_t *ticket,
-                bool writeLevel0);
+                bool writeLevel0, const TexSet *ts);
+int launch_chain_to_surfaces(cudaStream_t st, const VolumeParams &vol, const uint8_t *chain, const TexSet &ts, int firstLevel);
 int launch_finish_mips(cudaStream_t st, const VolumeParams &vol, uint8_t *chain, int firstLevel);
 int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol, const TraceParams &tp,
                  const BoardRec *recs, const Bins &b, const uint32_t *bits, const uint8_t *chain,
-                 const int8_t *noise, void *image, int format, unsigned long long *stats);
+                 const int8_t *noise, const TexSet *ts, void *image, int format, unsigned long long *stats);
 int launch_count_bits(cudaStream_t st, const uint32_t *bits, size_t words, unsigned long long *out);
 
 } // namespace crn

@@ -31,6 +31,8 @@ struct MipArgs {
     int writeLevel0;
     int tail;               // compute levels >= 5 in the last CTA (off in slab mode)
     int zBrick0;            // first brick row in z (slab mode)
+    int useSurf;            // also write every level into the texture-unit copy (CRN_SAMPLER_TEXTURE)
+    cudaSurfaceObject_t surf[kMaxLevels];
 };
 
 __device__ __forceinline__ uint32_t spread4(uint32_t nib) {    // 4 bits -> 4 bytes of 0x00/0xFF
@@ -46,7 +48,7 @@ template <int WX>   // words per brick row: 1, 2 or 4
 __global__ void __launch_bounds__(256) mip_chain_kernel(MipArgs a) {
     constexpr int BX = WX * 32;
     __shared__ uint32_t sBits[256 * WX];                 // [row = z*16+y][word]
-    __shared__ uint8_t sL1[(BX / 2) * 8 * 8];
+    __shared__ __align__(16) uint8_t sL1[(BX / 2) * 8 * 8];
     __shared__ uint8_t sL2[(BX / 4) * 4 * 4];
     __shared__ uint8_t sL3[(BX / 8) * 2 * 2];
     __shared__ uint8_t sL4[(BX / 16)];
@@ -84,6 +86,7 @@ __global__ void __launch_bounds__(256) mip_chain_kernel(MipArgs a) {
             o.x = spread4(h & 15u); o.y = spread4((h >> 4) & 15u); o.z = spread4((h >> 8) & 15u); o.w = spread4(h >> 12);
             const int y = row & 15, z = row >> 4;
             *reinterpret_cast<uint4 *>(l0 + ((size_t)(z0 + z) * D + (y0 + y)) * D + x0 + seg * 16) = o;
+            if (a.useSurf) surf3Dwrite(o, a.surf[0], x0 + seg * 16, y0 + y, z0 + z);
         }
     }
 
@@ -114,6 +117,7 @@ __global__ void __launch_bounds__(256) mip_chain_kernel(MipArgs a) {
             const int D1 = D >> 1;
             uint8_t *l1 = a.chain + a.vol.levelOff[1];
             *reinterpret_cast<uint4 *>(l1 + ((size_t)((z0 >> 1) + z1) * D1 + ((y0 >> 1) + y1)) * D1 + (x0 >> 1) + w * 16) = ov;
+            if (a.useSurf) surf3Dwrite(ov, a.surf[1], (x0 >> 1) + w * 16, (y0 >> 1) + y1, (z0 >> 1) + z1);
         }
     }
     __syncthreads();
@@ -134,6 +138,7 @@ __global__ void __launch_bounds__(256) mip_chain_kernel(MipArgs a) {
             const uint8_t v = (uint8_t)box8(s);
             dst[o] = v;
             out[((size_t)((z0 >> lvl) + z) * Dl + ((y0 >> lvl) + y)) * Dl + (x0 >> lvl) + x] = v;
+            if (a.useSurf) surf3Dwrite(v, a.surf[lvl], (x0 >> lvl) + x, (y0 >> lvl) + y, (z0 >> lvl) + z);
         }
     };
     if (L > 2) { reduce(sL1, sL2, BX / 2, 8, 2); __syncthreads(); }
@@ -166,7 +171,9 @@ __global__ void __launch_bounds__(256) mip_chain_kernel(MipArgs a) {
                 const uint16_t two = __ldcg(reinterpret_cast<const uint16_t *>(p));
                 s += (two & 0xFFu) + (two >> 8);
             }
-            dst[o] = (uint8_t)box8(s);
+            const uint8_t v = (uint8_t)box8(s);
+            dst[o] = v;
+            if (a.useSurf) surf3Dwrite(v, a.surf[lvl], x, y, z);
         }
         __threadfence();
         __syncthreads();
@@ -191,6 +198,24 @@ __global__ void __launch_bounds__(256) mip_level_kernel(const uint8_t *__restric
     }
 }
 
+// linear chain level -> its texture-unit copy (after a slab exchange / crn_finish_mips)
+__global__ void __launch_bounds__(256) level_to_surface_kernel(const uint8_t *__restrict__ src, cudaSurfaceObject_t surf, int n) {
+    const size_t total = (size_t)n * n * n;
+    if (n >= 16) {
+        const size_t vecs = total / 16;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < vecs; i += (size_t)gridDim.x * blockDim.x) {
+            const size_t e = i * 16;
+            const int x = (int)(e % n), y = (int)((e / n) % n), z = (int)(e / ((size_t)n * n));
+            surf3Dwrite(*reinterpret_cast<const uint4 *>(src + e), surf, x, y, z);
+        }
+    } else {
+        for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+            const int x = (int)(e % n), y = (int)((e / n) % n), z = (int)(e / ((size_t)n * n));
+            surf3Dwrite(src[e], surf, x, y, z);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) count_bits_kernel(const uint32_t *__restrict__ bits, size_t words, unsigned long long *out) {
     unsigned long long c = 0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x)
@@ -202,7 +227,7 @@ __global__ void __launch_bounds__(256) count_bits_kernel(const uint32_t *__restr
 } // namespace
 
 int launch_mips(cudaStream_t st, const VolumeParams &vol, const uint32_t *bits, uint8_t *chain, uint32_t *ticket,
-                bool writeLevel0) {
+                bool writeLevel0, const TexSet *ts) {
     MipArgs a;
     a.vol = vol; a.bits = bits; a.chain = chain; a.ticket = ticket;
     a.bx = vol.dim >= 128 ? 128 : vol.dim;
@@ -210,11 +235,25 @@ int launch_mips(cudaStream_t st, const VolumeParams &vol, const uint32_t *bits, 
     const bool whole = vol.z0 == 0 && vol.z1 == vol.dim;
     a.tail = whole ? 1 : 0;
     a.zBrick0 = vol.z0 / 16;
+    a.useSurf = (ts && ts->enabled) ? 1 : 0;
+    for (int l = 0; l < kMaxLevels; l++) a.surf[l] = a.useSurf ? ts->surf[l] : 0;
     dim3 grid(vol.dim / a.bx, vol.dim / 16, (vol.z1 - vol.z0) / 16);
     if (a.bx == 128) mip_chain_kernel<4><<<grid, 256, 0, st>>>(a);
     else if (a.bx == 64) mip_chain_kernel<2><<<grid, 256, 0, st>>>(a);
     else mip_chain_kernel<1><<<grid, 256, 0, st>>>(a);
     return 1;
+}
+
+int launch_chain_to_surfaces(cudaStream_t st, const VolumeParams &vol, const uint8_t *chain, const TexSet &ts, int firstLevel) {
+    int launches = 0;
+    for (int l = firstLevel; l < vol.levels; l++) {
+        const int n = vol.levelSize[l];
+        const size_t work = (size_t)n * n * n / (n >= 16 ? 16 : 1);
+        const int blocks = (int)((work + 255) / 256 < 148 * 8 ? (work + 255) / 256 : 148 * 8);
+        level_to_surface_kernel<<<blocks, 256, 0, st>>>(chain + vol.levelOff[l], ts.surf[l], n);
+        launches++;
+    }
+    return launches;
 }
 
 int launch_finish_mips(cudaStream_t st, const VolumeParams &vol, uint8_t *chain, int firstLevel) {

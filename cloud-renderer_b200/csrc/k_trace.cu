@@ -152,8 +152,10 @@ __device__ __forceinline__ bool sun_fragment(const TraceParams &tp, const ViewPa
     return true;
 }
 
+// kTex = false: explicit filtering (CRN_SAMPLER_EXPLICIT);  kTex = true: texture units (CRN_SAMPLER_TEXTURE)
+template <bool kTex>
 __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ TraceArgs a, const __grid_constant__ ViewParams cam,
-                                                    const __grid_constant__ TraceParams tp) {
+                                                    const __grid_constant__ TraceParams tp, const __grid_constant__ TexSet ts) {
     const int tile = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tx = tile % a.tilesX, ty = tile / a.tilesX;
@@ -186,6 +188,7 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
     const uint32_t off = cnt ? a.tileOff[tile] : 0;
     const float cutoff = tp.p.transmittanceCutoff;
     const int D = a.vol.dim;
+    (void)D;
     const int nzDim = tp.noiseDim;
     const float invAdjust = 1.0f / tp.p.adjustSize;
     const float noiseSpan = (float)(tp.p.maxNoiseSteps - tp.p.minNoiseSteps);
@@ -246,7 +249,13 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
                         float ng = 0.0f, na = 0.0f, freq = 1.0f, pers = 1.0f;
                         for (int o = 0; o < tp.p.numOctaves; o++) {     // noise3D, :103-120
                             const float offs = o < 3 ? tp.octaveOffsets[o] : 0.0f;
-                            const float2 s = sample_noise(a.noise, nzDim, (tx + offs) * freq, (tyy + offs) * freq, (tz + offs) * freq);
+                            float2 s;
+                            if constexpr (kTex) {
+                                const float4 t = tex3D<float4>(ts.noise, (tx + offs) * freq, (tyy + offs) * freq, (tz + offs) * freq);
+                                s = make_float2(t.y, t.w);
+                            } else {
+                                s = sample_noise(a.noise, nzDim, (tx + offs) * freq, (tyy + offs) * freq, (tz + offs) * freq);
+                            }
                             ng = fmaf(pers, s.x, ng);
                             na = fmaf(pers, s.y, na);
                             freq *= tp.p.freqStep;
@@ -280,12 +289,26 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
                 dx *= il; dy *= il; dz *= il;
                 float indirect = 0.0f;
                 if (shade) {
-                    for (int i = 0; i < tp.nSteps; i++) {
-                        const ConeStep st = tp.steps[i];
-                        const float sx = fmaf(st.height, dx, vx), sy = fmaf(st.height, dy, vy), sz = fmaf(st.height, dz, vz);
-                        float s = sample_level(a, st.level0, sx, sy, sz);
-                        if (st.frac != 0.0f) s = lerpf(s, sample_level(a, st.level0 + 1, sx, sy, sz), st.frac);
-                        indirect = fmaf(s, st.weight, indirect);
+                    if constexpr (kTex) {
+                        // normalized texture coordinates are the same on every level: voxel position / D
+                        const float invD = 1.0f / (float)D;
+                        const float nx = vx * invD, ny = vy * invD, nz = vz * invD;
+                        const float ex = dx * invD, ey = dy * invD, ez = dz * invD;
+                        for (int i = 0; i < tp.nSteps; i++) {
+                            const ConeStep st = tp.steps[i];
+                            const float sx = fmaf(st.height, ex, nx), sy = fmaf(st.height, ey, ny), sz = fmaf(st.height, ez, nz);
+                            float s = tex3D<float>(ts.tex[st.level0], sx, sy, sz);
+                            if (st.frac != 0.0f) s = lerpf(s, tex3D<float>(ts.tex[st.level0 + 1], sx, sy, sz), st.frac);
+                            indirect = fmaf(s, st.weight, indirect);
+                        }
+                    } else {
+                        for (int i = 0; i < tp.nSteps; i++) {
+                            const ConeStep st = tp.steps[i];
+                            const float sx = fmaf(st.height, dx, vx), sy = fmaf(st.height, dy, vy), sz = fmaf(st.height, dz, vz);
+                            float s = sample_level(a, st.level0, sx, sy, sz);
+                            if (st.frac != 0.0f) s = lerpf(s, sample_level(a, st.level0 + 1, sx, sy, sz), st.frac);
+                            indirect = fmaf(s, st.weight, indirect);
+                        }
                     }
                 }
                 if (tp.stats && shade) nCone += tp.nSteps;
@@ -341,7 +364,7 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
 
 int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol, const TraceParams &tp,
                  const BoardRec *recs, const Bins &b, const uint32_t *bits, const uint8_t *chain,
-                 const int8_t *noise, void *image, int format, unsigned long long *stats) {
+                 const int8_t *noise, const TexSet *ts, void *image, int format, unsigned long long *stats) {
     TraceArgs a;
     a.vol = vol;
     a.recs = recs;
@@ -354,7 +377,9 @@ int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol
     a.volScale[0] = fd / (vol.xB[1] - vol.xB[0]);
     a.volScale[1] = fd / (vol.yB[1] - vol.yB[0]);
     a.volScale[2] = fd / (vol.zB[1] - vol.zB[0]);
-    trace_kernel<<<b.tilesX * b.tilesY, 256, 0, st>>>(a, cam, tp);
+    TexSet none{};
+    if (ts && ts->enabled && tp.p.sampler == CRN_SAMPLER_TEXTURE) trace_kernel<true><<<b.tilesX * b.tilesY, 256, 0, st>>>(a, cam, tp, *ts);
+    else trace_kernel<false><<<b.tilesX * b.tilesY, 256, 0, st>>>(a, cam, tp, none);
     return 1;
 }
 

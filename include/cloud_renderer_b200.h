@@ -44,6 +44,10 @@ extern "C" {
 #define CRN_IMAGE_RGBA8    0   /* what the reference's window framebuffer holds */
 #define CRN_IMAGE_RGBA32F  1   /* un-quantised accumulator, for parity measurement */
 
+/* how crn_cone_trace filters the volume chain and the noise texture */
+#define CRN_SAMPLER_EXPLICIT 0  /* in-kernel trilinear / mip-linear in full float precision     */
+#define CRN_SAMPLER_TEXTURE  1  /* B200 texture units (8-bit filter weights, like any GL GPU)   */
+
 /* volume texel formats. R8 is the shipped reference format (src/CloudVolume.cpp:18). */
 #define CRN_VOLUME_R8      0
 #define CRN_VOLUME_R32F    1   /* mip chain only: same box filter without re-quantisation */
@@ -124,6 +128,7 @@ typedef struct crn_trace_params {
                                        the transmittance of everything in front of the
                                        next billboard is below this. 0 = shade every
                                        fragment (reference behaviour).                */
+    int32_t sampler;                /* CRN_SAMPLER_*                                   */
 } crn_trace_params;
 
 /* Counters of one crn_cone_trace call (read back on demand). */
@@ -233,6 +238,11 @@ int crn_set_timing(crn_ctx *ctx, int32_t enable);
 int crn_get_timings(crn_ctx *ctx, crn_timings *out);
 /* number of kernels this ctx has launched since creation */
 int crn_get_launch_count(crn_ctx *ctx, uint64_t *count);
+
+/* Measures one hardware ceiling with a resident synthetic kernel; result in giga lane-operations
+ * per second.  which: 0 tex3D trilinear RGBA8 32^3, 1 tex3D trilinear R8 256^3, 2 LDG.32 L1-hit,
+ * 3 global atomicOr (RED) on a 2 MB set, 4 shared-memory atomicOr, 5 FFMA issue. */
+int crn_microbench(int device, int32_t which, double *giga_ops_per_s);
 
 /* library identification: "cloud-renderer_b200 <version> sm_100a" */
 const char *crn_version(void);

@@ -17,17 +17,15 @@ _scene_cls = None
 
 
 def build(force=False):
-    src = os.path.join(_HERE, "oracle.cpp")
-    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(src) > os.path.getmtime(LIB_PATH):
-        subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s", "liboracle.so"], stdout=subprocess.DEVNULL)
+    """(re)builds liboracle.so through the Makefile, which knows the header dependency"""
+    subprocess.check_call(["make", "-C", _HERE] + (["-B"] if force else []) + ["-s", "liboracle.so"], stdout=subprocess.DEVNULL)
     return LIB_PATH
 
 
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            build()
+        build()
         _lib = C.CDLL(LIB_PATH)
         _lib.orc_board_distance.restype = C.c_float
     return _lib
