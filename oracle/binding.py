@@ -178,3 +178,10 @@ def second_voxelize_indices(vol, world_pos):
     out = (C.c_int32 * 27)()
     lib().orc_second_voxelize_indices(C.byref(vol), (C.c_float * 3)(*world_pos), out)
     return np.array(out[:], dtype=np.int32).reshape(9, 3)
+
+
+def cone_lods(tp):
+    n = tp.vctSteps
+    lods, hs = (C.c_float * n)(), (C.c_float * n)()
+    lib().orc_cone_lods(C.byref(tp), lods, hs)
+    return np.array(lods[:], dtype=np.float32), np.array(hs[:], dtype=np.float32)

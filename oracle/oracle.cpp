@@ -762,6 +762,19 @@ void orc_cone_trace(const orc_scene *sc, const uint8_t *chain_bytes, float *imag
     if (stats) { stats->fragments = nfrag; stats->coneSamples = ncone; stats->noiseSamples = nnoise; stats->rectPixels = nrect; }
 }
 
+/* The LOD textureLod() is called with at every traceCone step (res/conetrace_frag.glsl:70-76);
+ * identical for every fragment.  lods[vctSteps], heights[vctSteps]. */
+void orc_cone_lods(const crn_trace_params *tp, float *lods, float *heights) {
+    float coneHeight = tp->vctConeInitialHeight;
+    float tanHalf = tanf(tp->vctConeAngle / 2.0f);
+    for (int i = 1; i <= tp->vctSteps; i++) {
+        float coneRadius = coneHeight * tanHalf;
+        lods[i - 1] = log2f(fmaxf(1.0f, 2.0f * coneRadius)) + tp->vctLodOffset;
+        heights[i - 1] = coneHeight;
+        coneHeight += coneRadius;
+    }
+}
+
 /* One fragment of conetrace_frag.glsl at an explicit (fragPos, fragTex, center, radius):
  * the probe tests/test_oracle_vs_ref_glsl.py compares against the compiled reference
  * shader.  Returns 0 on discard. */

@@ -44,3 +44,205 @@ def test_image_psnr(name, sampler, pkg, scenes, orc, renderer):
     d = np.abs(u8.astype(np.int32) - ref_u8.astype(np.int32))
     print(f"{name}/{sampler}: RGBA8 max diff {d.max()} LSB, {100.0 * (d > 0).mean():.3f}% of channels differ")
     assert d.max() <= (2 if sampler == "explicit" else 6)
+
+
+def _expected_bins(rects, order, W, H, tile=16):
+    tx, ty = (W + tile - 1) // tile, (H + tile - 1) // tile
+    lists = [[] for _ in range(tx * ty)]
+    for b in order:
+        i0, i1, j0, j1 = rects[b]
+        if i1 < i0 or j1 < j0:
+            continue
+        for t_y in range(j0 // tile, j1 // tile + 1):
+            for t_x in range(i0 // tile, i1 // tile + 1):
+                lists[t_y * tx + t_x].append(b)
+    return tx, ty, lists
+
+
+@pytest.mark.parametrize("name", ["tiny", "small", "C1"])
+def test_sort_order_and_bins_exact(name, pkg, scenes, orc, renderer):
+    """billboard order = CloudVolume::sortBoards's (far -> near); bins = every tile the quad's
+    window rectangle touches, in pass order (camera: front to back)."""
+    s = scenes.make_scene(name)                      # UNSORTED arrays: the device sort does the work
+    renderer.set_scene(s)
+    renderer.voxelize()
+    renderer.cone_trace()
+    n = s.n_boards
+    d = orc.board_distances(s.board_pos, s.vol.position, s.cam.position)
+    assert len(np.unique(d)) == n
+    draw = renderer.read_sorted_order(n)
+    assert np.array_equal(draw, np.argsort(-d, kind="stable")), "draw order differs from sortBoards"
+    sp, ss = orc.sort_boards(s.board_pos, s.board_scale, s.vol.position, s.cam.position)
+    assert np.array_equal(s.board_pos[draw], sp) and np.array_equal(s.board_scale[draw], ss)
+    # camera bins: exact ordered lists, front to back
+    rc = orc.board_rects(s, 1)
+    tx, ty, exp = _expected_bins(rc, draw[::-1], s.width, s.height)
+    bins = renderer.read_bins(1)
+    assert (bins["tiles_x"], bins["tiles_y"], bins["tile_w"]) == (tx, ty, 16)
+    assert np.array_equal(bins["counts"], [len(l) for l in exp])
+    assert np.array_equal(bins["entries"], np.concatenate([np.array(l, dtype=np.int32) for l in exp if l] or [np.zeros(0, np.int32)]))
+    # light bins: same membership (their internal order is the sun-depth pruning order)
+    rl = orc.board_rects(s, 0)
+    tx, ty, exp = _expected_bins(rl, range(n), s.width, s.height)
+    bins = renderer.read_bins(0)
+    assert np.array_equal(bins["counts"], [len(l) for l in exp])
+    o = 0
+    for l in exp:
+        assert sorted(bins["entries"][o:o + len(l)]) == sorted(l)
+        o += len(l)
+
+
+def _variant(scenes, which):
+    s = scenes.make_scene("small")
+    if which == "fluffy":
+        s.vol.fluffiness = 1.35
+    elif which == "moved_anisotropic":
+        s.vol.position[:] = (3.0, -2.0, 7.5)
+        s.vol.xBounds[:], s.vol.yBounds[:], s.vol.zBounds[:] = (-6.0, 4.0), (-3.0, 5.0), (-5.0, 5.5)
+        s.eye, s.look_at = (-20.0, 3.0, 1.0), (3.0, -2.0, 7.5)
+        from cloud_renderer_b200 import camera_update
+        s.cam = camera_update(s.width, s.height, s.eye, s.look_at)
+    elif which == "sun_low":
+        s.sun.position[:] = (60.0, 1.0, 14.0)
+    elif which == "offscreen":
+        s.board_pos[:, 1] += 7.0                     # half the cloud leaves the volume and the top of the screen
+    elif which == "params":
+        s.tp.vctSteps, s.tp.vctConeAngle, s.tp.vctConeInitialHeight, s.tp.vctDownScaling = 22, 0.76, 0.64, 1.52
+        s.tp.freqStep, s.tp.persStep, s.tp.numOctaves, s.tp.vctLodOffset = 1.475, 0.75, 3, 0.4
+        s.tp.runTime, s.tp.windVel[1] = 12.5, 0.02
+    elif which == "no_noise":
+        s.tp.doNoiseSample = 0
+    elif which == "no_cone":
+        s.tp.doConeTrace = 0
+    elif which == "show_quad":
+        s.tp.showQuad = 1
+    elif which == "no_sun_disc":
+        s.tp.drawSun = 0
+    elif which == "sun_in_view":
+        s.sun.position[:] = (40.0, 6.0, -4.0)        # the sun disc is on screen, behind the cloud
+    elif which == "two_levels":
+        s.vol.levels = 2
+    elif which == "empty":
+        s.board_pos, s.board_scale = s.board_pos[:0].copy(), s.board_scale[:0].copy()
+    return s
+
+
+VARIANTS = ["fluffy", "moved_anisotropic", "sun_low", "offscreen", "params", "no_noise", "no_cone", "show_quad", "no_sun_disc",
+            "sun_in_view", "two_levels", "empty"]
+
+
+@pytest.mark.parametrize("which", VARIANTS)
+def test_edge_cases(which, pkg, scenes, orc, renderer):
+    s = _variant(scenes, which)
+    if s.n_boards:
+        steady_state(s, orc)
+    renderer.keep_position_map(True)
+    renderer.set_scene(s)
+    renderer.voxelize()
+    ref_posmap, _, ref_l0 = orc.voxelize(s)
+    assert np.array_equal(renderer.read_position_map().view(np.uint32), ref_posmap.view(np.uint32))
+    ref_chain = orc.mips(ref_l0, s.vol.levels)
+    assert np.array_equal(renderer.read_chain(), ref_chain)
+    renderer.keep_position_map(False)
+    ref, _, st = orc.cone_trace(s, ref_chain, want_u8=False)
+    for sampler, bar in ((pkg.SAMPLER_EXPLICIT, 90.0), (pkg.SAMPLER_TEXTURE, 45.0)):
+        s.tp.sampler = sampler
+        renderer.set_trace_params(s.tp)
+        img = renderer.cone_trace(fmt=pkg.IMAGE_RGBA32F)
+        p = psnr(img, ref)
+        print(f"{which}/sampler{sampler}: PSNR {p:.1f} dB, max err {np.abs(img - ref).max():.2e}, {st.fragments} fragments")
+        assert p >= bar
+
+
+def test_early_termination_cutoff(pkg, scenes, orc, renderer):
+    """the only approximation the trace makes: fragments behind transmittance < cutoff are skipped"""
+    s = steady_state(scenes.make_scene("C1"), orc)
+    renderer.set_scene(s)
+    renderer.voxelize()
+    _, _, l0 = orc.voxelize(s, want_posmap=False)
+    ref, _, st = orc.cone_trace(s, orc.mips(l0, s.vol.levels), want_u8=False)
+    renderer.set_stats(True)
+    prev = None
+    for cutoff in (0.0, 1.0 / 1024, 1.0 / 64):
+        s.tp.transmittanceCutoff = cutoff
+        renderer.set_trace_params(s.tp)
+        img = renderer.cone_trace(fmt=pkg.IMAGE_RGBA32F)
+        frags = renderer.trace_stats().fragments
+        p = psnr(img, ref)
+        print(f"cutoff {cutoff:.5f}: {frags} fragments shaded (oracle {st.fragments}), PSNR {p:.1f} dB, max err {np.abs(img - ref).max():.2e}")
+        if cutoff == 0.0:
+            assert abs(int(frags) - int(st.fragments)) <= max(4, st.fragments // 100000)
+        if cutoff <= 1.0 / 1024:
+            assert p >= 45.0
+        assert prev is None or frags <= prev
+        prev = frags
+    renderer.set_stats(False)
+
+
+def test_reference_8bit_framebuffer_mode(pkg, scenes, orc, renderer):
+    """the reference blends into an 8-bit window framebuffer; our float accumulation stays >= 45 dB from it"""
+    s = steady_state(scenes.make_scene("C1"), orc)
+    renderer.set_scene(s)
+    renderer.voxelize()
+    img = renderer.cone_trace(fmt=pkg.IMAGE_RGBA32F)
+    _, _, l0 = orc.voxelize(s, want_posmap=False)
+    ref8, _, _ = orc.cone_trace(s, orc.mips(l0, s.vol.levels), quantize_fb8=True, want_u8=False)
+    p = psnr(img, ref8)
+    print(f"vs per-blend 8-bit quantised oracle: PSNR {p:.1f} dB, max err {np.abs(img - ref8).max():.2e}")
+    assert p >= 45.0
+
+
+def test_sharding_hooks_do_not_change_results(pkg, scenes, orc, renderer):
+    """row bands and Z-slabs executed one after the other on one GPU reproduce the unsharded frame bit for bit"""
+    s = steady_state(scenes.make_scene("small"), orc)
+    s.tp.sampler = pkg.SAMPLER_TEXTURE
+    renderer.set_scene(s)
+    renderer.voxelize()
+    whole = renderer.cone_trace(fmt=pkg.IMAGE_RGBA32F)
+    chain = renderer.read_chain()
+    from cloud_renderer_b200 import sharding as sh
+    r2 = pkg.Renderer(0)
+    r2.set_scene(s)
+    D, L = s.vol.dimension, s.vol.levels
+    for rank in range(4):                               # 64 slices -> 4 slabs of 16
+        r2.set_z_slab(*sh.z_slab(D, rank, 4))
+        r2.voxelize()
+    if L > sh.slab_local_levels(L):
+        r2.finish_mips(sh.slab_local_levels(L))
+    assert np.array_equal(r2.read_chain(), chain), "slab-by-slab chain differs"
+    asm = np.zeros_like(whole)
+    for rank in range(3):
+        a, b = sh.row_range(s.height, rank, 3)
+        r2.set_row_range(a, b)
+        band = np.zeros_like(whole)
+        r2.cone_trace(band, pkg.IMAGE_RGBA32F)
+        assert not band[:a].any() and not band[b:].any(), "rows outside the band were written"
+        asm[a:b] = band[a:b]
+    assert np.array_equal(asm.view(np.uint32), whole.view(np.uint32)), "row-band image differs"
+    r2.close()
+
+
+def test_c3_crop_against_oracle(pkg, scenes, orc, renderer):
+    """full-size headline config: voxel occupancy of the whole 256^3 volume exact, and the image
+    checked on a spread of rows the oracle can finish in seconds"""
+    s = scenes.make_scene("C3", frame=1)
+    s.tp.sampler = pkg.SAMPLER_TEXTURE
+    s.tp.transmittanceCutoff = 1.0 / 1024
+    renderer.set_scene(s)
+    renderer.voxelize()
+    img = renderer.cone_trace(fmt=pkg.IMAGE_RGBA32F)
+    order = renderer.read_sorted_order(s.n_boards)
+    _, _, l0 = orc.voxelize(s, want_posmap=False)
+    chain = orc.mips(l0, s.vol.levels)
+    assert np.array_equal(renderer.read_chain(), chain), "C3 occupancy / chain differ"
+    assert renderer.count_active_voxels() == int((l0 > 0).sum())
+    s.board_pos, s.board_scale = s.board_pos[order].copy(), s.board_scale[order].copy()     # draw order, as sortBoards leaves it
+    rows = [540, 900, 1080, 1260, 1500]
+    errs = []
+    for r in rows:
+        ref, _, _ = orc.cone_trace(s, chain, rows=(r, r + 1), want_u8=False)
+        errs.append(img[r] - ref[r])
+    e = np.stack(errs)
+    p = 10.0 * np.log10(1.0 / max(float(np.mean(e.astype(np.float64) ** 2)), 1e-30))
+    print(f"C3 rows {rows}: PSNR {p:.1f} dB, max per-channel error {np.abs(e).max():.2e}")
+    assert p >= 45.0
