@@ -185,3 +185,113 @@ def cone_lods(tp):
     lods, hs = (C.c_float * n)(), (C.c_float * n)()
     lib().orc_cone_lods(C.byref(tp), lods, hs)
     return np.array(lods[:], dtype=np.float32), np.array(hs[:], dtype=np.float32)
+
+
+def list_fragments(scene, which):
+    """(n,8) float32: i, j, board, fragPos xyz, fragTex xy — the fragments of the billboard draw, in draw order"""
+    s = _scene_struct(scene)
+    lib().orc_list_fragments.restype = C.c_int64
+    n = lib().orc_list_fragments(C.byref(s), which, C.c_int64(0), None)
+    out = np.zeros((n, 8), dtype=np.float32)
+    lib().orc_list_fragments(C.byref(s), which, C.c_int64(n), C.c_void_p(out.ctypes.data))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# oracle/_ref/libref_glsl.so: the reference's own shaders compiled as C++ (oracle/ref_glsl/build_ref.sh)
+# ------------------------------------------------------------------------------------------------
+REF_LIB_PATH = os.path.join(_HERE, "_ref", "libref_glsl.so")
+_ref = None
+
+
+class RefConetraceUniforms(C.Structure):
+    _fields_ = [("V", C.c_float * 16), ("lightPos", C.c_float * 3), ("showQuad", C.c_int), ("voxelDim", C.c_int),
+                ("xBounds", C.c_float * 2), ("yBounds", C.c_float * 2), ("zBounds", C.c_float * 2),
+                ("doConeTrace", C.c_int), ("vctSteps", C.c_int), ("vctConeAngle", C.c_float), ("vctConeInitialHeight", C.c_float),
+                ("vctLodOffset", C.c_float), ("vctDownScaling", C.c_float),
+                ("doNoise", C.c_int), ("octaveOffsets", C.c_float * 3), ("stepSize", C.c_float), ("noiseOpacity", C.c_float),
+                ("numOctaves", C.c_int), ("freqStep", C.c_float), ("persStep", C.c_float), ("adjustSize", C.c_float),
+                ("minNoiseSteps", C.c_int), ("maxNoiseSteps", C.c_int), ("minNoiseColor", C.c_float), ("noiseColorScale", C.c_float)]
+
+
+def ref_available():
+    return os.path.exists(REF_LIB_PATH)
+
+
+def ref_lib():
+    global _ref
+    if _ref is None:
+        lib()                                       # liboracle.so first: libref_glsl.so links against it
+        _ref = C.CDLL(REF_LIB_PATH)
+    return _ref
+
+
+def _f(*v):
+    return (C.c_float * len(v))(*[np.float32(x) for x in v])
+
+
+def ref_conetrace_uniforms(scene):
+    """the uniform uploads of ConeTraceShader::coneTrace / bindVolume (src/Shaders/ConeTraceShader.cpp:26-69,84-93)"""
+    u = RefConetraceUniforms()
+    tp, vol = scene.tp, scene.vol
+    u.V[:] = scene.cam.V[:]
+    u.lightPos[:] = scene.sun.position[:]
+    u.showQuad, u.voxelDim = tp.showQuad, vol.dimension
+    f = np.float32
+    u.xBounds[:] = [f(vol.position[0]) + f(vol.xBounds[k]) for k in range(2)]
+    u.yBounds[:] = [f(vol.position[1]) + f(vol.yBounds[k]) for k in range(2)]
+    u.zBounds[:] = [f(vol.position[2]) + f(vol.zBounds[k]) for k in range(2)]
+    u.doConeTrace, u.vctSteps, u.vctConeAngle, u.vctConeInitialHeight = tp.doConeTrace, tp.vctSteps, tp.vctConeAngle, tp.vctConeInitialHeight
+    u.vctLodOffset, u.vctDownScaling = tp.vctLodOffset, tp.vctDownScaling
+    u.doNoise = tp.doNoiseSample
+    u.octaveOffsets[:] = [f(tp.windVel[k]) * f(tp.runTime) for k in range(3)]
+    u.stepSize, u.noiseOpacity, u.numOctaves, u.freqStep, u.persStep, u.adjustSize = tp.stepSize, tp.noiseOpacity, tp.numOctaves, tp.freqStep, tp.persStep, tp.adjustSize
+    u.minNoiseSteps, u.maxNoiseSteps, u.minNoiseColor, u.noiseColorScale = tp.minNoiseSteps, tp.maxNoiseSteps, tp.minNoiseColor, tp.noiseColorScale
+    return u
+
+
+def ref_conetrace_fragment(scene, uniforms, chain, frag_pos, frag_nor, frag_tex, center, radius):
+    col = (C.c_float * 4)()
+    ch = np.ascontiguousarray(chain, dtype=np.uint8)
+    nz = np.ascontiguousarray(scene.noise, dtype=np.int8)
+    ok = ref_lib().ref_conetrace_fragment(C.byref(uniforms), C.c_void_p(ch.ctypes.data), scene.vol.levels, C.c_void_p(nz.ctypes.data),
+                                          round((nz.size // 4) ** (1 / 3)), _f(*frag_pos), _f(*frag_nor), _f(*frag_tex), _f(*center),
+                                          C.c_float(radius), col)
+    return bool(ok), np.array(col[:], dtype=np.float32)
+
+
+def ref_first_voxelize_fragment(frag_pos, frag_nor, center, radius, near_plane, clip):
+    col, d = (C.c_float * 4)(), C.c_float()
+    ok = ref_lib().ref_first_voxelize_fragment(_f(*frag_pos), _f(*frag_nor), _f(*center), C.c_float(radius), _f(*near_plane), C.c_float(clip), col, C.byref(d))
+    return bool(ok), np.array(col[:], dtype=np.float32), d.value
+
+
+def ref_second_voxelize_fragment(vol, texel):
+    f = np.float32
+    xb = [f(vol.position[0]) + f(vol.xBounds[k]) for k in range(2)]
+    yb = [f(vol.position[1]) + f(vol.yBounds[k]) for k in range(2)]
+    zb = [f(vol.position[2]) + f(vol.zBounds[k]) for k in range(2)]
+    d = f(vol.dimension)
+    step = min(f(f(vol.xBounds[1]) - f(vol.xBounds[0])) / d, f(f(vol.yBounds[1]) - f(vol.yBounds[0])) / d, f(f(vol.zBounds[1]) - f(vol.zBounds[0])) / d)
+    idx, val = (C.c_int * 27)(), (C.c_float * 9)()
+    n = ref_lib().ref_second_voxelize_fragment(_f(*texel), vol.dimension, _f(*xb), _f(*yb), _f(*zb), C.c_float(step), idx, val)
+    return n, np.array(idx[:], dtype=np.int32).reshape(9, 3), np.array(val[:], dtype=np.float32)
+
+
+def ref_sun_fragment(sun, frag_pos):
+    col = (C.c_float * 4)()
+    ok = ref_lib().ref_sun_fragment(_f(*frag_pos), _f(*sun.position), _f(*sun.innerColor), _f(*sun.outerColor), C.c_float(sun.innerRadius),
+                                    C.c_float(sun.outerRadius), col)
+    return bool(ok), np.array(col[:], dtype=np.float32)
+
+
+def ref_billboard_vertex(P, V, volume_position, vert, board_position, board_scale):
+    """billboard_vert_instanced.glsl for one vertex; Vi = transpose(V with zeroed translation) as the drivers build it"""
+    Vm = np.array(V[:], dtype=np.float32).reshape(4, 4).copy()      # [col][row]
+    Vm[3, :3] = 0.0
+    Vi = Vm.T.copy()
+    glpos, fpos, fnor, ftex, cen, sc = (C.c_float * 4)(), (C.c_float * 3)(), (C.c_float * 3)(), (C.c_float * 2)(), (C.c_float * 3)(), C.c_float()
+    ref_lib().ref_billboard_vertex(_f(*P[:]), _f(*V[:]), _f(*Vi.ravel()), _f(*volume_position), _f(vert[0], vert[1], 0.0), _f(0.0, 0.0, 1.0),
+                                   _f(*board_position), C.c_float(board_scale), glpos, fpos, fnor, ftex, cen, C.byref(sc))
+    return dict(gl_Position=np.array(glpos[:], np.float32), fragPos=np.array(fpos[:], np.float32), fragNor=np.array(fnor[:], np.float32),
+                fragTex=np.array(ftex[:], np.float32), center=np.array(cen[:], np.float32), scale=sc.value)

@@ -15,9 +15,9 @@
  *       (res/first_voxelize.glsl, res/second_voxelize.glsl, res/conetrace_frag.glsl,
  *       res/sun_frag.glsl, res/billboard_vert*.glsl), read in place from /root/reference,
  *       as C++ through a small GLSL-vocabulary shim into oracle/_ref/, and
- *       tests/test_oracle_vs_ref_glsl.py + tests/golden/ compare this file's per-fragment
- *       arithmetic against them;
- *   (2) closed-form anchors (tests/test_oracle_closed_form.py).
+ *       tests/test_oracle_vs_ref_glsl_cpu.py (live) and tests/test_golden_cpu.py (committed
+ *       vectors, tests/golden/) compare this file's per-fragment arithmetic against them;
+ *   (2) closed-form anchors (tests/test_oracle_closed_form_cpu.py).
  * The fixed-function stages a GL driver supplies (rasterisation, depth test, texture
  * filtering, mip generation, blending) exist nowhere in /root/reference and are restated
  * here from the OpenGL 4.4 core specification; driver-defined choices are decreed once,
@@ -762,6 +762,18 @@ void orc_cone_trace(const orc_scene *sc, const uint8_t *chain_bytes, float *imag
     if (stats) { stats->fragments = nfrag; stats->coneSamples = ncone; stats->noiseSamples = nnoise; stats->rectPixels = nrect; }
 }
 
+/* The fixed-function texture units, exported for oracle/ref_glsl (the reference's compiled
+ * shaders call back into these; GL 4.4 §8.14 restated above). */
+void orc_sample_volume(const uint8_t *chain_bytes, int32_t dim, int32_t levels, float u, float v, float w, float lod, float out[4]) {
+    Chain c = make_chain(chain_bytes, dim, levels);
+    float r = texture_lod(c, {u, v, w}, lod);
+    out[0] = r; out[1] = 0.0f; out[2] = 0.0f; out[3] = 1.0f;              /* GL_R8: (r,0,0,1) */
+}
+void orc_sample_noise(const int8_t *rgba, int32_t dim, float u, float v, float w, float out[4]) {
+    Noise nz = {rgba, dim};
+    sample_noise(nz, {u, v, w}, out);
+}
+
 /* The LOD textureLod() is called with at every traceCone step (res/conetrace_frag.glsl:70-76);
  * identical for every fragment.  lods[vctSteps], heights[vctSteps]. */
 void orc_cone_lods(const crn_trace_params *tp, float *lods, float *heights) {
@@ -826,6 +838,37 @@ void orc_second_voxelize_indices(const crn_volume_desc *vol, const float worldPo
         bool ok = f.x > -1.0f && f.x < (float)D && f.y > -1.0f && f.y < (float)D && f.z > -1.0f && f.z < (float)D;
         out[3 * s + 0] = ok ? (int)f.x : -1; out[3 * s + 1] = ok ? (int)f.y : -1; out[3 * s + 2] = ok ? (int)f.z : -1;
     }
+}
+
+/* Enumerates, in draw order, the fragments the rasteriser hands to the fragment stage for the
+ * billboard draw of pass `which` (0: light camera / first_voxelize, 1: user camera / conetrace):
+ * every pixel centre inside each quad, with the interpolated attributes.  Lets a test run the
+ * reference's compiled shader on exactly the fragments the oracle shades.  Returns the count
+ * (fills at most `cap`).  rec: {i, j, board, fragPos[3], fragTex[2]} as 8 floats per fragment. */
+int64_t orc_list_fragments(const orc_scene *sc, int32_t which, int64_t cap, float *rec) {
+    crn_sun_derived sd;
+    ViewBasis vb;
+    if (which == 0) { orc_sun_update(&sc->vol, &sc->sun, &sd); vb = make_basis(sd.P, sd.V); }
+    else vb = make_basis(sc->cam.P, sc->cam.V);
+    const int W = sc->width, H = sc->height;
+    int64_t n = 0;
+    for (int b = 0; b < sc->n_boards; b++) {
+        QuadSetup q = quad_setup(vb, v3(sc->vol.position) + v3(sc->board_pos + 3 * b), board_radius(sc->vol, sc->board_scale[b]), W, H);
+        if (q.clipped) continue;
+        for (int j = q.j0; j <= q.j1; j++)
+            for (int i = q.i0; i <= q.i1; i++) {
+                float uu, vv;
+                vec3 fp = frag_pos(vb, q, i, j, W, H, &uu, &vv);
+                if (!(fabsf(uu) < q.scale && fabsf(vv) < q.scale)) continue;
+                if (n < cap) {
+                    float *r = rec + 8 * n;
+                    r[0] = (float)i; r[1] = (float)j; r[2] = (float)b; r[3] = fp.x; r[4] = fp.y; r[5] = fp.z;
+                    r[6] = (uu / q.scale + 1.0f) / 2.0f; r[7] = (vv / q.scale + 1.0f) / 2.0f;
+                }
+                n++;
+            }
+    }
+    return n;
 }
 
 /* Conservative window-space rectangle of one billboard quad as both passes rasterise it
