@@ -65,7 +65,18 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed")
     cmd = [nvcc] + host + ARCH + ["-shared", "-o", OUT] + objs
     subprocess.check_call(cmd)
+    build_example()
     return OUT
+
+
+def build_example():
+    """examples/frame.cpp: the reference's frame loop against include/cloud_renderer_b200.hpp"""
+    root = os.path.dirname(HERE)
+    exe = os.path.join(OBJ, "crn_frame")
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([gxx, "-O2", "-std=c++17", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "frame.cpp"),
+                           "-o", exe, OUT, "-Wl,-rpath," + HERE])
+    return exe
 
 
 if __name__ == "__main__":
