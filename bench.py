@@ -187,6 +187,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: cloud-renderer_b200 has no CPU path (use --impl reference for the CPU oracle)")
     torch.cuda.set_device(local)
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)                      # NCCL / libraries may print to stdout; the JSON line goes to the real one
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg = entry.import_package()
@@ -221,7 +223,7 @@ def main():
         from cloud_renderer_b200 import sharding as sh
         z0, z1 = sh.z_slab(D, rank, world)
         r.set_z_slab(z0, z1)
-        r.set_row_range(*sh.row_range(Ht, rank, world))
+        r.set_tile_row_interleave(rank, world)              # balanced: 16-row tile rows dealt round-robin
         r.voxelize()                                        # allocates bits + chain
         torch.cuda.synchronize()
         tens = sh.chain_tensors(torch, r, L, dev)
@@ -308,7 +310,7 @@ def main():
             "config": {
                 "workload": (f"{args.config}: {D}^3 R8 volume ({L} levels), {N} billboards ({frames[0].meta['radius_mode']} radii), {Wd}x{Ht}, "
                              f"animated (one new frame per step), sun shadow cones 16 steps, noise 4 octaves"),
-                "sharding": ("Z-slab voxelize+mips, one all-gather of the finished chain (NCCL), row-band trace" if slab_mode else
+                "sharding": ("Z-slab voxelize+mips, one all-gather of the finished chain (NCCL), tile-row-interleaved trace" if slab_mode else
                              "frames round-robin over ranks, volume replicated, no collective" if world > 1 else "single GPU"),
                 "transmittance_cutoff": args.cutoff, "sampler": args.sampler,
                 "l2": "none (back to back)" if args.no_flush else "256 MiB fill between steps, outside the per-step event pairs",
@@ -327,7 +329,7 @@ def main():
             orc = entry.import_oracle()
             orc.build()
             out["cpu_baseline"] = cpu_baseline(args.config, orc, sc)
-        print(json.dumps(out))
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
     r.close()
     if world > 1:
         dist.destroy_process_group()

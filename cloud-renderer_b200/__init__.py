@@ -64,6 +64,7 @@ EXPORTS = [
     "crn_create", "crn_destroy", "crn_last_error", "crn_sync", "crn_set_volume", "crn_set_billboards", "crn_set_sun",
     "crn_sun_update", "crn_set_camera", "crn_camera_update", "crn_set_window", "crn_set_trace_params",
     "crn_default_trace_params", "crn_set_noise", "crn_build_noise", "crn_voxelize", "crn_cone_trace", "crn_set_row_range",
+    "crn_set_tile_row_interleave",
     "crn_set_z_slab", "crn_volume_level_ptr", "crn_volume_bits_ptr", "crn_finish_mips", "crn_read_volume",
     "crn_count_active_voxels", "crn_keep_position_map", "crn_read_position_map", "crn_read_sorted_order", "crn_read_bins",
     "crn_get_trace_stats", "crn_set_stats", "crn_set_timing", "crn_get_timings", "crn_get_launch_count", "crn_version",
@@ -106,6 +107,7 @@ def load_library():
     lib.crn_cone_trace.argtypes = [vp, vp, i32, i32]
     lib.crn_set_row_range.argtypes = [vp, i32, i32]
     lib.crn_set_z_slab.argtypes = [vp, i32, i32]
+    lib.crn_set_tile_row_interleave.argtypes = [vp, i32, i32]
     lib.crn_volume_level_ptr.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(C.c_size_t)]
     lib.crn_volume_bits_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     lib.crn_finish_mips.argtypes = [vp, i32]
@@ -257,6 +259,9 @@ class Renderer:
     # ---- sharding hooks
     def set_row_range(self, r0, r1):
         self._ck(self.lib.crn_set_row_range(self.h, r0, r1))
+
+    def set_tile_row_interleave(self, index, count):
+        self._ck(self.lib.crn_set_tile_row_interleave(self.h, index, count))
 
     def set_z_slab(self, z0, z1):
         self._ck(self.lib.crn_set_z_slab(self.h, z0, z1))

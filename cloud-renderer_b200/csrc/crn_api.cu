@@ -134,6 +134,7 @@ struct crn_ctx {
     int nBoards = 0;
     int noiseDim = 0;
     int row0 = 0, row1 = 1 << 30;
+    int ilvIndex = 0, ilvCount = 1;
     int z0 = 0, z1 = -1;                 // -1: whole volume
     bool keepPosmap = false, statsOn = false, timingOn = false;
     bool voxelized = false, traced = false;
@@ -374,6 +375,7 @@ void build_trace_params(crn_ctx *c, const ViewParams &cam, TraceParams *tp) {
     tp->nSteps = c->tp.vctSteps;
     tp->noiseDim = c->noiseDim;
     tp->row0 = std::max(0, c->row0); tp->row1 = std::min(c->H, c->row1);
+    tp->ilvIndex = c->ilvIndex; tp->ilvCount = c->ilvCount;
     tp->active = (c->tp.doConeTrace || c->tp.doNoiseSample || c->tp.showQuad) ? 1 : 0;   // ConeTraceShader.cpp:16-18
     tp->stats = c->statsOn ? 1 : 0;
     // traceCone (res/conetrace_frag.glsl:64-79): per-step constants, float ops as written
@@ -704,9 +706,25 @@ int crn_cone_trace(crn_ctx *c, void *out, int32_t mem, int32_t format) {
     c->traced = true;
     const size_t texel = format == CRN_IMAGE_RGBA32F ? 16 : 4;
     const int r0 = std::max(0, c->row0), r1 = std::min(c->H, c->row1);
-    if (r1 > r0) {
-        const size_t offB = (size_t)r0 * c->W * texel, bytes = (size_t)(r1 - r0) * c->W * texel;
-        const cudaMemcpyKind kind = mem == CRN_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    const cudaMemcpyKind kind = mem == CRN_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    const size_t rowB = (size_t)c->W * texel;
+    if (c->ilvCount > 1) {
+        // only the tile rows this context owns: one strided 2-D copy (+ the partial last tile row)
+        const int tilesY = (c->H + kTile - 1) / kTile;
+        for (int ty = c->ilvIndex; ty < tilesY;) {
+            const int full = (c->H - ty * kTile) / kTile > 0 ? ((c->H / kTile - 1 - ty) / c->ilvCount + 1) : 0;   // owned tile rows of full height
+            if (full > 0) {
+                const size_t off = (size_t)ty * kTile * rowB, pitch = (size_t)c->ilvCount * kTile * rowB;
+                CRN_CUDA(c, cudaMemcpy2DAsync((char *)out + off, pitch, (char *)c->image.p + off, pitch, (size_t)kTile * rowB, full, kind, c->stream));
+                ty += full * c->ilvCount;
+            } else {
+                const size_t off = (size_t)ty * kTile * rowB;
+                CRN_CUDA(c, cudaMemcpyAsync((char *)out + off, (char *)c->image.p + off, (size_t)(c->H - ty * kTile) * rowB, kind, c->stream));
+                ty += c->ilvCount;
+            }
+        }
+    } else if (r1 > r0) {
+        const size_t offB = (size_t)r0 * rowB, bytes = (size_t)(r1 - r0) * rowB;
         CRN_CUDA(c, cudaMemcpyAsync((char *)out + offB, (char *)c->image.p + offB, bytes, kind, c->stream));
     }
     if (mem == CRN_MEM_HOST) CRN_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -716,6 +734,12 @@ int crn_cone_trace(crn_ctx *c, void *out, int32_t mem, int32_t format) {
 int crn_set_row_range(crn_ctx *c, int32_t row0, int32_t row1) {
     if (!c || row0 < 0 || row1 < row0) return fail(c, CRN_ERR_INVALID_ARG, "bad row range");
     c->row0 = row0; c->row1 = row1;
+    return CRN_OK;
+}
+
+int crn_set_tile_row_interleave(crn_ctx *c, int32_t index, int32_t count) {
+    if (!c || count < 1 || index < 0 || index >= count) return fail(c, CRN_ERR_INVALID_ARG, "bad interleave %d of %d", index, count);
+    c->ilvIndex = index; c->ilvCount = count;
     return CRN_OK;
 }
 

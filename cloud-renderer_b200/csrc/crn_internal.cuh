@@ -68,6 +68,7 @@ struct TraceParams {
     int32_t nSteps;
     int32_t noiseDim;
     int32_t row0, row1;
+    int32_t ilvIndex, ilvCount;       // tile-row interleave (image-space sharding)
     int32_t active;                   // doConeTrace || doNoiseSample || showQuad
     int32_t stats;
     ConeStep steps[kMaxConeSteps];

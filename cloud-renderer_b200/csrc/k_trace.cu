@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
     const int px = tx * kTile + (warp & 1) * 8 + (lane & 7);
     const int py = ty * kTile + (warp >> 1) * 4 + (lane >> 3);
     // rows outside [row0,row1) belong to another rank (image-space sharding)
+    if (tp.ilvCount > 1 && (ty % tp.ilvCount) != tp.ilvIndex) return;
     const bool valid = px < cam.W && py < cam.H && py >= tp.row0 && py < tp.row1;
     if (__all_sync(0xFFFFFFFFu, !valid)) return;
 

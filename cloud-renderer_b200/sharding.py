@@ -31,6 +31,13 @@ def row_range(height, rank, world, align=16):
     return min(t0 * align, height), min(t1 * align, height)
 
 
+def tile_rows_of_rank(height, rank, world, tile=16):
+    """load-balanced alternative to row_range: 16-pixel tile rows dealt round-robin (the cloud sits in the
+    middle of the frame, so contiguous bands would leave the outer ranks idle).  -> list of (row0,row1)"""
+    tiles = (height + tile - 1) // tile
+    return [(t * tile, min(height, (t + 1) * tile)) for t in range(rank, tiles, world)]
+
+
 def z_slab(dim, rank, world):
     """voxel slices [z0,z1) owned by `rank`; equal, SLAB_ALIGN-aligned slabs"""
     if dim % (world * SLAB_ALIGN):

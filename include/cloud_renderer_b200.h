@@ -206,6 +206,9 @@ int crn_cone_trace(crn_ctx *ctx, void *out, int32_t mem, int32_t format);
 /* ---- sharding hooks (multi-GPU; results are invariant to them) --------------------- */
 /* restrict crn_cone_trace to image rows [row0,row1); other rows of `out` are untouched */
 int crn_set_row_range(crn_ctx *ctx, int32_t row0, int32_t row1);
+/* load-balanced image-space sharding: this context traces only the 16-pixel tile rows ty with
+ * ty % count == index (count = 1 turns it off); combines with crn_set_row_range */
+int crn_set_tile_row_interleave(crn_ctx *ctx, int32_t index, int32_t count);
 /* restrict crn_voxelize to voxel slices z in [z0,z1): only those slices of every
  * slab-local level are produced (levels whose texel spans more than the slab are left
  * for crn_finish_mips after the exchange) */

@@ -268,7 +268,34 @@ def test_cpp_mirror_example_runs(pkg):
         n = int(p.stdout.split("Voxels in scene:")[1].split()[0])
         assert 1000 < n < 32 ** 3
         data = open(out, "rb").read()
-        assert data.startswith(b"P6\n1280 720\n255\n") and len(data) == 15 + 1280 * 720 * 3
-        img = np.frombuffer(data[15:], dtype=np.uint8).reshape(720, 1280, 3)
+        hdr = b"P6\n1280 720\n255\n"
+        assert data.startswith(hdr) and len(data) == len(hdr) + 1280 * 720 * 3
+        img = np.frombuffer(data[len(hdr):], dtype=np.uint8).reshape(720, 1280, 3)
         assert (img[0, 0] == [51, 77, 128]).all()                 # clear colour (0.2,0.3,0.5)
         assert img[300:420, 500:780].mean() > 140                  # the cloud sits in the middle of the frame
+
+
+def test_tile_row_interleave_is_result_invariant(pkg, scenes, orc, renderer):
+    s = steady_state(scenes.make_scene("small", size=(320, 200)), orc)     # 12.5 tile rows: partial last row
+    s.tp.sampler = pkg.SAMPLER_TEXTURE
+    renderer.set_scene(s)
+    renderer.voxelize()
+    whole = renderer.cone_trace(fmt=pkg.IMAGE_RGBA8)
+    from cloud_renderer_b200 import sharding as sh
+    r2 = pkg.Renderer(0)
+    r2.set_scene(s)
+    r2.voxelize()
+    asm = np.zeros_like(whole)
+    cover = np.zeros(s.height, dtype=np.int32)
+    for rank in range(3):
+        r2.set_tile_row_interleave(rank, 3)
+        part = np.full_like(whole, 7)
+        r2.cone_trace(part, pkg.IMAGE_RGBA8)
+        mine = np.zeros(s.height, dtype=bool)
+        for a, b in sh.tile_rows_of_rank(s.height, rank, 3):
+            mine[a:b] = True
+            cover[a:b] += 1
+        assert (part[~mine] == 7).all(), "rows of another rank were copied"
+        asm[mine] = part[mine]
+    assert (cover == 1).all() and np.array_equal(asm, whole)
+    r2.close()
