@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--config", default="C3")
     ap.add_argument("--cutoff", type=float, default=CUTOFF)
     ap.add_argument("--sampler", default="texture", choices=["texture", "explicit"])
+    ap.add_argument("--no-skip", action="store_true", help="fetch every cone sample (no empty-space skipping)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="back-to-back steps (no L2 flush between them)")
     return ap.parse_args()
@@ -204,6 +205,7 @@ def main():
     for f in frames:
         f.tp.transmittanceCutoff = args.cutoff
         f.tp.sampler = pkg.SAMPLER_TEXTURE if args.sampler == "texture" else pkg.SAMPLER_EXPLICIT
+        f.tp.skipEmptySpace = 0 if args.no_skip else 1
     r.set_scene(frames[0])
 
     # resident inputs (value leg) and pinned host inputs (e2e leg)
@@ -292,6 +294,7 @@ def main():
     st = r.trace_stats()
     r.set_stats(False)
     frag, cone, noise, bins = st.fragments, st.coneSamples, st.noiseSamples, st.binEntries
+    cone_skipped = st.coneSamplesSkipped
 
     if rank == 0:
         job_frames = K if slab_mode else world * K          # C4 shards ONE frame per step over all ranks
@@ -312,14 +315,15 @@ def main():
                              f"animated (one new frame per step), sun shadow cones 16 steps, noise 4 octaves"),
                 "sharding": ("Z-slab voxelize+mips, one all-gather of the finished chain (NCCL), tile-row-interleaved trace" if slab_mode else
                              "frames round-robin over ranks, volume replicated, no collective" if world > 1 else "single GPU"),
-                "transmittance_cutoff": args.cutoff, "sampler": args.sampler,
+                "transmittance_cutoff": args.cutoff, "sampler": args.sampler, "skip_empty_space": not args.no_skip,
                 "l2": "none (back to back)" if args.no_flush else "256 MiB fill between steps, outside the per-step event pairs",
             },
             "clocks": clocks,
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": N * 16, "d2h_bytes_per_step": Wd * Ht * 4},
             "gpu_launches": launches,
             "stages_ms": stage, "voxelize_mip_ms": stage["lightBinMs"] + stage["voxelizeMs"] + stage["mipMs"],
-            "per_frame": {"fragments_shaded": frag, "cone_samples": cone, "noise_samples": noise, "bin_entries": bins,
+            "per_frame": {"fragments_shaded": frag, "cone_samples": cone, "cone_samples_skipped_as_empty": cone_skipped,
+                          "noise_samples": noise, "bin_entries": bins,
                           "cone_samples_per_s": cone / (trace_ms * 1e-3), "filtered_samples_per_s": (cone + noise) / (trace_ms * 1e-3)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "kernel": "trace_kernel", "peak_source": peak_src,

@@ -48,11 +48,11 @@ class TraceParams(C.Structure):
                 ("vctDownScaling", f32),
                 ("showQuad", i32), ("doConeTrace", i32), ("doNoiseSample", i32),
                 ("runTime", f32),
-                ("clearColor", f32 * 4), ("drawSun", i32), ("transmittanceCutoff", f32), ("sampler", i32)]
+                ("clearColor", f32 * 4), ("drawSun", i32), ("transmittanceCutoff", f32), ("sampler", i32), ("skipEmptySpace", i32)]
 
 
 class TraceStats(C.Structure):
-    _fields_ = [("fragments", u64), ("coneSamples", u64), ("noiseSamples", u64), ("binEntries", u64)]
+    _fields_ = [("fragments", u64), ("coneSamples", u64), ("noiseSamples", u64), ("binEntries", u64), ("coneSamplesSkipped", u64)]
 
 
 class Timings(C.Structure):

@@ -24,6 +24,7 @@ SOURCES = {
     "k_voxelize.cu": ["-fmad=false"],
     "k_mips.cu": [],
     "k_trace.cu": [],
+    "k_skipmask.cu": [],
     "k_microbench.cu": [],
 }
 

@@ -143,7 +143,8 @@ struct crn_ctx {
     size_t chainBytes = 0;
 
     DevBuf pos, scale, keyL, keyC, rankL, rankC, recTmpL, recTmpC, rectTmpL, rectTmpC, lbTmp, recL, recC, rectL, rectC,
-        lbSorted, drawOrder, bits, chain, noise, posmap, image, misc;
+        lbSorted, drawOrder, bits, chain, noise, posmap, image, misc, maskNz, maskDil, mask;
+    bool maskCurrent = false;
     Bins binsL, binsC;
     uint32_t *hCursors = nullptr;        // pinned: [0..1] light cursors, [2..3] camera cursors
     unsigned long long *hStats = nullptr;
@@ -313,6 +314,18 @@ int require(crn_ctx *c, bool ok, const char *what) {
     return ok ? CRN_OK : fail(c, CRN_ERR_STATE, "%s has not been set", what);
 }
 
+int build_masks(crn_ctx *c) {
+    const size_t words = skipmask_words(c->vparams, nullptr);
+    int r;
+    if ((r = reserve(c, c->maskNz, words * 4))) return r;
+    if ((r = reserve(c, c->maskDil, words * 4))) return r;
+    if ((r = reserve(c, c->mask, words * 4))) return r;
+    c->launches += launch_skipmask(c->stream, c->vparams, (const uint32_t *)c->bits.p, (const uint8_t *)c->chain.p,
+                                   (uint32_t *)c->maskNz.p, (uint32_t *)c->maskDil.p, (uint32_t *)c->mask.p);
+    c->maskCurrent = true;
+    return CRN_OK;
+}
+
 int enqueue_voxelize(crn_ctx *c) {
     const int n = c->nBoards;
     crn_sun_derived sd;
@@ -357,7 +370,12 @@ int enqueue_voxelize(crn_ctx *c) {
     if (c->timingOn) cudaEventRecord(c->evV[3], st);
     c->launches += launch_mips(st, c->vparams, (const uint32_t *)c->bits.p, (uint8_t *)c->chain.p, (uint32_t *)c->misc.p, true,
                                toTex ? &c->ts : nullptr);
-    c->texCurrent = toTex && c->vparams.z0 == 0 && c->vparams.z1 == c->vol.dimension;
+    const bool whole = c->vparams.z0 == 0 && c->vparams.z1 == c->vol.dimension;
+    c->texCurrent = toTex && whole;
+    c->maskCurrent = false;
+    if (whole && c->tp.skipEmptySpace) {
+        if ((r = build_masks(c))) return r;
+    }
     if (c->timingOn) { cudaEventRecord(c->evV[4], st); c->evVValid = true; }
     CRN_CUDA(c, cudaGetLastError());
     c->voxelized = true;
@@ -393,6 +411,20 @@ void build_trace_params(crn_ctx *c, const ViewParams &cam, TraceParams *tp) {
         else { const float fl = floorf(lod); s.level0 = (int)fl; s.frac = lod - fl; }
         coneHeight += coneRadius;
     }
+    // groups for the empty-space test: consecutive steps with the same lower level whose sample points
+    // all lie within one level-l texel of the group's mid height (so M_l's 5x5x5 dilation covers them)
+    tp->nGroups = 0;
+    for (int i = 0; i < c->tp.vctSteps;) {
+        const int l = tp->steps[i].level0;
+        const float texel = 0.98f * (float)(1 << l);
+        int j = i;
+        while (j + 1 < c->tp.vctSteps && tp->steps[j + 1].level0 == l &&
+               0.5f * fabsf(tp->steps[j + 1].height - tp->steps[i].height) < texel) j++;
+        ConeGroup &g = tp->groups[tp->nGroups++];
+        g.height = 0.5f * (tp->steps[i].height + tp->steps[j].height);
+        g.level = l; g.first = i; g.count = j - i + 1;
+        i = j + 1;
+    }
 }
 
 int enqueue_trace(crn_ctx *c, int format) {
@@ -416,6 +448,9 @@ int enqueue_trace(crn_ctx *c, int format) {
     TraceParams tp;
     build_trace_params(c, cam, &tp);
     cudaStream_t st = c->stream;
+    if (c->tp.skipEmptySpace && !c->maskCurrent) {     // chain came from an exchange, or the option was just switched on
+        if ((r = build_masks(c))) return r;
+    }
     const bool useTex = c->tp.sampler == CRN_SAMPLER_TEXTURE;
     if (useTex) {
         if ((r = ensure_vol_textures(c))) return r;
@@ -438,8 +473,8 @@ int enqueue_trace(crn_ctx *c, int format) {
     cudaMemcpyAsync(c->hCursors + 2, c->binsC.cursors, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
     if (c->timingOn) cudaEventRecord(c->evT[2], st);
     c->launches += launch_trace(st, cam, c->vparams, tp, (const BoardRec *)c->recC.p, c->binsC, (const uint32_t *)c->bits.p,
-                                (const uint8_t *)c->chain.p, (const int8_t *)c->noise.p, useTex ? &c->ts : nullptr, c->image.p, format,
-                                dStats);
+                                (const uint8_t *)c->chain.p, (const int8_t *)c->noise.p, useTex ? &c->ts : nullptr,
+                                c->tp.skipEmptySpace ? (const uint32_t *)c->mask.p : nullptr, c->image.p, format, dStats);
     if (c->timingOn) { cudaEventRecord(c->evT[3], st); c->evTValid = true; }
     if (c->statsOn) cudaMemcpyAsync(c->hStats, dStats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
     CRN_CUDA(c, cudaGetLastError());
@@ -501,7 +536,7 @@ void crn_destroy(crn_ctx *c) {
     cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = {&c->pos, &c->scale, &c->keyL, &c->keyC, &c->rankL, &c->rankC, &c->recTmpL, &c->recTmpC, &c->rectTmpL,
                       &c->rectTmpC, &c->lbTmp, &c->recL, &c->recC, &c->rectL, &c->rectC, &c->lbSorted, &c->drawOrder, &c->bits,
-                      &c->chain, &c->noise, &c->posmap, &c->image, &c->misc};
+                      &c->chain, &c->noise, &c->posmap, &c->image, &c->misc, &c->maskNz, &c->maskDil, &c->mask};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     free_bins(c->binsL); free_bins(c->binsC);
     free_vol_textures(c);
@@ -535,6 +570,7 @@ void crn_default_trace_params(crn_trace_params *p) {          // src/Shaders/Con
     p->drawSun = 1;
     p->transmittanceCutoff = 0.0f;
     p->sampler = CRN_SAMPLER_EXPLICIT;
+    p->skipEmptySpace = 1;
 }
 
 int crn_set_volume(crn_ctx *c, const crn_volume_desc *d) {
@@ -783,6 +819,7 @@ int crn_finish_mips(crn_ctx *c, int32_t first_level) {
     CRN_CUDA(c, cudaGetLastError());
     c->voxelized = true;
     c->texCurrent = false;              // the texture-unit copy is refreshed from the chain at the next trace
+    c->maskCurrent = false;
     return CRN_OK;
 }
 
@@ -878,6 +915,7 @@ int crn_get_trace_stats(crn_ctx *c, crn_trace_stats *out) {
     CRN_CUDA(c, cudaStreamSynchronize(c->stream));
     out->fragments = c->hStats[0]; out->coneSamples = c->hStats[1]; out->noiseSamples = c->hStats[2];
     out->binEntries = c->hCursors[3];
+    out->coneSamplesSkipped = c->hStats[3];
     return CRN_OK;
 }
 

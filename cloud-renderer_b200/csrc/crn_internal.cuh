@@ -57,6 +57,12 @@ struct ConeStep {                     // traceCone's per-step constants (identic
     float frac;                       // blend toward level0+1 (0: single level)
 };
 
+struct ConeGroup {                    // consecutive cone steps decided by ONE empty-space lookup (k_skipmask.cu)
+    float height;                     // lookup point along the cone, voxels
+    int32_t level;                    // lower mip level of every step in the group
+    int32_t first, count;             // steps [first, first+count)
+};
+
 struct TraceParams {
     crn_trace_params p;
     float lightPos[3];
@@ -71,7 +77,9 @@ struct TraceParams {
     int32_t ilvIndex, ilvCount;       // tile-row interleave (image-space sharding)
     int32_t active;                   // doConeTrace || doNoiseSample || showQuad
     int32_t stats;
+    int32_t nGroups;
     ConeStep steps[kMaxConeSteps];
+    ConeGroup groups[kMaxConeSteps];
 };
 
 // bins of one pass
@@ -110,7 +118,11 @@ int launch_chain_to_surfaces(cudaStream_t st, const VolumeParams &vol, const uin
 int launch_finish_mips(cudaStream_t st, const VolumeParams &vol, uint8_t *chain, int firstLevel);
 int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol, const TraceParams &tp,
                  const BoardRec *recs, const Bins &b, const uint32_t *bits, const uint8_t *chain,
-                 const int8_t *noise, const TexSet *ts, void *image, int format, unsigned long long *stats);
+                 const int8_t *noise, const TexSet *ts, const uint32_t *skipMask, void *image, int format,
+                 unsigned long long *stats);
+size_t skipmask_words(const VolumeParams &vol, uint32_t *off);
+int launch_skipmask(cudaStream_t st, const VolumeParams &vol, const uint32_t *bits, const uint8_t *chain, uint32_t *nz,
+                    uint32_t *dil, uint32_t *mask);
 int launch_count_bits(cudaStream_t st, const uint32_t *bits, size_t words, unsigned long long *out);
 
 } // namespace crn

@@ -40,7 +40,21 @@ struct TraceArgs {
     int format;
     unsigned long long *stats;
     float volScale[3];            // voxelDim / range per axis
+    const uint32_t *mask;         // empty-space masks M_l (k_skipmask.cu), or nullptr
+    uint32_t maskOff[kMaxLevels];
 };
+
+// M_l at the level-l texel containing voxel-space point p: 0 => every filter footprint of the group is all-zero
+__device__ __forceinline__ bool group_occupied(const TraceArgs &a, int l, float px, float py, float pz) {
+    const int n = a.vol.levelSize[l];
+    const float s = 1.0f / (float)(1 << l);
+    const int ix = min(max(__float2int_rd(px * s), 0), n - 1);
+    const int iy = min(max(__float2int_rd(py * s), 0), n - 1);
+    const int iz = min(max(__float2int_rd(pz * s), 0), n - 1);
+    const int wpr = n >= 32 ? n >> 5 : 1;
+    const uint32_t w = __ldg(a.mask + a.maskOff[l] + (uint32_t)((iz * n + iy) * wpr + (ix >> 5)));
+    return (w >> (ix & 31)) & 1u;
+}
 
 __device__ __forceinline__ float saturatef(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
 
@@ -183,7 +197,7 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
 
     float C[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     float T = 1.0f;
-    unsigned long long nFrag = 0, nCone = 0, nNoise = 0;
+    unsigned long long nFrag = 0, nCone = 0, nNoise = 0, nSkip = 0;
 
     const uint32_t cnt = tp.active ? a.tileCnt[tile] : 0;
     const uint32_t off = cnt ? a.tileOff[tile] : 0;
@@ -290,24 +304,29 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
                 dx *= il; dy *= il; dz *= il;
                 float indirect = 0.0f;
                 if (shade) {
-                    if constexpr (kTex) {
-                        // normalized texture coordinates are the same on every level: voxel position / D
-                        const float invD = 1.0f / (float)D;
-                        const float nx = vx * invD, ny = vy * invD, nz = vz * invD;
-                        const float ex = dx * invD, ey = dy * invD, ez = dz * invD;
-                        for (int i = 0; i < tp.nSteps; i++) {
-                            const ConeStep st = tp.steps[i];
-                            const float sx = fmaf(st.height, ex, nx), sy = fmaf(st.height, ey, ny), sz = fmaf(st.height, ez, nz);
-                            float s = tex3D<float>(ts.tex[st.level0], sx, sy, sz);
-                            if (st.frac != 0.0f) s = lerpf(s, tex3D<float>(ts.tex[st.level0 + 1], sx, sy, sz), st.frac);
-                            indirect = fmaf(s, st.weight, indirect);
+                    // normalized texture coordinates are the same on every level: voxel position / D
+                    const float invD = 1.0f / (float)D;
+                    const float nx = vx * invD, ny = vy * invD, nz = vz * invD;
+                    const float ex = dx * invD, ey = dy * invD, ez = dz * invD;
+                    for (int g = 0; g < tp.nGroups; g++) {
+                        const ConeGroup gr = tp.groups[g];
+                        // one conservative lookup decides the whole group: all-zero footprints contribute exactly 0
+                        if (a.mask && !group_occupied(a, gr.level, fmaf(gr.height, dx, vx), fmaf(gr.height, dy, vy), fmaf(gr.height, dz, vz))) {
+                            if (tp.stats) nSkip += gr.count;
+                            continue;
                         }
-                    } else {
-                        for (int i = 0; i < tp.nSteps; i++) {
+                        for (int i = gr.first; i < gr.first + gr.count; i++) {
                             const ConeStep st = tp.steps[i];
-                            const float sx = fmaf(st.height, dx, vx), sy = fmaf(st.height, dy, vy), sz = fmaf(st.height, dz, vz);
-                            float s = sample_level(a, st.level0, sx, sy, sz);
-                            if (st.frac != 0.0f) s = lerpf(s, sample_level(a, st.level0 + 1, sx, sy, sz), st.frac);
+                            float s;
+                            if constexpr (kTex) {
+                                const float sx = fmaf(st.height, ex, nx), sy = fmaf(st.height, ey, ny), sz = fmaf(st.height, ez, nz);
+                                s = tex3D<float>(ts.tex[st.level0], sx, sy, sz);
+                                if (st.frac != 0.0f) s = lerpf(s, tex3D<float>(ts.tex[st.level0 + 1], sx, sy, sz), st.frac);
+                            } else {
+                                const float sx = fmaf(st.height, dx, vx), sy = fmaf(st.height, dy, vy), sz = fmaf(st.height, dz, vz);
+                                s = sample_level(a, st.level0, sx, sy, sz);
+                                if (st.frac != 0.0f) s = lerpf(s, sample_level(a, st.level0 + 1, sx, sy, sz), st.frac);
+                            }
                             indirect = fmaf(s, st.weight, indirect);
                         }
                     }
@@ -352,11 +371,13 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
             nFrag += __shfl_down_sync(0xFFFFFFFFu, nFrag, s);
             nCone += __shfl_down_sync(0xFFFFFFFFu, nCone, s);
             nNoise += __shfl_down_sync(0xFFFFFFFFu, nNoise, s);
+            nSkip += __shfl_down_sync(0xFFFFFFFFu, nSkip, s);
         }
         if (lane == 0) {
             if (nFrag) atomicAdd(&a.stats[0], nFrag);
             if (nCone) atomicAdd(&a.stats[1], nCone);
             if (nNoise) atomicAdd(&a.stats[2], nNoise);
+            if (nSkip) atomicAdd(&a.stats[3], nSkip);
         }
     }
 }
@@ -365,7 +386,8 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
 
 int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol, const TraceParams &tp,
                  const BoardRec *recs, const Bins &b, const uint32_t *bits, const uint8_t *chain,
-                 const int8_t *noise, const TexSet *ts, void *image, int format, unsigned long long *stats) {
+                 const int8_t *noise, const TexSet *ts, const uint32_t *skipMask, void *image, int format,
+                 unsigned long long *stats) {
     TraceArgs a;
     a.vol = vol;
     a.recs = recs;
@@ -374,6 +396,8 @@ int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol
     a.bits = bits; a.chain = chain;
     a.noise = reinterpret_cast<const float2 *>(noise);
     a.image = image; a.format = format; a.stats = stats;
+    a.mask = (skipMask && tp.p.skipEmptySpace) ? skipMask : nullptr;
+    skipmask_words(vol, a.maskOff);
     const float fd = (float)vol.dim;
     a.volScale[0] = fd / (vol.xB[1] - vol.xB[0]);
     a.volScale[1] = fd / (vol.yB[1] - vol.yB[0]);

@@ -129,6 +129,8 @@ typedef struct crn_trace_params {
                                        next billboard is below this. 0 = shade every
                                        fragment (reference behaviour).                */
     int32_t sampler;                /* CRN_SAMPLER_*                                   */
+    int32_t skipEmptySpace;         /* skip cone samples whose whole filter footprint is
+                                       provably zero (exact: they contribute 0). 1 = on  */
 } crn_trace_params;
 
 /* Counters of one crn_cone_trace call (read back on demand). */
@@ -137,6 +139,7 @@ typedef struct crn_trace_stats {
     uint64_t coneSamples;      /* textureLod() taps taken by traceCone                  */
     uint64_t noiseSamples;     /* texture(noiseMap) taps taken by noise3D               */
     uint64_t binEntries;       /* (tile, billboard) pairs in the camera-space bins      */
+    uint64_t coneSamplesSkipped; /* of coneSamples: proven zero by the empty-space masks, not fetched */
 } crn_trace_stats;
 
 /* Stage timings of the most recent frame, milliseconds, measured with CUDA events on

@@ -299,3 +299,28 @@ def test_tile_row_interleave_is_result_invariant(pkg, scenes, orc, renderer):
         asm[mine] = part[mine]
     assert (cover == 1).all() and np.array_equal(asm, whole)
     r2.close()
+
+
+@pytest.mark.parametrize("name", ["small", "C1"])
+def test_empty_space_skipping_is_exact(name, pkg, scenes, orc, renderer):
+    """cone samples proven all-zero by the dilated occupancy masks contribute exactly 0: the image with
+    skipping on is bit-identical to the image with every sample fetched, for both samplers"""
+    s = steady_state(scenes.make_scene(name), orc)
+    renderer.set_scene(s)
+    renderer.voxelize()
+    renderer.set_stats(True)
+    for sampler in (pkg.SAMPLER_EXPLICIT, pkg.SAMPLER_TEXTURE):
+        s.tp.sampler = sampler
+        imgs, skipped = [], []
+        for skip in (0, 1):
+            s.tp.skipEmptySpace = skip
+            renderer.set_trace_params(s.tp)
+            imgs.append(renderer.cone_trace(fmt=pkg.IMAGE_RGBA32F).copy())
+            st = renderer.trace_stats()
+            skipped.append(st.coneSamplesSkipped)
+            assert st.coneSamples == st.fragments * s.tp.vctSteps
+        assert skipped[0] == 0 and skipped[1] > 0
+        assert np.array_equal(imgs[0].view(np.uint32), imgs[1].view(np.uint32)), f"sampler {sampler}: skipping changed the image"
+        print(f"{name}/sampler{sampler}: {skipped[1]} of {st.coneSamples} cone samples skipped ({100.0 * skipped[1] / st.coneSamples:.1f} %)")
+    renderer.set_stats(False)
+    s.tp.skipEmptySpace = 1
