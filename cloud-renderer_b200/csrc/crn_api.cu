@@ -249,6 +249,8 @@ void free_vol_textures(crn_ctx *c) {
         if (c->ts.surf[l]) cudaDestroySurfaceObject(c->ts.surf[l]);
         c->ts.tex[l] = 0; c->ts.surf[l] = 0;
     }
+    if (c->ts.vol) cudaDestroyTextureObject(c->ts.vol);
+    c->ts.vol = 0;
     if (c->volArray) cudaFreeMipmappedArray(c->volArray);
     c->volArray = nullptr; c->volArrayDim = c->volArrayLevels = 0; c->ts.enabled = 0; c->texCurrent = false;
 }
@@ -272,6 +274,16 @@ int ensure_vol_textures(crn_ctx *c) {
         td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
         td.filterMode = cudaFilterModeLinear; td.readMode = cudaReadModeNormalizedFloat; td.normalizedCoords = 1;
         CRN_CUDA(c, cudaCreateTextureObject(&c->ts.tex[l], &rd, &td, nullptr));
+    }
+    {   // one object over the whole chain for tex3DLod: LINEAR inside a level, POINT between levels
+        cudaResourceDesc rd{};
+        rd.resType = cudaResourceTypeMipmappedArray; rd.res.mipmap.mipmap = c->volArray;
+        cudaTextureDesc td{};
+        td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModeLinear; td.mipmapFilterMode = cudaFilterModePoint;
+        td.readMode = cudaReadModeNormalizedFloat; td.normalizedCoords = 1;
+        td.minMipmapLevelClamp = 0.0f; td.maxMipmapLevelClamp = (float)(L - 1);
+        CRN_CUDA(c, cudaCreateTextureObject(&c->ts.vol, &rd, &td, nullptr));
     }
     c->volArrayDim = D; c->volArrayLevels = L; c->ts.enabled = 1; c->texCurrent = false;
     return CRN_OK;
@@ -414,6 +426,8 @@ void build_trace_params(crn_ctx *c, const ViewParams &cam, TraceParams *tp) {
     // groups for the empty-space test: consecutive steps with the same lower level whose sample points
     // all lie within one level-l texel of the group's mid height (so M_l's 5x5x5 dilation covers them)
     tp->nGroups = 0;
+    uint32_t maskOff[kMaxLevels] = {};
+    skipmask_words(c->vparams, maskOff);
     for (int i = 0; i < c->tp.vctSteps;) {
         const int l = tp->steps[i].level0;
         const float texel = 0.98f * (float)(1 << l);
@@ -422,8 +436,19 @@ void build_trace_params(crn_ctx *c, const ViewParams &cam, TraceParams *tp) {
                0.5f * fabsf(tp->steps[j + 1].height - tp->steps[i].height) < texel) j++;
         ConeGroup &g = tp->groups[tp->nGroups++];
         g.height = 0.5f * (tp->steps[i].height + tp->steps[j].height);
-        g.level = l; g.first = i; g.count = j - i + 1;
+        g.invScale = 1.0f / (float)(1 << l);
+        g.size = c->vparams.levelSize[l]; g.nMinus1 = g.size - 1;
+        g.wpr = g.size >= 32 ? g.size / 32 : 1;
+        g.maskOff = maskOff[l];
+        g.first = i; g.count = j - i + 1;
         i = j + 1;
+    }
+    // noise3D's per-octave constants (res/conetrace_frag.glsl:107-114)
+    float freq = 1.0f, pers = 1.0f;
+    for (int o = 0; o < kMaxOctaves; o++) {
+        tp->octFreq[o] = freq; tp->octPers[o] = pers;
+        tp->octBias[o] = (o < 3 ? tp->octaveOffsets[o] : 0.0f) * freq;
+        freq *= c->tp.freqStep; pers *= c->tp.persStep;
     }
 }
 

@@ -59,7 +59,11 @@ struct ConeStep {                     // traceCone's per-step constants (identic
 
 struct ConeGroup {                    // consecutive cone steps decided by ONE empty-space lookup (k_skipmask.cu)
     float height;                     // lookup point along the cone, voxels
-    int32_t level;                    // lower mip level of every step in the group
+    float invScale;                   // 2^-level: voxel units -> level texels
+    int32_t nMinus1;                  // level size - 1 (index clamp)
+    int32_t size;                     // level size
+    int32_t wpr;                      // mask words per row
+    uint32_t maskOff;                 // word offset of M_level
     int32_t first, count;             // steps [first, first+count)
 };
 
@@ -78,6 +82,9 @@ struct TraceParams {
     int32_t active;                   // doConeTrace || doNoiseSample || showQuad
     int32_t stats;
     int32_t nGroups;
+    float octFreq[kMaxOctaves];       // freq of octave o (freqStep^o)
+    float octBias[kMaxOctaves];       // octaveOffsets[o] * freq: uv*freq + bias == (uv + offset)*freq
+    float octPers[kMaxOctaves];       // persStep^o
     ConeStep steps[kMaxConeSteps];
     ConeGroup groups[kMaxConeSteps];
 };
@@ -108,6 +115,7 @@ int launch_voxelize(cudaStream_t st, const ViewParams &light, const VolumeParams
 struct TexSet {
     cudaSurfaceObject_t surf[kMaxLevels];   // one per level, written by the mip kernel
     cudaTextureObject_t tex[kMaxLevels];    // one per level: LINEAR, CLAMP, normalized coords, UNORM8 -> float
+    cudaTextureObject_t vol;                // the whole mipmapped array: LINEAR in-level, POINT between levels (tex3DLod)
     cudaTextureObject_t noise;              // RGBA8_SNORM, LINEAR, REPEAT
     int32_t enabled;
 };

@@ -41,18 +41,14 @@ struct TraceArgs {
     unsigned long long *stats;
     float volScale[3];            // voxelDim / range per axis
     const uint32_t *mask;         // empty-space masks M_l (k_skipmask.cu), or nullptr
-    uint32_t maskOff[kMaxLevels];
 };
 
 // M_l at the level-l texel containing voxel-space point p: 0 => every filter footprint of the group is all-zero
-__device__ __forceinline__ bool group_occupied(const TraceArgs &a, int l, float px, float py, float pz) {
-    const int n = a.vol.levelSize[l];
-    const float s = 1.0f / (float)(1 << l);
-    const int ix = min(max(__float2int_rd(px * s), 0), n - 1);
-    const int iy = min(max(__float2int_rd(py * s), 0), n - 1);
-    const int iz = min(max(__float2int_rd(pz * s), 0), n - 1);
-    const int wpr = n >= 32 ? n >> 5 : 1;
-    const uint32_t w = __ldg(a.mask + a.maskOff[l] + (uint32_t)((iz * n + iy) * wpr + (ix >> 5)));
+__device__ __forceinline__ bool group_occupied(const uint32_t *__restrict__ mask, const ConeGroup &g, float px, float py, float pz) {
+    const int ix = min(max(__float2int_rd(px * g.invScale), 0), g.nMinus1);
+    const int iy = min(max(__float2int_rd(py * g.invScale), 0), g.nMinus1);
+    const int iz = min(max(__float2int_rd(pz * g.invScale), 0), g.nMinus1);
+    const uint32_t w = __ldg(mask + g.maskOff + (uint32_t)((iz * g.size + iy) * g.wpr + (ix >> 5)));
     return (w >> (ix & 31)) & 1u;
 }
 
@@ -261,20 +257,18 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
                 const int nMax = __reduce_max_sync(0xFFFFFFFFu, nIter);
                 for (int i = 0; i < nMax; i++) {
                     if (i < nIter) {
-                        float ng = 0.0f, na = 0.0f, freq = 1.0f, pers = 1.0f;
-                        for (int o = 0; o < tp.p.numOctaves; o++) {     // noise3D, :103-120
-                            const float offs = o < 3 ? tp.octaveOffsets[o] : 0.0f;
+                        float ng = 0.0f, na = 0.0f;
+                        for (int o = 0; o < tp.p.numOctaves; o++) {     // noise3D, :103-120: texture(noiseMap, (uv + offset_o) * freq_o) * pers_o
+                            const float f = tp.octFreq[o], b = tp.octBias[o];
                             float2 s;
                             if constexpr (kTex) {
-                                const float4 t = tex3D<float4>(ts.noise, (tx + offs) * freq, (tyy + offs) * freq, (tz + offs) * freq);
+                                const float4 t = tex3D<float4>(ts.noise, fmaf(tx, f, b), fmaf(tyy, f, b), fmaf(tz, f, b));
                                 s = make_float2(t.y, t.w);
                             } else {
-                                s = sample_noise(a.noise, nzDim, (tx + offs) * freq, (tyy + offs) * freq, (tz + offs) * freq);
+                                s = sample_noise(a.noise, nzDim, fmaf(tx, f, b), fmaf(tyy, f, b), fmaf(tz, f, b));
                             }
-                            ng = fmaf(pers, s.x, ng);
-                            na = fmaf(pers, s.y, na);
-                            freq *= tp.p.freqStep;
-                            pers *= tp.p.persStep;
+                            ng = fmaf(tp.octPers[o], s.x, ng);
+                            na = fmaf(tp.octPers[o], s.y, na);
                         }
                         na = fabsf(na);
                         const float uu = ux * ux + uy * uy + uz * uz;
@@ -303,25 +297,26 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
                 const float il = rsqrtf(dx * dx + dy * dy + dz * dz);
                 dx *= il; dy *= il; dz *= il;
                 float indirect = 0.0f;
-                if (shade) {
-                    // normalized texture coordinates are the same on every level: voxel position / D
-                    const float invD = 1.0f / (float)D;
-                    const float nx = vx * invD, ny = vy * invD, nz = vz * invD;
-                    const float ex = dx * invD, ey = dy * invD, ez = dz * invD;
-                    for (int g = 0; g < tp.nGroups; g++) {
-                        const ConeGroup gr = tp.groups[g];
-                        // one conservative lookup decides the whole group: all-zero footprints contribute exactly 0
-                        if (a.mask && !group_occupied(a, gr.level, fmaf(gr.height, dx, vx), fmaf(gr.height, dy, vy), fmaf(gr.height, dz, vz))) {
-                            if (tp.stats) nSkip += gr.count;
-                            continue;
-                        }
-                        for (int i = gr.first; i < gr.first + gr.count; i++) {
-                            const ConeStep st = tp.steps[i];
+                // normalized texture coordinates are the same on every level: voxel position / D
+                const float invD = 1.0f / (float)D;
+                const float nx = vx * invD, ny = vy * invD, nz = vz * invD;
+                const float ex = dx * invD, ey = dy * invD, ez = dz * invD;
+                // group and step loops are warp-uniform (constants come from uniform registers); lanes take part by predicate
+                for (int g = 0; g < tp.nGroups; g++) {
+                    const ConeGroup &gr = tp.groups[g];
+                    bool need = shade;
+                    // one conservative lookup decides the whole group: all-zero footprints contribute exactly 0
+                    if (a.mask && need) need = group_occupied(a.mask, gr, fmaf(gr.height, dx, vx), fmaf(gr.height, dy, vy), fmaf(gr.height, dz, vz));
+                    if (tp.stats && shade && !need) nSkip += gr.count;
+                    if (!__any_sync(0xFFFFFFFFu, need)) continue;
+                    for (int i = gr.first; i < gr.first + gr.count; i++) {
+                        const ConeStep &st = tp.steps[i];
+                        if (need) {
                             float s;
                             if constexpr (kTex) {
                                 const float sx = fmaf(st.height, ex, nx), sy = fmaf(st.height, ey, ny), sz = fmaf(st.height, ez, nz);
-                                s = tex3D<float>(ts.tex[st.level0], sx, sy, sz);
-                                if (st.frac != 0.0f) s = lerpf(s, tex3D<float>(ts.tex[st.level0 + 1], sx, sy, sz), st.frac);
+                                s = tex3DLod<float>(ts.vol, sx, sy, sz, (float)st.level0);
+                                if (st.frac != 0.0f) s = lerpf(s, tex3DLod<float>(ts.vol, sx, sy, sz, (float)(st.level0 + 1)), st.frac);
                             } else {
                                 const float sx = fmaf(st.height, dx, vx), sy = fmaf(st.height, dy, vy), sz = fmaf(st.height, dz, vz);
                                 s = sample_level(a, st.level0, sx, sy, sz);
@@ -397,7 +392,6 @@ int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol
     a.noise = reinterpret_cast<const float2 *>(noise);
     a.image = image; a.format = format; a.stats = stats;
     a.mask = (skipMask && tp.p.skipEmptySpace) ? skipMask : nullptr;
-    skipmask_words(vol, a.maskOff);
     const float fd = (float)vol.dim;
     a.volScale[0] = fd / (vol.xB[1] - vol.xB[0]);
     a.volScale[1] = fd / (vol.yB[1] - vol.yB[0]);
