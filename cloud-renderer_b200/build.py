@@ -23,7 +23,7 @@ SOURCES = {
     "k_bin.cu": [],
     "k_voxelize.cu": ["-fmad=false"],
     "k_mips.cu": [],
-    "k_trace.cu": [],
+    "k_trace.cu": ["--use_fast_math"],      # image parity is PSNR-based; div/sqrt/rcp as MUFU approximations
     "k_skipmask.cu": [],
     "k_microbench.cu": [],
 }

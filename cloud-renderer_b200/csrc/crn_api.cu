@@ -143,7 +143,7 @@ struct crn_ctx {
     size_t chainBytes = 0;
 
     DevBuf pos, scale, keyL, keyC, rankL, rankC, recTmpL, recTmpC, rectTmpL, rectTmpC, lbTmp, recL, recC, rectL, rectC,
-        lbSorted, drawOrder, bits, chain, noise, posmap, image, misc, maskNz, maskDil, mask;
+        lbSorted, drawOrder, bits, chain, noise, posmap, image, misc, maskNz, maskDil, mask, sortTmp;
     bool maskCurrent = false;
     Bins binsL, binsC;
     uint32_t *hCursors = nullptr;        // pinned: [0..1] light cursors, [2..3] camera cursors
@@ -211,14 +211,9 @@ int ensure_bins(crn_ctx *c, Bins &b, int W, int H, int n) {
         r = alloc_u32(c, b.tileCnt, h2, tiles); if (r) return r;
         b.tilesAlloc = tiles;
     }
-    if (coarse > b.coarseAlloc) {
-        size_t h1 = b.coarseAlloc, h2 = b.coarseAlloc;
-        int r = alloc_u32(c, b.coarseOff, h1, coarse); if (r) return r;
-        r = alloc_u32(c, b.coarseCnt, h2, coarse); if (r) return r;
-        b.coarseAlloc = coarse;
-    }
+    (void)coarse;
     if (!b.cursors) CRN_CUDA(c, cudaMalloc(&b.cursors, 2 * sizeof(uint32_t)));
-    int r = alloc_u32(c, b.coarseList, b.coarseCap, std::max<size_t>((size_t)1 << 16, (size_t)n * 8)); if (r) return r;
+    int r = alloc_u32(c, b.coarseList, b.coarseCap, 4 * std::max<size_t>((size_t)1 << 16, (size_t)n * 8)); if (r) return r;   // uint4 entries
     r = alloc_u32(c, b.tileList, b.tileCap, std::max<size_t>((size_t)1 << 20, (size_t)n * 96)); if (r) return r;
     return CRN_OK;
 }
@@ -232,8 +227,8 @@ void free_bins(Bins &b) {
 // grow a pool whose cursor ran past its capacity; returns true if anything grew
 int grow_if_overflowed(crn_ctx *c, Bins &b, const uint32_t *cur, bool *grew) {
     *grew = false;
-    if (cur[0] > b.coarseCap) {
-        int r = alloc_u32(c, b.coarseList, b.coarseCap, (size_t)cur[0] + cur[0] / 2); if (r) return r;
+    if ((size_t)cur[0] * 4 > b.coarseCap) {                 // cursor counts uint4 entries
+        int r = alloc_u32(c, b.coarseList, b.coarseCap, 4 * ((size_t)cur[0] + cur[0] / 2)); if (r) return r;
         *grew = true;
     }
     if (cur[1] > b.tileCap) {
@@ -355,6 +350,7 @@ int enqueue_voxelize(crn_ctx *c) {
     if ((r = reserve(c, c->recL, nn * sizeof(BoardRec)))) return r;
     if ((r = reserve(c, c->rectL, nn * sizeof(BoardRect)))) return r;
     if ((r = reserve(c, c->lbSorted, nn * 4))) return r;
+    if ((r = reserve(c, c->sortTmp, sort_tmp_bytes((int)nn) + 128))) return r;
     const size_t D = c->vol.dimension;
     if ((r = reserve(c, c->bits, D * D * D / 8))) return r;
     if ((r = reserve(c, c->chain, c->chainBytes))) return r;
@@ -371,9 +367,9 @@ int enqueue_voxelize(crn_ctx *c) {
                                     light, sd.nearPlane, sd.clipDistance, dummy, zero3, true, false, (uint32_t *)c->rankL.p, nullptr,
                                     (uint64_t *)c->keyL.p, nullptr, (BoardRec *)c->recTmpL.p, nullptr, (BoardRect *)c->rectTmpL.p,
                                     nullptr, (float *)c->lbTmp.p, (BoardRec *)c->recL.p, nullptr, (BoardRect *)c->rectL.p, nullptr,
-                                    (float *)c->lbSorted.p, nullptr);
+                                    (float *)c->lbSorted.p, nullptr, c->sortTmp.p);
     if (c->timingOn) cudaEventRecord(c->evV[1], st);
-    c->launches += launch_bin(st, (const BoardRect *)c->rectL.p, n, c->W, c->H, c->binsL);
+    c->launches += launch_bin(st, (const BoardRect *)c->rectL.p, sort_tmp_bounds(c->sortTmp.p, (int)nn, 0), n, c->W, c->H, c->binsL);
     cudaMemcpyAsync(c->hCursors, c->binsL.cursors, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
     if (c->timingOn) cudaEventRecord(c->evV[2], st);
     c->launches += launch_voxelize(st, light, c->vparams, sd.nearPlane, sd.clipDistance, (const BoardRec *)c->recL.p,
@@ -465,6 +461,7 @@ int enqueue_trace(crn_ctx *c, int format) {
     if ((r = reserve(c, c->recC, nn * sizeof(BoardRec)))) return r;
     if ((r = reserve(c, c->rectC, nn * sizeof(BoardRect)))) return r;
     if ((r = reserve(c, c->drawOrder, nn * 4))) return r;
+    if ((r = reserve(c, c->sortTmp, sort_tmp_bytes((int)nn) + 128))) return r;
     if ((r = reserve(c, c->misc, 256))) return r;
     const size_t texel = format == CRN_IMAGE_RGBA32F ? 16 : 4;
     if ((r = reserve(c, c->image, (size_t)c->W * c->H * texel))) return r;
@@ -492,9 +489,9 @@ int enqueue_trace(crn_ctx *c, int format) {
                                     zero3, 1.0f, cam, c->cam.position, false, true, nullptr, (uint32_t *)c->rankC.p, nullptr,
                                     (uint64_t *)c->keyC.p, nullptr, (BoardRec *)c->recTmpC.p, nullptr, (BoardRect *)c->rectTmpC.p,
                                     nullptr, nullptr, (BoardRec *)c->recC.p, nullptr, (BoardRect *)c->rectC.p, nullptr,
-                                    (int32_t *)c->drawOrder.p);
+                                    (int32_t *)c->drawOrder.p, c->sortTmp.p);
     if (c->timingOn) cudaEventRecord(c->evT[1], st);
-    c->launches += launch_bin(st, (const BoardRect *)c->rectC.p, n, c->W, c->H, c->binsC);
+    c->launches += launch_bin(st, (const BoardRect *)c->rectC.p, sort_tmp_bounds(c->sortTmp.p, (int)nn, 1), n, c->W, c->H, c->binsC);
     cudaMemcpyAsync(c->hCursors + 2, c->binsC.cursors, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
     if (c->timingOn) cudaEventRecord(c->evT[2], st);
     c->launches += launch_trace(st, cam, c->vparams, tp, (const BoardRec *)c->recC.p, c->binsC, (const uint32_t *)c->bits.p,
@@ -561,7 +558,7 @@ void crn_destroy(crn_ctx *c) {
     cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = {&c->pos, &c->scale, &c->keyL, &c->keyC, &c->rankL, &c->rankC, &c->recTmpL, &c->recTmpC, &c->rectTmpL,
                       &c->rectTmpC, &c->lbTmp, &c->recL, &c->recC, &c->rectL, &c->rectC, &c->lbSorted, &c->drawOrder, &c->bits,
-                      &c->chain, &c->noise, &c->posmap, &c->image, &c->misc, &c->maskNz, &c->maskDil, &c->mask};
+                      &c->chain, &c->noise, &c->posmap, &c->image, &c->misc, &c->maskNz, &c->maskDil, &c->mask, &c->sortTmp};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     free_bins(c->binsL); free_bins(c->binsC);
     free_vol_textures(c);

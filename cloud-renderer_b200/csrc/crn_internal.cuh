@@ -15,7 +15,7 @@ namespace crn {
 // geometry of the two tilings
 // ----------------------------------------------------------------------------------------
 constexpr int kTile = 16;            // fine tile edge in pixels: one 256-thread CTA, 8 warps of 8x4
-constexpr int kCoarse = 8;           // coarse tile = kCoarse x kCoarse fine tiles (128 px)
+constexpr int kCoarse = 4;           // coarse tile = kCoarse x kCoarse fine tiles (64 px)
 constexpr int kMaxConeSteps = 128;   // vctSteps upper bound (reference UI slider tops out far lower)
 constexpr int kMaxLevels = 16;
 constexpr int kMaxOctaves = 8;
@@ -106,8 +106,10 @@ int launch_prep_sort(cudaStream_t st, const float *pos, const float *scale, int 
                      const float camPos[3], bool doLight, bool doCam, uint32_t *rankL, uint32_t *rankC,
                      uint64_t *keyL, uint64_t *keyC, BoardRec *recTmpL, BoardRec *recTmpC, BoardRect *rectTmpL,
                      BoardRect *rectTmpC, float *lbTmp, BoardRec *recL, BoardRec *recC, BoardRect *rectL,
-                     BoardRect *rectC, float *lbSorted, int32_t *drawOrder);
-int launch_bin(cudaStream_t st, const BoardRect *rects, int n, int W, int H, Bins &b);
+                     BoardRect *rectC, float *lbSorted, int32_t *drawOrder, void *sortTmp);
+size_t sort_tmp_bytes(int n);      // sortTmp must hold sort_tmp_bytes(n) + 16 bytes
+int launch_bin(cudaStream_t st, const BoardRect *rects, const int32_t *bounds, int n, int W, int H, Bins &b);
+const int32_t *sort_tmp_bounds(const void *sortTmp, int n, int pass);   // rect bounds written by prep_kernel (pass 0 light, 1 camera)
 int launch_voxelize(cudaStream_t st, const ViewParams &light, const VolumeParams &vol, const float nearPlane[3],
                     float clip, const BoardRec *recs, const float *lbSorted, const Bins &b, uint32_t *bits,
                     float4 *posmap);

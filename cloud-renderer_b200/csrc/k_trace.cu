@@ -48,7 +48,8 @@ __device__ __forceinline__ bool group_occupied(const uint32_t *__restrict__ mask
     const int ix = min(max(__float2int_rd(px * g.invScale), 0), g.nMinus1);
     const int iy = min(max(__float2int_rd(py * g.invScale), 0), g.nMinus1);
     const int iz = min(max(__float2int_rd(pz * g.invScale), 0), g.nMinus1);
-    const uint32_t w = __ldg(mask + g.maskOff + (uint32_t)((iz * g.size + iy) * g.wpr + (ix >> 5)));
+    const uint32_t word = g.maskOff + (uint32_t)((iz * g.size + iy) * g.wpr + (ix >> 5));
+    const uint32_t w = __ldg(mask + word);
     return (w >> (ix & 31)) & 1u;
 }
 
