@@ -432,8 +432,8 @@ void build_trace_params(crn_ctx *c, const ViewParams &cam, TraceParams *tp) {
                0.5f * fabsf(tp->steps[j + 1].height - tp->steps[i].height) < texel) j++;
         ConeGroup &g = tp->groups[tp->nGroups++];
         g.height = 0.5f * (tp->steps[i].height + tp->steps[j].height);
-        g.invScale = 1.0f / (float)(1 << l);
         g.size = c->vparams.levelSize[l]; g.nMinus1 = g.size - 1;
+        g.sizeF = (float)g.size;
         g.wpr = g.size >= 32 ? g.size / 32 : 1;
         g.maskOff = maskOff[l];
         g.first = i; g.count = j - i + 1;

@@ -39,15 +39,17 @@ struct TraceArgs {
     void *image;
     int format;
     unsigned long long *stats;
-    float volScale[3];            // voxelDim / range per axis
+    float invRange[3];            // 1 / range per axis
+    float invDim;                 // 1 / voxelDim
     const uint32_t *mask;         // empty-space masks M_l (k_skipmask.cu), or nullptr
 };
 
 // M_l at the level-l texel containing voxel-space point p: 0 => every filter footprint of the group is all-zero
+// (p = normalized texture coordinate of the lookup point)
 __device__ __forceinline__ bool group_occupied(const uint32_t *__restrict__ mask, const ConeGroup &g, float px, float py, float pz) {
-    const int ix = min(max(__float2int_rd(px * g.invScale), 0), g.nMinus1);
-    const int iy = min(max(__float2int_rd(py * g.invScale), 0), g.nMinus1);
-    const int iz = min(max(__float2int_rd(pz * g.invScale), 0), g.nMinus1);
+    const int ix = min(max(__float2int_rd(px * g.sizeF), 0), g.nMinus1);
+    const int iy = min(max(__float2int_rd(py * g.sizeF), 0), g.nMinus1);
+    const int iz = min(max(__float2int_rd(pz * g.sizeF), 0), g.nMinus1);
     const uint32_t word = g.maskOff + (uint32_t)((iz * g.size + iy) * g.wpr + (ix >> 5));
     const uint32_t w = __ldg(mask + word);
     return (w >> (ix & 31)) & 1u;
@@ -164,7 +166,7 @@ __device__ __forceinline__ bool sun_fragment(const TraceParams &tp, const ViewPa
 }
 
 // kTex = false: explicit filtering (CRN_SAMPLER_EXPLICIT);  kTex = true: texture units (CRN_SAMPLER_TEXTURE)
-template <bool kTex>
+template <bool kTex, bool kStats>
 __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ TraceArgs a, const __grid_constant__ ViewParams cam,
                                                     const __grid_constant__ TraceParams tp, const __grid_constant__ TexSet ts) {
     const int tile = blockIdx.x;
@@ -202,7 +204,7 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
     const int D = a.vol.dim;
     (void)D;
     const int nzDim = tp.noiseDim;
-    const float invAdjust = 1.0f / tp.p.adjustSize;
+    const float invAdjust = 1.0f / tp.p.adjustSize, invStep = 1.0f / tp.p.stepSize;
     const float noiseSpan = (float)(tp.p.maxNoiseSteps - tp.p.minNoiseSteps);
     // viewRay = normalize(V[0][2], V[1][2], V[2][2]) = cam.nrm (res/conetrace_frag.glsl:138)
     const float rx = cam.nrm[0], ry = cam.nrm[1], rz = cam.nrm[2];
@@ -221,14 +223,14 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
         const float u = xv - r1.x, v = yv - r1.y;
         const float d2 = u * u + v * v, r2 = radius * radius;
         const float h2 = r2 - d2;                                       // half chord squared
+        const float invr = 1.0f / radius;
 
         float col[4];
         bool shade = live && fabsf(u) < radius && fabsf(v) < radius;    // inside the quad
         if (tp.p.showQuad) {                                            // conetrace_frag.glsl:124-134
             if (shade) {
-                const float q = sqrtf(d2) / radius;
-                const float sc = sqrtf(fmaxf(0.0f, 1.0f - q * q));
-                const float ftx = (u / radius + 1.0f) * 0.5f, fty = (v / radius + 1.0f) * 0.5f;
+                const float sc = sqrtf(fmaxf(0.0f, h2)) * invr;              // sqrt(1 - d^2/r^2)
+                const float ftx = (u * invr + 1.0f) * 0.5f, fty = (v * invr + 1.0f) * 0.5f;
                 const bool border = ftx < 0.01f || fty < 0.01f || ftx > 0.99f || fty > 0.99f;
                 col[0] = col[1] = col[2] = col[3] = border ? 1.0f : sc;
             }
@@ -236,7 +238,7 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
             // discards: raySphereIntersect's disc = 4*(r^2 - d^2) < 0.01 (noise on), and
             // sphereContrib = sqrt(1 - d^2/r^2) < 0.01 (cone trace on)
             if (tp.p.doNoiseSample) shade = shade && !(4.0f * h2 < 0.01f);
-            if (tp.p.doConeTrace) shade = shade && !(sqrtf(fmaxf(0.0f, 1.0f - d2 / r2)) < 0.01f);
+            if (tp.p.doConeTrace) shade = shade && !(h2 < 1.0e-4f * r2);   // sqrt(1 - d2/r2) < 0.01
             if (!__any_sync(0xFFFFFFFFu, shade)) continue;
             const float h = sqrtf(fmaxf(h2, 0.0f));
             // fragPos - center, and the two sphere hits along the view ray: near = -h, far = +h
@@ -246,11 +248,11 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
             col[0] = col[1] = col[2] = col[3] = 0.0f;
 
             if (tp.p.doNoiseSample) {                                   // conetrace_frag.glsl:137-174
-                float ux = (ox - rx * h) / radius, uy = (oy - ry * h) / radius, uz = (oz - rz * h) / radius;   // unitTex
+                float ux = (ox - rx * h) * invr, uy = (oy - ry * h) * invr, uz = (oz - rz * h) * invr;        // unitTex
                 float tx = (r0.x + ox - rx * h) * invAdjust, tyy = (r0.y + oy - ry * h) * invAdjust,
                       tz = (r0.z + oz - rz * h) * invAdjust;                                                // localTexNear
                 const float len = 2.0f * h * invAdjust;
-                float iSteps = fminf(len / tp.p.stepSize, noiseSpan) + (float)tp.p.minNoiseSteps;
+                float iSteps = fminf(len * invStep, noiseSpan) + (float)tp.p.minNoiseSteps;
                 const float inv = 1.0f / (iSteps - 1.0f);
                 const float dxs = rx * len * inv, dys = ry * len * inv, dzs = rz * len * inv;              // localTexDelta
                 float opacity = 0.0f, light = 0.0f;
@@ -278,12 +280,11 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
                         light += saturatef(ng * 0.5f + 0.5f);
                         tx += dxs; tyy += dys; tz += dzs;
                         ux += dxs; uy += dys; uz += dzs;                // (sic) tex-space delta on the unit-sphere coord
-                        if (tp.stats) nNoise += tp.p.numOctaves;
+                        if (kStats) nNoise += tp.p.numOctaves;
                     }
                 }
                 const float c = tp.p.minNoiseColor + tp.p.noiseColorScale * light * inv;
-                const float ftx = (u / radius + 1.0f) * 0.5f - 0.5f, fty = (v / radius + 1.0f) * 0.5f - 0.5f;
-                const float alpha = 1.0f - sqrtf(ftx * ftx + fty * fty) * 2.0f;
+                const float alpha = 1.0f - sqrtf(d2) * invr;                   // 1 - length(fragTex - 0.5) * 2
                 col[0] = col[1] = col[2] = c;
                 col[3] = saturatef(opacity * tp.p.noiseOpacity * inv) * alpha;
             }
@@ -291,43 +292,42 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
             if (tp.p.doConeTrace) {                                     // conetrace_frag.glsl:176-200, traceCone :64-79
                 // start on the camera-facing sphere surface: fragPos + n * r * sphereContrib = center + o + n*h
                 const float wx3 = r0.x + ox + rx * h, wy3 = r0.y + oy + ry * h, wz3 = r0.z + oz + rz * h;
-                const float vx = (wx3 - a.vol.xB[0]) * a.volScale[0];   // calculateVoxelLerp
-                const float vy = (wy3 - a.vol.yB[0]) * a.volScale[1];
-                const float vz = (wz3 - a.vol.zB[0]) * a.volScale[2];
-                float dx = tp.lightPos[0] - wx3, dy = tp.lightPos[1] - wy3, dz = tp.lightPos[2] - wz3;
-                const float il = rsqrtf(dx * dx + dy * dy + dz * dz);
-                dx *= il; dy *= il; dz *= il;
+                // calculateVoxelLerp / voxelDim: the normalized texture coordinate, identical on every level
+                const float nx = (wx3 - a.vol.xB[0]) * a.invRange[0];
+                const float ny = (wy3 - a.vol.yB[0]) * a.invRange[1];
+                const float nz = (wz3 - a.vol.zB[0]) * a.invRange[2];
+                float ex = tp.lightPos[0] - wx3, ey = tp.lightPos[1] - wy3, ez = tp.lightPos[2] - wz3;
+                const float il = rsqrtf(ex * ex + ey * ey + ez * ez) * a.invDim;      // normalize(dir) / voxelDim
+                ex *= il; ey *= il; ez *= il;
                 float indirect = 0.0f;
-                // normalized texture coordinates are the same on every level: voxel position / D
-                const float invD = 1.0f / (float)D;
-                const float nx = vx * invD, ny = vy * invD, nz = vz * invD;
-                const float ex = dx * invD, ey = dy * invD, ez = dz * invD;
                 // group and step loops are warp-uniform (constants come from uniform registers); lanes take part by predicate
                 for (int g = 0; g < tp.nGroups; g++) {
                     const ConeGroup &gr = tp.groups[g];
                     bool need = shade;
                     // one conservative lookup decides the whole group: all-zero footprints contribute exactly 0
-                    if (a.mask && need) need = group_occupied(a.mask, gr, fmaf(gr.height, dx, vx), fmaf(gr.height, dy, vy), fmaf(gr.height, dz, vz));
-                    if (tp.stats && shade && !need) nSkip += gr.count;
+                    if (a.mask && need)
+                        need = group_occupied(a.mask, gr, fmaf(gr.height, ex, nx), fmaf(gr.height, ey, ny), fmaf(gr.height, ez, nz));
+                    if (kStats && shade && !need) nSkip += gr.count;
                     if (!__any_sync(0xFFFFFFFFu, need)) continue;
+#pragma unroll 2
                     for (int i = gr.first; i < gr.first + gr.count; i++) {
                         const ConeStep &st = tp.steps[i];
                         if (need) {
+                            const float sx = fmaf(st.height, ex, nx), sy = fmaf(st.height, ey, ny), sz = fmaf(st.height, ez, nz);
                             float s;
                             if constexpr (kTex) {
-                                const float sx = fmaf(st.height, ex, nx), sy = fmaf(st.height, ey, ny), sz = fmaf(st.height, ez, nz);
                                 s = tex3DLod<float>(ts.vol, sx, sy, sz, (float)st.level0);
                                 if (st.frac != 0.0f) s = lerpf(s, tex3DLod<float>(ts.vol, sx, sy, sz, (float)(st.level0 + 1)), st.frac);
                             } else {
-                                const float sx = fmaf(st.height, dx, vx), sy = fmaf(st.height, dy, vy), sz = fmaf(st.height, dz, vz);
-                                s = sample_level(a, st.level0, sx, sy, sz);
-                                if (st.frac != 0.0f) s = lerpf(s, sample_level(a, st.level0 + 1, sx, sy, sz), st.frac);
+                                const float fd = (float)D;
+                                s = sample_level(a, st.level0, sx * fd, sy * fd, sz * fd);
+                                if (st.frac != 0.0f) s = lerpf(s, sample_level(a, st.level0 + 1, sx * fd, sy * fd, sz * fd), st.frac);
                             }
                             indirect = fmaf(s, st.weight, indirect);
                         }
                     }
                 }
-                if (tp.stats && shade) nCone += tp.nSteps;
+                if (kStats && shade) nCone += tp.nSteps;
                 if (tp.p.doNoiseSample) { col[0] *= indirect; col[1] *= indirect; col[2] *= indirect; }
                 else col[0] = col[1] = col[2] = col[3] = indirect;
             }
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
         }
     }
 
-    if (tp.stats) {
+    if (kStats) {
         for (int s = 16; s > 0; s >>= 1) {
             nFrag += __shfl_down_sync(0xFFFFFFFFu, nFrag, s);
             nCone += __shfl_down_sync(0xFFFFFFFFu, nCone, s);
@@ -393,13 +393,17 @@ int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol
     a.noise = reinterpret_cast<const float2 *>(noise);
     a.image = image; a.format = format; a.stats = stats;
     a.mask = (skipMask && tp.p.skipEmptySpace) ? skipMask : nullptr;
-    const float fd = (float)vol.dim;
-    a.volScale[0] = fd / (vol.xB[1] - vol.xB[0]);
-    a.volScale[1] = fd / (vol.yB[1] - vol.yB[0]);
-    a.volScale[2] = fd / (vol.zB[1] - vol.zB[0]);
+    a.invRange[0] = 1.0f / (vol.xB[1] - vol.xB[0]);
+    a.invRange[1] = 1.0f / (vol.yB[1] - vol.yB[0]);
+    a.invRange[2] = 1.0f / (vol.zB[1] - vol.zB[0]);
+    a.invDim = 1.0f / (float)vol.dim;
     TexSet none{};
-    if (ts && ts->enabled && tp.p.sampler == CRN_SAMPLER_TEXTURE) trace_kernel<true><<<b.tilesX * b.tilesY, 256, 0, st>>>(a, cam, tp, *ts);
-    else trace_kernel<false><<<b.tilesX * b.tilesY, 256, 0, st>>>(a, cam, tp, none);
+    const bool useTex = ts && ts->enabled && tp.p.sampler == CRN_SAMPLER_TEXTURE;
+    const int grid = b.tilesX * b.tilesY;
+    if (useTex && tp.stats) trace_kernel<true, true><<<grid, 256, 0, st>>>(a, cam, tp, *ts);
+    else if (useTex) trace_kernel<true, false><<<grid, 256, 0, st>>>(a, cam, tp, *ts);
+    else if (tp.stats) trace_kernel<false, true><<<grid, 256, 0, st>>>(a, cam, tp, none);
+    else trace_kernel<false, false><<<grid, 256, 0, st>>>(a, cam, tp, none);
     return 1;
 }
 
