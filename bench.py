@@ -100,6 +100,29 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def metric_name(config):
+    return "cone-traced frames/s @4K with 256^3 volume" if config in ("C3", "C5") else f"cone-traced frames/s ({config})"
+
+
+def workload_name(sc, config, radius_mode):
+    D, L, N, W, H = sc.CONFIGS[config]
+    return (f"{config}: {D}^3 R8 volume ({L} levels), {N} billboards ({radius_mode} radii), {W}x{H}, "
+            f"animated (one new frame per step), sun shadow cones 16 steps, noise 4 octaves")
+
+
+def ncu_traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu capture of the dominant kernel (per launch)"""
+    try:
+        tot = 0.0
+        for line in open(os.path.join(ROOT, "profiles", name)):
+            f = line.split()
+            if f and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(f[1]) * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}[f[2]]
+        return tot or None
+    except Exception:
+        return None
+
+
 def frame_inputs(sc, config, n_frames, rank, world):
     """billboard offsets for the frames this rank renders + the camera/sun of each"""
     base = sc.make_scene(config, cutoff=0.0)
@@ -157,7 +180,7 @@ def run_reference(args):
     vals = []
     cb = None
     for i in range(args.warmup + args.steps):
-        cb = cpu_baseline(args.config, orc, sc, budget_rows=8)
+        cb = cpu_baseline(args.config, orc, sc, budget_rows=32)
         if i >= args.warmup:
             vals.append(cb["value"])
         if i == 0 and 1.0 / cb["value"] > 60:        # keep the whole run within minutes
@@ -166,10 +189,12 @@ def run_reference(args):
     cb["value"] = v
     D, L, N, W, H = sc.CONFIGS[args.config]
     print(json.dumps({
-        "impl": "reference", "metric": "cone-traced frames/s", "value": v, "unit": "frames/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric_name(args.config), "value": v, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.config}: {D}^3 R8 volume, {N} billboards, {W}x{H}, CPU oracle (restated reference, not llvmpipe)"},
+        "config": {"workload": workload_name(sc, args.config, sc.make_scene(args.config).meta["radius_mode"]),
+                   "implementation": "CPU oracle: the reference's algorithm restated in C++/OpenMP (oracle/oracle.cpp), all host threads; "
+                                     "the reference's GL 4.4 executable cannot be built or run here (BASELINE.md 2), not llvmpipe"},
         "cpu_baseline": cb,
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -294,7 +319,13 @@ def main():
     st = r.trace_stats()
     r.set_stats(False)
     frag, cone, noise, bins = st.fragments, st.coneSamples, st.noiseSamples, st.binEntries
-    cone_skipped = st.coneSamplesSkipped
+    cone_skipped, fetches = st.coneSamplesSkipped, st.filteredFetches
+    tex_peak = None
+    if rank == 0 and args.sampler == "texture":
+        try:
+            tex_peak = min(pkg.microbench(0, local), pkg.microbench(1, local))     # G trilinear fetches/s, measured now
+        except Exception:
+            tex_peak = None
 
     if rank == 0:
         job_frames = K if slab_mode else world * K          # C4 shards ONE frame per step over all ranks
@@ -304,15 +335,15 @@ def main():
         # dominant kernel = cone trace.  ALGORITHMIC bytes per launch: every cone tap
         # reads 8 texels per level (16 when two levels blend), every noise tap 8 RGBA8 texels, plus the image.
         trace_ms = stage["traceMs"]
-        alg_bytes = cone * 16 * 1 + noise * 8 * 4 + Wd * Ht * 4
+        alg_bytes = (cone - cone_skipped) * 16 * 1 + noise * 8 * 4 + Wd * Ht * 4
         achieved = alg_bytes / (trace_ms * 1e-3) / 1e9
+        traffic = ncu_traffic("r01_trace_texture_final.txt" if args.sampler == "texture" else "r01_trace_explicit.txt")
         out = {
-            "metric": "cone-traced frames/s @4K with 256^3 volume" if args.config in ("C3", "C5") else f"cone-traced frames/s ({args.config})",
+            "metric": metric_name(args.config),
             "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "strong" if slab_mode else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": (f"{args.config}: {D}^3 R8 volume ({L} levels), {N} billboards ({frames[0].meta['radius_mode']} radii), {Wd}x{Ht}, "
-                             f"animated (one new frame per step), sun shadow cones 16 steps, noise 4 octaves"),
+                "workload": workload_name(sc, args.config, frames[0].meta['radius_mode']),
                 "sharding": ("Z-slab voxelize+mips, one all-gather of the finished chain (NCCL), tile-row-interleaved trace" if slab_mode else
                              "frames round-robin over ranks, volume replicated, no collective" if world > 1 else "single GPU"),
                 "transmittance_cutoff": args.cutoff, "sampler": args.sampler, "skip_empty_space": not args.no_skip,
@@ -325,9 +356,15 @@ def main():
             "per_frame": {"fragments_shaded": frag, "cone_samples": cone, "cone_samples_skipped_as_empty": cone_skipped,
                           "noise_samples": noise, "bin_entries": bins,
                           "cone_samples_per_s": cone / (trace_ms * 1e-3), "filtered_samples_per_s": (cone + noise) / (trace_ms * 1e-3)},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "trace_kernel", "peak_source": peak_src,
-                         "note": "texel bytes are served by L1/L2 (volume chain 19 MB, noise 256 KB): the binding ceiling is the L1 fetch rate, see DESIGN.md"},
+                         "note": ("algorithmic texel bytes (SURVEY 8d: 16 B per fetched cone sample, 32 B per noise tap, + the image) are served "
+                                  "by L1 at a 99.9% hit rate, so this fraction can exceed 1 and HBM is NOT the binding roof (traffic = DRAM bytes "
+                                  "of one ncu capture, profiles/); the binding roof is the texture pipe: see roofline_tex")},
+            "roofline_tex": None if not tex_peak else {
+                "bound": "tex", "achieved": fetches / (trace_ms * 1e-3) / 1e9, "peak": tex_peak, "unit": "G trilinear fetches/s",
+                "frac": fetches / (trace_ms * 1e-3) / 1e9 / tex_peak, "fetches_per_launch": fetches,
+                "peak_source": "crn_microbench tex3D trilinear (min of RGBA8 32^3 and R8 256^3), measured in this run"},
         }
         if not args.no_cpu_baseline and world == 1:
             orc = entry.import_oracle()

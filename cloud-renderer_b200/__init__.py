@@ -52,7 +52,7 @@ class TraceParams(C.Structure):
 
 
 class TraceStats(C.Structure):
-    _fields_ = [("fragments", u64), ("coneSamples", u64), ("noiseSamples", u64), ("binEntries", u64), ("coneSamplesSkipped", u64)]
+    _fields_ = [("fragments", u64), ("coneSamples", u64), ("noiseSamples", u64), ("binEntries", u64), ("coneSamplesSkipped", u64), ("filteredFetches", u64)]
 
 
 class Timings(C.Structure):

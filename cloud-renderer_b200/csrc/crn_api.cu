@@ -482,7 +482,7 @@ int enqueue_trace(crn_ctx *c, int format) {
         }
     }
     unsigned long long *dStats = (unsigned long long *)((char *)c->misc.p + 64);
-    if (c->statsOn) cudaMemsetAsync(dStats, 0, 4 * sizeof(unsigned long long), st);
+    if (c->statsOn) cudaMemsetAsync(dStats, 0, 8 * sizeof(unsigned long long), st);
     if (c->timingOn) cudaEventRecord(c->evT[0], st);
     const float zero3[3] = {0, 0, 0};
     c->launches += launch_prep_sort(st, (const float *)c->pos.p, (const float *)c->scale.p, n, c->vol.fluffiness, c->vol.position, cam,
@@ -498,7 +498,7 @@ int enqueue_trace(crn_ctx *c, int format) {
                                 (const uint8_t *)c->chain.p, (const int8_t *)c->noise.p, useTex ? &c->ts : nullptr,
                                 c->tp.skipEmptySpace ? (const uint32_t *)c->mask.p : nullptr, c->image.p, format, dStats);
     if (c->timingOn) { cudaEventRecord(c->evT[3], st); c->evTValid = true; }
-    if (c->statsOn) cudaMemcpyAsync(c->hStats, dStats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+    if (c->statsOn) cudaMemcpyAsync(c->hStats, dStats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
     CRN_CUDA(c, cudaGetLastError());
     return CRN_OK;
 }
@@ -538,9 +538,9 @@ int crn_create(int device, void *stream, crn_ctx **out) {
         c->ownStream = true;
     }
     cudaMallocHost(&c->hCursors, 4 * sizeof(uint32_t));
-    cudaMallocHost(&c->hStats, 4 * sizeof(unsigned long long));
+    cudaMallocHost(&c->hStats, 8 * sizeof(unsigned long long));
     std::memset(c->hCursors, 0, 4 * sizeof(uint32_t));
-    std::memset(c->hStats, 0, 4 * sizeof(unsigned long long));
+    std::memset(c->hStats, 0, 8 * sizeof(unsigned long long));
     for (auto &ev : c->evV) cudaEventCreate(&ev);
     for (auto &ev : c->evT) cudaEventCreate(&ev);
     crn_default_trace_params(&c->tp);
@@ -938,6 +938,7 @@ int crn_get_trace_stats(crn_ctx *c, crn_trace_stats *out) {
     out->fragments = c->hStats[0]; out->coneSamples = c->hStats[1]; out->noiseSamples = c->hStats[2];
     out->binEntries = c->hCursors[3];
     out->coneSamplesSkipped = c->hStats[3];
+    out->filteredFetches = c->hStats[4] + c->hStats[2];      // cone fetches + noise taps
     return CRN_OK;
 }
 

@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
 
     float C[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     float T = 1.0f;
-    unsigned long long nFrag = 0, nCone = 0, nNoise = 0, nSkip = 0;
+    unsigned long long nFrag = 0, nCone = 0, nNoise = 0, nSkip = 0, nFetch = 0;
 
     const uint32_t cnt = tp.active ? a.tileCnt[tile] : 0;
     const uint32_t off = cnt ? a.tileOff[tile] : 0;
@@ -324,6 +324,7 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
                                 if (st.frac != 0.0f) s = lerpf(s, sample_level(a, st.level0 + 1, sx * fd, sy * fd, sz * fd), st.frac);
                             }
                             indirect = fmaf(s, st.weight, indirect);
+                            if (kStats) nFetch += st.frac != 0.0f ? 2 : 1;
                         }
                     }
                 }
@@ -368,12 +369,14 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
             nCone += __shfl_down_sync(0xFFFFFFFFu, nCone, s);
             nNoise += __shfl_down_sync(0xFFFFFFFFu, nNoise, s);
             nSkip += __shfl_down_sync(0xFFFFFFFFu, nSkip, s);
+            nFetch += __shfl_down_sync(0xFFFFFFFFu, nFetch, s);
         }
         if (lane == 0) {
             if (nFrag) atomicAdd(&a.stats[0], nFrag);
             if (nCone) atomicAdd(&a.stats[1], nCone);
             if (nNoise) atomicAdd(&a.stats[2], nNoise);
             if (nSkip) atomicAdd(&a.stats[3], nSkip);
+            if (nFetch) atomicAdd(&a.stats[4], nFetch);
         }
     }
 }

@@ -140,6 +140,7 @@ typedef struct crn_trace_stats {
     uint64_t noiseSamples;     /* texture(noiseMap) taps taken by noise3D               */
     uint64_t binEntries;       /* (tile, billboard) pairs in the camera-space bins      */
     uint64_t coneSamplesSkipped; /* of coneSamples: proven zero by the empty-space masks, not fetched */
+    uint64_t filteredFetches;  /* trilinear fetches actually issued (noise taps + 1 or 2 per fetched cone sample) */
 } crn_trace_stats;
 
 /* Stage timings of the most recent frame, milliseconds, measured with CUDA events on
