@@ -141,6 +141,7 @@ def cpu_baseline(config, orc, sc, budget_rows=64):
     """The oracle on a bounded sample of one frame: voxelize + mips in full, the trace on every
     `stride`-th image row (an unbiased sample of the frame), extrapolated to the frame."""
     s = sc.make_scene(config, frame=1)
+    orc.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     t0 = time.perf_counter()
     _, _, l0 = orc.voxelize(s, want_posmap=False)
     t1 = time.perf_counter()

@@ -143,7 +143,7 @@ struct crn_ctx {
     size_t chainBytes = 0;
 
     DevBuf pos, scale, keyL, keyC, rankL, rankC, recTmpL, recTmpC, rectTmpL, rectTmpC, lbTmp, recL, recC, rectL, rectC,
-        lbSorted, drawOrder, bits, chain, noise, posmap, image, misc, maskNz, maskDil, mask, sortTmp;
+        lbSorted, drawOrder, bits, chain, noise, posmap, image, misc, maskNz, maskDil, mask, sortTmp, tileOrder;
     bool maskCurrent = false;
     Bins binsL, binsC;
     uint32_t *hCursors = nullptr;        // pinned: [0..1] light cursors, [2..3] camera cursors
@@ -466,6 +466,7 @@ int enqueue_trace(crn_ctx *c, int format) {
     const size_t texel = format == CRN_IMAGE_RGBA32F ? 16 : 4;
     if ((r = reserve(c, c->image, (size_t)c->W * c->H * texel))) return r;
     if ((r = ensure_bins(c, c->binsC, c->W, c->H, n))) return r;
+    if ((r = reserve(c, c->tileOrder, ((size_t)c->binsC.tilesX * c->binsC.tilesY + 66) * 4))) return r;
 
     TraceParams tp;
     build_trace_params(c, cam, &tp);
@@ -493,10 +494,12 @@ int enqueue_trace(crn_ctx *c, int format) {
     if (c->timingOn) cudaEventRecord(c->evT[1], st);
     c->launches += launch_bin(st, (const BoardRect *)c->rectC.p, sort_tmp_bounds(c->sortTmp.p, (int)nn, 1), n, c->W, c->H, c->binsC);
     cudaMemcpyAsync(c->hCursors + 2, c->binsC.cursors, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    c->launches += launch_tile_order(st, c->binsC, (uint32_t *)c->tileOrder.p);
     if (c->timingOn) cudaEventRecord(c->evT[2], st);
     c->launches += launch_trace(st, cam, c->vparams, tp, (const BoardRec *)c->recC.p, c->binsC, (const uint32_t *)c->bits.p,
                                 (const uint8_t *)c->chain.p, (const int8_t *)c->noise.p, useTex ? &c->ts : nullptr,
-                                c->tp.skipEmptySpace ? (const uint32_t *)c->mask.p : nullptr, c->image.p, format, dStats);
+                                c->tp.skipEmptySpace ? (const uint32_t *)c->mask.p : nullptr, (const uint32_t *)c->tileOrder.p,
+                                c->image.p, format, dStats);
     if (c->timingOn) { cudaEventRecord(c->evT[3], st); c->evTValid = true; }
     if (c->statsOn) cudaMemcpyAsync(c->hStats, dStats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
     CRN_CUDA(c, cudaGetLastError());
@@ -558,7 +561,7 @@ void crn_destroy(crn_ctx *c) {
     cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = {&c->pos, &c->scale, &c->keyL, &c->keyC, &c->rankL, &c->rankC, &c->recTmpL, &c->recTmpC, &c->rectTmpL,
                       &c->rectTmpC, &c->lbTmp, &c->recL, &c->recC, &c->rectL, &c->rectC, &c->lbSorted, &c->drawOrder, &c->bits,
-                      &c->chain, &c->noise, &c->posmap, &c->image, &c->misc, &c->maskNz, &c->maskDil, &c->mask, &c->sortTmp};
+                      &c->chain, &c->noise, &c->posmap, &c->image, &c->misc, &c->maskNz, &c->maskDil, &c->mask, &c->sortTmp, &c->tileOrder};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     free_bins(c->binsL); free_bins(c->binsC);
     free_vol_textures(c);

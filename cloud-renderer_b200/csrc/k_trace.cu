@@ -42,6 +42,7 @@ struct TraceArgs {
     float invRange[3];            // 1 / range per axis
     float invDim;                 // 1 / voxelDim
     const uint32_t *mask;         // empty-space masks M_l (k_skipmask.cu), or nullptr
+    const uint32_t *order;        // launch order of the tiles, longest list first (k_bin.cu)
 };
 
 // M_l at the level-l texel containing voxel-space point p: 0 => every filter footprint of the group is all-zero
@@ -169,7 +170,7 @@ __device__ __forceinline__ bool sun_fragment(const TraceParams &tp, const ViewPa
 template <bool kTex, bool kStats>
 __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ TraceArgs a, const __grid_constant__ ViewParams cam,
                                                     const __grid_constant__ TraceParams tp, const __grid_constant__ TexSet ts) {
-    const int tile = blockIdx.x;
+    const int tile = (int)a.order[blockIdx.x];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tx = tile % a.tilesX, ty = tile / a.tilesX;
     const int px = tx * kTile + (warp & 1) * 8 + (lane & 7);
@@ -385,8 +386,8 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
 
 int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol, const TraceParams &tp,
                  const BoardRec *recs, const Bins &b, const uint32_t *bits, const uint8_t *chain,
-                 const int8_t *noise, const TexSet *ts, const uint32_t *skipMask, void *image, int format,
-                 unsigned long long *stats) {
+                 const int8_t *noise, const TexSet *ts, const uint32_t *skipMask, const uint32_t *tileOrder, void *image,
+                 int format, unsigned long long *stats) {
     TraceArgs a;
     a.vol = vol;
     a.recs = recs;
@@ -396,6 +397,7 @@ int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol
     a.noise = reinterpret_cast<const float2 *>(noise);
     a.image = image; a.format = format; a.stats = stats;
     a.mask = (skipMask && tp.p.skipEmptySpace) ? skipMask : nullptr;
+    a.order = tileOrder;
     a.invRange[0] = 1.0f / (vol.xB[1] - vol.xB[0]);
     a.invRange[1] = 1.0f / (vol.yB[1] - vol.yB[0]);
     a.invRange[2] = 1.0f / (vol.zB[1] - vol.zB[0]);

@@ -59,6 +59,10 @@ def num_threads():
     return lib().orc_num_threads()
 
 
+def set_num_threads(n):
+    lib().orc_set_num_threads(int(n))
+
+
 def sun_update(vol, sun, derived_cls):
     out = derived_cls()
     lib().orc_sun_update(C.byref(vol), C.byref(sun), C.byref(out))

@@ -480,6 +480,15 @@ typedef struct orc_trace_stats {
     uint64_t fragments, coneSamples, noiseSamples, rectPixels;
 } orc_trace_stats;
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the baseline legs ask for every host core explicitly */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
