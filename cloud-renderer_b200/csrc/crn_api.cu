@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -145,6 +146,7 @@ struct crn_ctx {
     DevBuf pos, scale, keyL, keyC, rankL, rankC, recTmpL, recTmpC, rectTmpL, rectTmpC, lbTmp, recL, recC, rectL, rectC,
         lbSorted, drawOrder, bits, chain, noise, posmap, image, misc, maskNz, maskDil, mask, sortTmp, tileOrder;
     bool maskCurrent = false;
+    size_t poolMin = (size_t)1 << 20;    // initial bin-pool entries (CRN_BIN_POOL_MIN overrides: tests force the growth path)
     Bins binsL, binsC;
     uint32_t *hCursors = nullptr;        // pinned: [0..1] light cursors, [2..3] camera cursors
     unsigned long long *hStats = nullptr;
@@ -213,8 +215,9 @@ int ensure_bins(crn_ctx *c, Bins &b, int W, int H, int n) {
     }
     (void)coarse;
     if (!b.cursors) CRN_CUDA(c, cudaMalloc(&b.cursors, 2 * sizeof(uint32_t)));
-    int r = alloc_u32(c, b.coarseList, b.coarseCap, 4 * std::max<size_t>((size_t)1 << 16, (size_t)n * 8)); if (r) return r;   // uint4 entries
-    r = alloc_u32(c, b.tileList, b.tileCap, std::max<size_t>((size_t)1 << 20, (size_t)n * 96)); if (r) return r;
+    const bool forced = c->poolMin != ((size_t)1 << 20);
+    int r = alloc_u32(c, b.coarseList, b.coarseCap, 4 * (forced ? c->poolMin : std::max<size_t>((size_t)1 << 16, (size_t)n * 8))); if (r) return r;   // uint4 entries
+    r = alloc_u32(c, b.tileList, b.tileCap, forced ? c->poolMin : std::max<size_t>(c->poolMin, (size_t)n * 96)); if (r) return r;
     return CRN_OK;
 }
 
@@ -547,6 +550,7 @@ int crn_create(int device, void *stream, crn_ctx **out) {
     for (auto &ev : c->evV) cudaEventCreate(&ev);
     for (auto &ev : c->evT) cudaEventCreate(&ev);
     crn_default_trace_params(&c->tp);
+    if (const char *pm = getenv("CRN_BIN_POOL_MIN")) { const long v = atol(pm); if (v > 0) c->poolMin = (size_t)v; }
     if ((e = cudaGetLastError()) != cudaSuccess) {
         crn_destroy(c);
         return fail(nullptr, CRN_ERR_CUDA, "context set-up: %s", cudaGetErrorString(e));

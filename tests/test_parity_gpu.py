@@ -324,3 +324,99 @@ def test_empty_space_skipping_is_exact(name, pkg, scenes, orc, renderer):
         print(f"{name}/sampler{sampler}: {skipped[1]} of {st.coneSamples} cone samples skipped ({100.0 * skipped[1] / st.coneSamples:.1f} %)")
     renderer.set_stats(False)
     s.tp.skipEmptySpace = 1
+
+
+def test_error_paths(pkg, scenes):
+    """status codes instead of the reference's print-and-exit (src/main.cpp:63-67); nothing aborts, nothing computes on bad input"""
+    s = scenes.make_scene("tiny")
+    r = pkg.Renderer(0)
+
+    def code(fn, *a):
+        with pytest.raises(pkg.CrnError) as e:
+            fn(*a)
+        return e.value.code
+
+    assert code(r.voxelize) == pkg.CRN_ERR_STATE                                  # nothing set yet
+    bad = scenes.make_scene("tiny").vol
+    bad.dimension = 48
+    assert code(r.set_volume, bad) == pkg.CRN_ERR_UNSUPPORTED                      # not a power of two
+    bad.dimension, bad.levels = 32, 7
+    assert code(r.set_volume, bad) == pkg.CRN_ERR_INVALID_ARG                      # 32^3 has 6 levels
+    bad.levels = 4
+    bad.xBounds[:] = (5.0, -5.0)
+    assert code(r.set_volume, bad) == pkg.CRN_ERR_INVALID_ARG
+    bad.xBounds[:] = (-5.0, 5.0)
+    bad.format = pkg.VOLUME_R32F
+    assert code(r.set_volume, bad) == pkg.CRN_ERR_UNSUPPORTED
+    tp = pkg.default_trace_params()
+    tp.vctSteps = 1000
+    assert code(r.set_trace_params, tp) == pkg.CRN_ERR_UNSUPPORTED
+    tp = pkg.default_trace_params()
+    tp.transmittanceCutoff = 1.5
+    assert code(r.set_trace_params, tp) == pkg.CRN_ERR_INVALID_ARG
+    tp = pkg.default_trace_params()
+    tp.sampler = 9
+    assert code(r.set_trace_params, tp) == pkg.CRN_ERR_INVALID_ARG
+    assert code(r.set_window, 0, 10) == pkg.CRN_ERR_INVALID_ARG
+    assert code(r.set_window, 40000, 10) == pkg.CRN_ERR_INVALID_ARG
+    cam = scenes.make_scene("tiny").cam
+    cam.P[4] = 0.3                                                                 # skewed projection
+    assert code(r.set_camera, cam) == pkg.CRN_ERR_UNSUPPORTED
+    # a frame with the inputs arriving one by one
+    r.set_volume(s.vol); r.set_sun(s.sun); r.set_window(s.width, s.height)
+    r.set_billboards(s.board_pos, s.board_scale)
+    assert code(r.cone_trace) == pkg.CRN_ERR_STATE                                 # camera / noise / volume missing
+    r.set_camera(s.cam)
+    assert code(r.cone_trace) == pkg.CRN_ERR_STATE                                 # noise texture missing
+    r.set_noise(s.noise)
+    assert code(r.cone_trace) == pkg.CRN_ERR_STATE                                 # no crn_voxelize yet
+    assert code(r.read_volume, 0) == pkg.CRN_ERR_STATE
+    assert code(r.read_position_map) == pkg.CRN_ERR_STATE
+    assert code(r.set_z_slab, 0, 8) == pkg.CRN_ERR_INVALID_ARG                     # slabs are 16-slice aligned
+    assert code(r.set_z_slab, 16, 16) == pkg.CRN_ERR_INVALID_ARG
+    assert code(r.set_row_range, 5, 2) == pkg.CRN_ERR_INVALID_ARG
+    assert code(r.set_tile_row_interleave, 3, 3) == pkg.CRN_ERR_INVALID_ARG
+    r.voxelize()
+    assert code(r.read_volume, 9) == pkg.CRN_ERR_INVALID_ARG
+    assert code(r.finish_mips, 0) == pkg.CRN_ERR_INVALID_ARG
+    assert code(r.trace_stats) == pkg.CRN_ERR_STATE                                # stats were never enabled
+    img = r.cone_trace()                                                           # and now everything works
+    assert img.shape == (s.height, s.width, 4) and img[..., 3].min() > 0
+    with pytest.raises(pkg.CrnError):
+        pkg.Renderer(99)                                                           # no such device
+    r.close()
+
+
+def test_bin_pool_growth(pkg, scenes, orc):
+    """a scene whose bins do not fit the initial pools: the library grows them and re-runs the frame"""
+    import os
+    s = scenes.make_scene("C1", size=(1920, 1080), boards=4000, radius_mode="reference")     # big quads: ~650 k bin entries
+    os.environ["CRN_BIN_POOL_MIN"] = "4096"                                                 # start with pools far too small
+    try:
+        r = pkg.Renderer(0)
+    finally:
+        del os.environ["CRN_BIN_POOL_MIN"]
+    s.tp.sampler = pkg.SAMPLER_TEXTURE
+    s.tp.transmittanceCutoff = 1.0 / 256
+    r.set_scene(s)
+    r.voxelize()
+    img = r.cone_trace()
+    bins = r.read_bins(1)
+    rc = orc.board_rects(s, 1)
+    exp = sum((int(i1) // 16 - int(i0) // 16 + 1) * (int(j1) // 16 - int(j0) // 16 + 1) for i0, i1, j0, j1 in rc if i1 >= i0 and j1 >= j0)
+    assert int(bins["counts"].sum()) == exp and exp > 100 * 4096                 # far more than the initial pools
+    _, _, l0 = orc.voxelize(s, want_posmap=False)
+    assert np.array_equal(r.read_volume(0), l0)
+    assert img[540, 960, :3].astype(int).sum() != 51 + 77 + 128                    # the cloud covers the centre pixel
+    r.close()
+
+
+def test_many_frames_reuse_one_context(pkg, scenes, orc, renderer):
+    """animated billboards through one context: every frame's occupancy is exact (state from the
+    previous frame must not leak: cleared bitset, re-armed mip ticket, rebuilt masks)"""
+    for frame in (0, 3, 17, 4):
+        s = scenes.make_scene("small", frame=frame * 40)
+        renderer.set_scene(s)
+        renderer.voxelize()
+        _, _, l0 = orc.voxelize(s, want_posmap=False)
+        assert np.array_equal(renderer.read_chain(), orc.mips(l0, s.vol.levels)), f"frame {frame}"
