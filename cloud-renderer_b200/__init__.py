@@ -63,7 +63,8 @@ class Timings(C.Structure):
 EXPORTS = [
     "crn_create", "crn_destroy", "crn_last_error", "crn_sync", "crn_set_volume", "crn_set_billboards", "crn_set_sun",
     "crn_sun_update", "crn_set_camera", "crn_camera_update", "crn_set_window", "crn_set_trace_params",
-    "crn_default_trace_params", "crn_set_noise", "crn_build_noise", "crn_voxelize", "crn_cone_trace", "crn_set_row_range",
+    "crn_default_trace_params", "crn_set_noise", "crn_build_noise", "crn_voxelize", "crn_cone_trace", "crn_cone_trace_async",
+    "crn_wait_images", "crn_set_row_range",
     "crn_set_tile_row_interleave",
     "crn_set_z_slab", "crn_volume_level_ptr", "crn_volume_bits_ptr", "crn_finish_mips", "crn_read_volume",
     "crn_count_active_voxels", "crn_keep_position_map", "crn_read_position_map", "crn_read_sorted_order", "crn_read_bins",
@@ -105,6 +106,8 @@ def load_library():
     lib.crn_build_noise.argtypes = [vp, i32, vp]
     lib.crn_voxelize.argtypes = [vp]
     lib.crn_cone_trace.argtypes = [vp, vp, i32, i32]
+    lib.crn_cone_trace_async.argtypes = [vp, vp, i32]
+    lib.crn_wait_images.argtypes = [vp]
     lib.crn_set_row_range.argtypes = [vp, i32, i32]
     lib.crn_set_z_slab.argtypes = [vp, i32, i32]
     lib.crn_set_tile_row_interleave.argtypes = [vp, i32, i32]
@@ -252,6 +255,14 @@ class Renderer:
         p, m = _ptr(out)
         self._ck(self.lib.crn_cone_trace(self.h, p, m, fmt))
         return out
+
+    def cone_trace_async(self, out, fmt=IMAGE_RGBA8):
+        p, m = _ptr(out)
+        assert m == MEM_HOST
+        self._ck(self.lib.crn_cone_trace_async(self.h, p, fmt))
+
+    def wait_images(self):
+        self._ck(self.lib.crn_wait_images(self.h))
 
     def sync(self):
         self._ck(self.lib.crn_sync(self.h))

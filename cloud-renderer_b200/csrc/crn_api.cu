@@ -158,6 +158,14 @@ struct crn_ctx {
     TexSet ts{};
     bool texCurrent = false;             // the arrays hold the chain of the last voxelize
 
+    // pipelined read-back (crn_cone_trace_async): second image buffer, copy stream, frame/copy events
+    DevBuf image2;
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t evFrame[2] = {}, evCopy[2] = {};
+    cudaEvent_t evBin[2] = {};           // bin cursors ready (light, camera): their read-back rides the copy stream
+    bool copyPending[2] = {false, false};
+    int imgSel = 0;
+
     cudaEvent_t evV[5] = {}, evT[4] = {};
     bool evVValid = false, evTValid = false;
 };
@@ -184,6 +192,7 @@ int fail(crn_ctx *c, int code, const char *fmt, ...) {
 int reserve(crn_ctx *c, DevBuf &b, size_t bytes) {
     if (bytes <= b.cap) return CRN_OK;
     CRN_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->copyStream) CRN_CUDA(c, cudaStreamSynchronize(c->copyStream));
     if (b.p) CRN_CUDA(c, cudaFree(b.p));
     b.p = nullptr; b.cap = 0;
     const size_t want = bytes + bytes / 4 + 256;
@@ -214,7 +223,7 @@ int ensure_bins(crn_ctx *c, Bins &b, int W, int H, int n) {
         b.tilesAlloc = tiles;
     }
     (void)coarse;
-    if (!b.cursors) CRN_CUDA(c, cudaMalloc(&b.cursors, 2 * sizeof(uint32_t)));
+    if (!b.cursors) { CRN_CUDA(c, cudaMalloc(&b.cursors, 4 * sizeof(uint32_t))); CRN_CUDA(c, cudaMemsetAsync(b.cursors, 0, 4 * sizeof(uint32_t), c->stream)); }
     const bool forced = c->poolMin != ((size_t)1 << 20);
     int r = alloc_u32(c, b.coarseList, b.coarseCap, 4 * (forced ? c->poolMin : std::max<size_t>((size_t)1 << 16, (size_t)n * 8))); if (r) return r;   // uint4 entries
     r = alloc_u32(c, b.tileList, b.tileCap, forced ? c->poolMin : std::max<size_t>(c->poolMin, (size_t)n * 96)); if (r) return r;
@@ -373,7 +382,11 @@ int enqueue_voxelize(crn_ctx *c) {
                                     (float *)c->lbSorted.p, nullptr, c->sortTmp.p);
     if (c->timingOn) cudaEventRecord(c->evV[1], st);
     c->launches += launch_bin(st, (const BoardRect *)c->rectL.p, sort_tmp_bounds(c->sortTmp.p, (int)nn, 0), n, c->W, c->H, c->binsL);
-    cudaMemcpyAsync(c->hCursors, c->binsL.cursors, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    // read the cursors back on the copy stream: a D2H on the compute stream would queue behind an image copy in
+    // flight on the same copy engine and stall the kernels of this frame
+    cudaEventRecord(c->evBin[0], st);
+    cudaStreamWaitEvent(c->copyStream, c->evBin[0], 0);
+    cudaMemcpyAsync(c->hCursors, c->binsL.cursors, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->copyStream);
     if (c->timingOn) cudaEventRecord(c->evV[2], st);
     c->launches += launch_voxelize(st, light, c->vparams, sd.nearPlane, sd.clipDistance, (const BoardRec *)c->recL.p,
                                    (const float *)c->lbSorted.p, c->binsL, (uint32_t *)c->bits.p,
@@ -451,7 +464,8 @@ void build_trace_params(crn_ctx *c, const ViewParams &cam, TraceParams *tp) {
     }
 }
 
-int enqueue_trace(crn_ctx *c, int format) {
+int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
+    DevBuf &img = target ? *target : c->image;
     const int n = c->nBoards;
     const ViewParams cam = make_view(c->cam.P, c->cam.V, c->W, c->H);
     fill_vparams(c);
@@ -467,7 +481,7 @@ int enqueue_trace(crn_ctx *c, int format) {
     if ((r = reserve(c, c->sortTmp, sort_tmp_bytes((int)nn) + 128))) return r;
     if ((r = reserve(c, c->misc, 256))) return r;
     const size_t texel = format == CRN_IMAGE_RGBA32F ? 16 : 4;
-    if ((r = reserve(c, c->image, (size_t)c->W * c->H * texel))) return r;
+    if ((r = reserve(c, img, (size_t)c->W * c->H * texel))) return r;
     if ((r = ensure_bins(c, c->binsC, c->W, c->H, n))) return r;
     if ((r = reserve(c, c->tileOrder, ((size_t)c->binsC.tilesX * c->binsC.tilesY + 66) * 4))) return r;
 
@@ -496,13 +510,15 @@ int enqueue_trace(crn_ctx *c, int format) {
                                     (int32_t *)c->drawOrder.p, c->sortTmp.p);
     if (c->timingOn) cudaEventRecord(c->evT[1], st);
     c->launches += launch_bin(st, (const BoardRect *)c->rectC.p, sort_tmp_bounds(c->sortTmp.p, (int)nn, 1), n, c->W, c->H, c->binsC);
-    cudaMemcpyAsync(c->hCursors + 2, c->binsC.cursors, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    cudaEventRecord(c->evBin[1], st);
+    cudaStreamWaitEvent(c->copyStream, c->evBin[1], 0);
+    cudaMemcpyAsync(c->hCursors + 2, c->binsC.cursors, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->copyStream);
     c->launches += launch_tile_order(st, c->binsC, (uint32_t *)c->tileOrder.p);
     if (c->timingOn) cudaEventRecord(c->evT[2], st);
     c->launches += launch_trace(st, cam, c->vparams, tp, (const BoardRec *)c->recC.p, c->binsC, (const uint32_t *)c->bits.p,
                                 (const uint8_t *)c->chain.p, (const int8_t *)c->noise.p, useTex ? &c->ts : nullptr,
                                 c->tp.skipEmptySpace ? (const uint32_t *)c->mask.p : nullptr, (const uint32_t *)c->tileOrder.p,
-                                c->image.p, format, dStats);
+                                img.p, format, dStats);
     if (c->timingOn) { cudaEventRecord(c->evT[3], st); c->evTValid = true; }
     if (c->statsOn) cudaMemcpyAsync(c->hStats, dStats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
     CRN_CUDA(c, cudaGetLastError());
@@ -547,6 +563,12 @@ int crn_create(int device, void *stream, crn_ctx **out) {
     cudaMallocHost(&c->hStats, 8 * sizeof(unsigned long long));
     std::memset(c->hCursors, 0, 4 * sizeof(uint32_t));
     std::memset(c->hStats, 0, 8 * sizeof(unsigned long long));
+    cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking);
+    for (int k = 0; k < 2; k++) {
+        cudaEventCreateWithFlags(&c->evFrame[k], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c->evCopy[k], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c->evBin[k], cudaEventDisableTiming);
+    }
     for (auto &ev : c->evV) cudaEventCreate(&ev);
     for (auto &ev : c->evT) cudaEventCreate(&ev);
     crn_default_trace_params(&c->tp);
@@ -563,9 +585,10 @@ void crn_destroy(crn_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->copyStream) cudaStreamSynchronize(c->copyStream);
     DevBuf *bufs[] = {&c->pos, &c->scale, &c->keyL, &c->keyC, &c->rankL, &c->rankC, &c->recTmpL, &c->recTmpC, &c->rectTmpL,
                       &c->rectTmpC, &c->lbTmp, &c->recL, &c->recC, &c->rectL, &c->rectC, &c->lbSorted, &c->drawOrder, &c->bits,
-                      &c->chain, &c->noise, &c->posmap, &c->image, &c->misc, &c->maskNz, &c->maskDil, &c->mask, &c->sortTmp, &c->tileOrder};
+                      &c->chain, &c->noise, &c->posmap, &c->image, &c->image2, &c->misc, &c->maskNz, &c->maskDil, &c->mask, &c->sortTmp, &c->tileOrder};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     free_bins(c->binsL); free_bins(c->binsC);
     free_vol_textures(c);
@@ -575,6 +598,15 @@ void crn_destroy(crn_ctx *c) {
     if (c->hStats) cudaFreeHost(c->hStats);
     for (auto &ev : c->evV) if (ev) cudaEventDestroy(ev);
     for (auto &ev : c->evT) if (ev) cudaEventDestroy(ev);
+    if (c->copyStream) {
+        cudaStreamSynchronize(c->copyStream);
+        for (int k = 0; k < 2; k++) {
+            if (c->evFrame[k]) cudaEventDestroy(c->evFrame[k]);
+            if (c->evCopy[k]) cudaEventDestroy(c->evCopy[k]);
+            if (c->evBin[k]) cudaEventDestroy(c->evBin[k]);
+        }
+        cudaStreamDestroy(c->copyStream);
+    }
     if (c->ownStream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -583,6 +615,7 @@ int crn_sync(crn_ctx *c) {
     if (!c) return CRN_ERR_INVALID_ARG;
     CRN_CUDA(c, cudaSetDevice(c->device));
     CRN_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->copyStream) CRN_CUDA(c, cudaStreamSynchronize(c->copyStream));
     return CRN_OK;
 }
 
@@ -741,10 +774,38 @@ int crn_voxelize(crn_ctx *c) {
     return CRN_OK;
 }
 
+// the rows this context owns (row range / tile-row interleave) of `src` -> `out`
+static int copy_image(crn_ctx *c, void *out, cudaMemcpyKind kind, int format, const DevBuf &src, cudaStream_t st) {
+    const size_t texel = format == CRN_IMAGE_RGBA32F ? 16 : 4;
+    const int r0 = std::max(0, c->row0), r1 = std::min(c->H, c->row1);
+    const size_t rowB = (size_t)c->W * texel;
+    if (c->ilvCount > 1) {
+        // only the tile rows this context owns: one strided 2-D copy (+ the partial last tile row)
+        const int tilesY = (c->H + kTile - 1) / kTile;
+        for (int ty = c->ilvIndex; ty < tilesY;) {
+            const int full = (c->H - ty * kTile) / kTile > 0 ? ((c->H / kTile - 1 - ty) / c->ilvCount + 1) : 0;   // owned tile rows of full height
+            if (full > 0) {
+                const size_t off = (size_t)ty * kTile * rowB, pitch = (size_t)c->ilvCount * kTile * rowB;
+                CRN_CUDA(c, cudaMemcpy2DAsync((char *)out + off, pitch, (char *)src.p + off, pitch, (size_t)kTile * rowB, full, kind, st));
+                ty += full * c->ilvCount;
+            } else {
+                const size_t off = (size_t)ty * kTile * rowB;
+                CRN_CUDA(c, cudaMemcpyAsync((char *)out + off, (char *)src.p + off, (size_t)(c->H - ty * kTile) * rowB, kind, st));
+                ty += c->ilvCount;
+            }
+        }
+    } else if (r1 > r0) {
+        const size_t offB = (size_t)r0 * rowB, bytes = (size_t)(r1 - r0) * rowB;
+        CRN_CUDA(c, cudaMemcpyAsync((char *)out + offB, (char *)src.p + offB, bytes, kind, st));
+    }
+    return CRN_OK;
+}
+
 // make sure neither pass ran with a truncated bin pool; re-run what did
 static int settle(crn_ctx *c, bool haveTrace, int format) {
     for (int attempt = 0; attempt < 4; attempt++) {
         CRN_CUDA(c, cudaStreamSynchronize(c->stream));
+        CRN_CUDA(c, cudaStreamSynchronize(c->copyStream));         // the cursors travel on the copy stream
         bool grewL = false, grewC = false;
         int r;
         if (c->voxelized && (r = grow_if_overflowed(c, c->binsL, c->hCursors, &grewL))) return r;
@@ -766,33 +827,60 @@ int crn_cone_trace(crn_ctx *c, void *out, int32_t mem, int32_t format) {
         return r;
     if (!c->voxelized) return fail(c, CRN_ERR_STATE, "crn_voxelize has not produced a volume yet");
     CRN_CUDA(c, cudaSetDevice(c->device));
+    if (c->copyPending[0]) { CRN_CUDA(c, cudaStreamWaitEvent(c->stream, c->evCopy[0], 0)); c->copyPending[0] = false; }
     if ((r = enqueue_trace(c, format))) return r;
     if ((r = settle(c, true, format))) return r;
     c->traced = true;
-    const size_t texel = format == CRN_IMAGE_RGBA32F ? 16 : 4;
-    const int r0 = std::max(0, c->row0), r1 = std::min(c->H, c->row1);
-    const cudaMemcpyKind kind = mem == CRN_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
-    const size_t rowB = (size_t)c->W * texel;
-    if (c->ilvCount > 1) {
-        // only the tile rows this context owns: one strided 2-D copy (+ the partial last tile row)
-        const int tilesY = (c->H + kTile - 1) / kTile;
-        for (int ty = c->ilvIndex; ty < tilesY;) {
-            const int full = (c->H - ty * kTile) / kTile > 0 ? ((c->H / kTile - 1 - ty) / c->ilvCount + 1) : 0;   // owned tile rows of full height
-            if (full > 0) {
-                const size_t off = (size_t)ty * kTile * rowB, pitch = (size_t)c->ilvCount * kTile * rowB;
-                CRN_CUDA(c, cudaMemcpy2DAsync((char *)out + off, pitch, (char *)c->image.p + off, pitch, (size_t)kTile * rowB, full, kind, c->stream));
-                ty += full * c->ilvCount;
-            } else {
-                const size_t off = (size_t)ty * kTile * rowB;
-                CRN_CUDA(c, cudaMemcpyAsync((char *)out + off, (char *)c->image.p + off, (size_t)(c->H - ty * kTile) * rowB, kind, c->stream));
-                ty += c->ilvCount;
-            }
-        }
-    } else if (r1 > r0) {
-        const size_t offB = (size_t)r0 * rowB, bytes = (size_t)(r1 - r0) * rowB;
-        CRN_CUDA(c, cudaMemcpyAsync((char *)out + offB, (char *)c->image.p + offB, bytes, kind, c->stream));
-    }
+    if ((r = copy_image(c, out, mem == CRN_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, format, c->image, c->stream))) return r;
     if (mem == CRN_MEM_HOST) CRN_CUDA(c, cudaStreamSynchronize(c->stream));
+    return CRN_OK;
+}
+
+int crn_cone_trace_async(crn_ctx *c, void *out, int32_t format) {
+    if (!c || !out) return fail(c, CRN_ERR_INVALID_ARG, "out is NULL");
+    if (format != CRN_IMAGE_RGBA8 && format != CRN_IMAGE_RGBA32F) return fail(c, CRN_ERR_INVALID_ARG, "unknown image format %d", format);
+    int r;
+    if ((r = require(c, c->haveVol, "volume")) || (r = require(c, c->haveSun, "sun")) || (r = require(c, c->haveCam, "camera")) ||
+        (r = require(c, c->haveWindow, "window")) || (r = require(c, c->haveNoise, "noise texture")))
+        return r;
+    if (!c->voxelized) return fail(c, CRN_ERR_STATE, "crn_voxelize has not produced a volume yet");
+    CRN_CUDA(c, cudaSetDevice(c->device));
+    const int k = c->imgSel;
+    DevBuf &img = k ? c->image2 : c->image;
+    // the frame two calls ago was copied out of this buffer: the kernels must not overwrite it before that copy is done
+    if (c->copyPending[k]) CRN_CUDA(c, cudaStreamWaitEvent(c->stream, c->evCopy[k], 0));
+    if ((r = enqueue_trace(c, format, &img))) return r;
+    c->traced = true;
+    CRN_CUDA(c, cudaEventRecord(c->evFrame[k], c->stream));
+    CRN_CUDA(c, cudaStreamWaitEvent(c->copyStream, c->evFrame[k], 0));
+    if ((r = copy_image(c, out, cudaMemcpyDeviceToHost, format, img, c->copyStream))) return r;
+    CRN_CUDA(c, cudaEventRecord(c->evCopy[k], c->copyStream));
+    c->copyPending[k] = true;
+    c->imgSel ^= 1;
+    return CRN_OK;
+}
+
+int crn_wait_images(crn_ctx *c) {
+    if (!c) return CRN_ERR_INVALID_ARG;
+    CRN_CUDA(c, cudaSetDevice(c->device));
+    if (c->copyStream) CRN_CUDA(c, cudaStreamSynchronize(c->copyStream));
+    CRN_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->copyPending[0] = c->copyPending[1] = false;
+    // a frame enqueued without a host round trip may have run with a truncated bin pool: the kernels leave a sticky flag
+    bool overflow = false;
+    Bins *bins[2] = {&c->binsL, &c->binsC};
+    for (int p = 0; p < 2; p++) {
+        if (!bins[p]->cursors) continue;
+        uint32_t cur[4] = {0, 0, 0, 0};
+        CRN_CUDA(c, cudaMemcpy(cur, bins[p]->cursors, sizeof cur, cudaMemcpyDeviceToHost));
+        if (cur[2]) {
+            overflow = true;
+            CRN_CUDA(c, cudaMemset(bins[p]->cursors + 2, 0, sizeof(uint32_t)));
+            int r = alloc_u32(c, bins[p]->coarseList, bins[p]->coarseCap, 2 * std::max<size_t>(bins[p]->coarseCap, (size_t)cur[0] * 4)); if (r) return r;
+            r = alloc_u32(c, bins[p]->tileList, bins[p]->tileCap, 2 * std::max<size_t>(bins[p]->tileCap, (size_t)cur[1])); if (r) return r;
+        }
+    }
+    if (overflow) return fail(c, CRN_ERR_STATE, "a bin pool overflowed during asynchronous frames: their images are incomplete; the pools have been grown, re-submit");
     return CRN_OK;
 }
 
@@ -942,6 +1030,7 @@ int crn_get_trace_stats(crn_ctx *c, crn_trace_stats *out) {
     if (!c->traced || !c->statsOn) return fail(c, CRN_ERR_STATE, "enable crn_set_stats before crn_cone_trace");
     CRN_CUDA(c, cudaSetDevice(c->device));
     CRN_CUDA(c, cudaStreamSynchronize(c->stream));
+    CRN_CUDA(c, cudaStreamSynchronize(c->copyStream));
     out->fragments = c->hStats[0]; out->coneSamples = c->hStats[1]; out->noiseSamples = c->hStats[2];
     out->binEntries = c->hCursors[3];
     out->coneSamplesSkipped = c->hStats[3];

@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(kBinThreads) bin_kernel(BinArgs a) {
                     const uint32_t sb = atomicAdd(&a.cursors[0], buf);
                     const uint32_t k2 = sSegs;
                     if (k2 < kMaxSegs && (uint64_t)sb + buf <= a.coarseCap) { sSegBase[k2] = sb; sSegCnt[k2] = buf; sSegs = k2 + 1; }
-                    else sBad = 1;
+                    else { sBad = 1; atomicOr(&a.cursors[2], 1u); }           // sticky: survives until the host clears it
                 }
                 __syncthreads();                                   // buffer + segment visible
                 const uint32_t segBase = sBad ? 0u : sSegBase[sSegs - 1];
@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(kBinThreads) bin_kernel(BinArgs a) {
         b = __shfl_sync(0xFFFFFFFFu, b, 0);
         base[k] = b;
         fits[k] = !bad && (uint64_t)b + cnt[k] <= a.tileCap;
+        if (lane == 0 && tOk[k] && cnt[k] && !fits[k]) atomicOr(&a.cursors[2], 1u);
         if (lane == 0 && tOk[k]) {
             a.tileOff[tIdx[k]] = b;
             a.tileCnt[tIdx[k]] = fits[k] ? cnt[k] : 0;

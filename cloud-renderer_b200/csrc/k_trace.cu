@@ -168,7 +168,7 @@ __device__ __forceinline__ bool sun_fragment(const TraceParams &tp, const ViewPa
 
 // kTex = false: explicit filtering (CRN_SAMPLER_EXPLICIT);  kTex = true: texture units (CRN_SAMPLER_TEXTURE)
 template <bool kTex, bool kStats>
-__global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ TraceArgs a, const __grid_constant__ ViewParams cam,
+__global__ void __launch_bounds__(256, 4) trace_kernel(const __grid_constant__ TraceArgs a, const __grid_constant__ ViewParams cam,
                                                     const __grid_constant__ TraceParams tp, const __grid_constant__ TexSet ts) {
     const int tile = (int)a.order[blockIdx.x];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -207,6 +207,14 @@ int crn_voxelize(crn_ctx *ctx);
  * With mem == CRN_MEM_HOST the call returns after the copy has completed. */
 int crn_cone_trace(crn_ctx *ctx, void *out, int32_t mem, int32_t format);
 
+/* Pipelined read-back: like crn_cone_trace(ctx, out_host, CRN_MEM_HOST, format) but returns as soon as the
+ * frame and its device->host copy are enqueued.  The copy runs on a second stream and overlaps the next frame's
+ * kernels (the context double-buffers the device image), so up to two frames may be in flight.  `out_host` must
+ * stay valid — and should be pinned — until crn_wait_images() returns; that call also reports a bin-pool overflow
+ * of any frame since the last wait (CRN_ERR_STATE: the pools have been grown, re-submit those frames). */
+int crn_cone_trace_async(crn_ctx *ctx, void *out_host, int32_t format);
+int crn_wait_images(crn_ctx *ctx);
+
 /* ---- sharding hooks (multi-GPU; results are invariant to them) --------------------- */
 /* restrict crn_cone_trace to image rows [row0,row1); other rows of `out` are untouched */
 int crn_set_row_range(crn_ctx *ctx, int32_t row0, int32_t row1);

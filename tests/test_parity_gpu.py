@@ -420,3 +420,31 @@ def test_many_frames_reuse_one_context(pkg, scenes, orc, renderer):
         renderer.voxelize()
         _, _, l0 = orc.voxelize(s, want_posmap=False)
         assert np.array_equal(renderer.read_chain(), orc.mips(l0, s.vol.levels)), f"frame {frame}"
+
+
+def test_pipelined_readback_matches_synchronous(pkg, scenes, orc):
+    """crn_cone_trace_async + crn_wait_images deliver exactly the images crn_cone_trace does, frame after frame"""
+    import torch
+    r = pkg.Renderer(0)
+    frames = [scenes.make_scene("small", frame=40 * k) for k in range(5)]
+    for f in frames:
+        f.tp.sampler = pkg.SAMPLER_TEXTURE
+    r.set_scene(frames[0])
+    want = []
+    for f in frames:
+        r.set_billboards(f.board_pos, f.board_scale)
+        r.set_trace_params(f.tp)
+        r.voxelize()
+        want.append(r.cone_trace().copy())
+    outs = [torch.empty((frames[0].height, frames[0].width, 4), dtype=torch.uint8).pin_memory() for _ in frames]
+    for f, o in zip(frames, outs):
+        r.set_billboards(f.board_pos, f.board_scale)
+        r.set_trace_params(f.tp)
+        r.voxelize()
+        r.cone_trace_async(o.numpy())
+    r.wait_images()
+    for k, (w, o) in enumerate(zip(want, outs)):
+        assert np.array_equal(w, o.numpy()), f"frame {k} differs"
+    img = r.cone_trace()                       # the synchronous call still works after asynchronous ones
+    assert np.array_equal(img, want[-1])
+    r.close()
