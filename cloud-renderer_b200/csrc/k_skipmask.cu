@@ -77,19 +77,23 @@ __global__ void __launch_bounds__(256) dilate_kernel(MaskArgs a) {
     if (!locate(a, w, l, z, y, wx)) return;
     const int n = a.size[l], wpr = a.wpr[l];
     const uint32_t *src = (l == 0 ? a.bits : a.nz + a.off[l]);
-    uint32_t acc = 0;
+    // dilation commutes with OR: gather the 5x5 (y,z) rows first, spread along x once
+    uint32_t c = 0, lo = 0, hi = 0;
+    const bool hasLo = wx > 0, hasHi = wx + 1 < wpr;
     for (int dz = -2; dz <= 2; dz++) {
         const int zz = z + dz;
         if (zz < 0 || zz >= n) continue;
+#pragma unroll
         for (int dy = -2; dy <= 2; dy++) {
             const int yy = y + dy;
             if (yy < 0 || yy >= n) continue;
-            const uint32_t *row = src + ((size_t)zz * n + yy) * wpr;
-            const uint32_t c = row[wx];
-            const uint32_t lo = wx > 0 ? row[wx - 1] : 0u, hi = wx + 1 < wpr ? row[wx + 1] : 0u;
-            acc |= c | (c << 1) | (c << 2) | (c >> 1) | (c >> 2) | (lo >> 31) | (lo >> 30) | (hi << 31) | (hi << 30);
+            const uint32_t *row = src + ((size_t)zz * n + yy) * wpr + wx;
+            c |= row[0];
+            if (hasLo) lo |= row[-1];
+            if (hasHi) hi |= row[1];
         }
     }
+    uint32_t acc = c | (c << 1) | (c << 2) | (c >> 1) | (c >> 2) | (lo >> 31) | (lo >> 30) | (hi << 31) | (hi << 30);
     if (n < 32) acc &= (1u << n) - 1u;
     a.dil[w] = acc;
 }

@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(256) voxelize_kernel(VoxArgs a, ViewParams lp)
     const float xv = (ndcx - lp.P[12]) / lp.P[0];
     const float yv = (ndcy - lp.P[13]) / lp.P[5];
 
+    const float invClip = 1.0f / a.clip;
     float best = valid ? 1.0f : -1.0f;                          // depth clear value; dead lanes never block the vote
     int bestIdx = -1;
     float wx = 0.0f, wy = 0.0f, wz = 0.0f;
@@ -72,6 +73,18 @@ __global__ void __launch_bounds__(256) voxelize_kernel(VoxArgs a, ViewParams lp)
         const float radius = r0.w;
         const float u = xv - r1.x, v = yv - r1.y;
         if (!(fabsf(u) < radius && fabsf(v) < radius) || !(lbk < best)) continue;
+        {   // cheap conservative filter (MUFU maths, relative error < 1e-5) before the exact IEEE evaluation:
+            // only candidates that are neither surely discarded nor surely behind the current winner go on
+            const float r2 = radius * radius, h2 = r2 - (u * u + v * v);
+            if (h2 < 0.9e-4f * r2) continue;                    // sphereContrib < 0.01 with margin: discarded for sure
+            const float hh = h2 * rsqrtf(h2);                   // ~ radius * sphereContrib
+            const float ax = (r0.x - a.nearPlane[0]) + (u * lp.right[0] + v * lp.up[0]) + lp.nrm[0] * hh;
+            const float ay = (r0.y - a.nearPlane[1]) + (u * lp.right[1] + v * lp.up[1]) + lp.nrm[1] * hh;
+            const float az = (r0.z - a.nearPlane[2]) + (u * lp.right[2] + v * lp.up[2]) + lp.nrm[2] * hh;
+            const float q2 = ax * ax + ay * ay + az * az;
+            const float dApprox = q2 * rsqrtf(q2) * invClip;
+            if (dApprox > best * 1.0001f + 1.0e-6f) continue;   // cannot win (ties included) even with the error margin
+        }
         // fragPos: interpolated quad position at this texel centre
         const float fx = r0.x + (u * lp.right[0] + v * lp.up[0]);
         const float fy = r0.y + (u * lp.right[1] + v * lp.up[1]);
