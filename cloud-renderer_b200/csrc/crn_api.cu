@@ -811,6 +811,9 @@ static int settle(crn_ctx *c, bool haveTrace, int format) {
         if (c->voxelized && (r = grow_if_overflowed(c, c->binsL, c->hCursors, &grewL))) return r;
         if (haveTrace && (r = grow_if_overflowed(c, c->binsC, c->hCursors + 2, &grewC))) return r;
         if (!grewL && !grewC) return CRN_OK;
+        // the truncated attempt left the sticky overflow flag behind; this frame is being redone, so clear it
+        if (grewL) CRN_CUDA(c, cudaMemsetAsync(c->binsL.cursors + 2, 0, sizeof(uint32_t), c->stream));
+        if (grewC) CRN_CUDA(c, cudaMemsetAsync(c->binsC.cursors + 2, 0, sizeof(uint32_t), c->stream));
         if (grewL && (r = enqueue_voxelize(c))) return r;
         if (haveTrace && (r = enqueue_trace(c, format))) return r;
     }

@@ -408,6 +408,12 @@ def test_bin_pool_growth(pkg, scenes, orc):
     _, _, l0 = orc.voxelize(s, want_posmap=False)
     assert np.array_equal(r.read_volume(0), l0)
     assert img[540, 960, :3].astype(int).sum() != 51 + 77 + 128                    # the cloud covers the centre pixel
+    # the overflow handled above must not haunt a later pipelined frame
+    import torch
+    out = torch.empty((s.height, s.width, 4), dtype=torch.uint8).pin_memory()
+    r.cone_trace_async(out.numpy())
+    r.wait_images()
+    assert np.array_equal(out.numpy(), img)
     r.close()
 
 
