@@ -226,7 +226,8 @@ int ensure_bins(crn_ctx *c, Bins &b, int W, int H, int n) {
     if (!b.cursors) { CRN_CUDA(c, cudaMalloc(&b.cursors, 4 * sizeof(uint32_t))); CRN_CUDA(c, cudaMemsetAsync(b.cursors, 0, 4 * sizeof(uint32_t), c->stream)); }
     const bool forced = c->poolMin != ((size_t)1 << 20);
     int r = alloc_u32(c, b.coarseList, b.coarseCap, 4 * (forced ? c->poolMin : std::max<size_t>((size_t)1 << 16, (size_t)n * 8))); if (r) return r;   // uint4 entries
-    r = alloc_u32(c, b.tileList, b.tileCap, forced ? c->poolMin : std::max<size_t>(c->poolMin, (size_t)n * 96)); if (r) return r;
+    // first guess: ~100 tiles per billboard, or 32 entries per tile, whichever is larger; grown on demand
+    r = alloc_u32(c, b.tileList, b.tileCap, forced ? c->poolMin : std::max<size_t>(std::max<size_t>(c->poolMin, (size_t)n * 96), tiles * 32)); if (r) return r;
     return CRN_OK;
 }
 
@@ -298,7 +299,8 @@ int ensure_vol_textures(crn_ctx *c) {
 
 int check_volume(crn_ctx *c, const crn_volume_desc *d) {
     const int D = d->dimension;
-    if (D < 32 || D > 2048 || (D & (D - 1))) return fail(c, CRN_ERR_UNSUPPORTED, "dimension %d: need a power of two in [32, 2048]", D);
+    // 1024^3 R8 + mips = 1.23 GB: level offsets are 32-bit
+    if (D < 32 || D > 1024 || (D & (D - 1))) return fail(c, CRN_ERR_UNSUPPORTED, "dimension %d: need a power of two in [32, 1024]", D);
     int maxL = 1; for (int s = D; s > 1; s >>= 1) maxL++;
     if (d->levels < 1 || d->levels > maxL || d->levels > kMaxLevels) return fail(c, CRN_ERR_INVALID_ARG, "levels %d out of range [1,%d]", d->levels, maxL);
     if (!(d->xBounds[1] > d->xBounds[0] && d->yBounds[1] > d->yBounds[0] && d->zBounds[1] > d->zBounds[0]))
@@ -611,9 +613,12 @@ void crn_destroy(crn_ctx *c) {
     delete c;
 }
 
+static int settle(crn_ctx *c, bool haveTrace, int format);
+
 int crn_sync(crn_ctx *c) {
     if (!c) return CRN_ERR_INVALID_ARG;
     CRN_CUDA(c, cudaSetDevice(c->device));
+    if (c->voxelized) return settle(c, false, 0);           // also re-runs a voxelize whose bin pool was too small
     CRN_CUDA(c, cudaStreamSynchronize(c->stream));
     if (c->copyStream) CRN_CUDA(c, cudaStreamSynchronize(c->copyStream));
     return CRN_OK;
@@ -771,6 +776,9 @@ int crn_voxelize(crn_ctx *c) {
     if ((r = require(c, c->haveVol, "volume")) || (r = require(c, c->haveSun, "sun")) || (r = require(c, c->haveWindow, "window"))) return r;
     CRN_CUDA(c, cudaSetDevice(c->device));
     if ((r = enqueue_voxelize(c))) return r;
+    // A slab is about to be handed to an exchange this library does not see (crn_volume_level_ptr + an external
+    // all-gather): it must be final when the call returns, so the bin-pool check cannot be deferred here.
+    if (c->z1 >= 0 && !(c->z0 == 0 && c->z1 == c->vol.dimension)) return settle(c, false, 0);
     return CRN_OK;
 }
 

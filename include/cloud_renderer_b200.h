@@ -223,9 +223,11 @@ int crn_set_row_range(crn_ctx *ctx, int32_t row0, int32_t row1);
 int crn_set_tile_row_interleave(crn_ctx *ctx, int32_t index, int32_t count);
 /* restrict crn_voxelize to voxel slices z in [z0,z1): only those slices of every
  * slab-local level are produced (levels whose texel spans more than the slab are left
- * for crn_finish_mips after the exchange) */
+ * for crn_finish_mips after the exchange).  With a slab set, crn_voxelize returns only
+ * once the slab is final (it synchronises), so the caller may exchange it right away. */
 int crn_set_z_slab(crn_ctx *ctx, int32_t z0, int32_t z1);
-/* device address + byte size of one level of the chain (for an external all-gather) */
+/* device address + byte size of one level of the chain (for an external all-gather); the contents are final after
+ * crn_sync (or after crn_voxelize itself when a Z-slab is set) */
 int crn_volume_level_ptr(crn_ctx *ctx, int32_t level, void **dev_ptr, size_t *bytes);
 /* device address + size of the level-0 occupancy bitset (1 bit per voxel, x-fastest) */
 int crn_volume_bits_ptr(crn_ctx *ctx, void **dev_ptr, size_t *bytes);
