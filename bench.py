@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--cutoff", type=float, default=CUTOFF)
     ap.add_argument("--sampler", default="texture", choices=["texture", "explicit"])
     ap.add_argument("--no-skip", action="store_true", help="fetch every cone sample (no empty-space skipping)")
+    ap.add_argument("--slab-exchange", default="chain", choices=["chain", "none"],
+                    help="C4 with N>1: 'chain' = Z-slab voxelize+mips and ONE all-gather of the finished chain (north_star); "
+                         "'none' = every rank voxelizes the whole volume (no collective), only the trace is sharded")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="back-to-back steps (no L2 flush between them)")
     return ap.parse_args()
@@ -246,14 +249,16 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     slab_mode = args.config == "C4" and world > 1
+    gather_mode = slab_mode and args.slab_exchange == "chain"
     if slab_mode:
+        r.set_tile_row_interleave(rank, world)              # balanced: 16-row tile rows dealt round-robin
+    if gather_mode:
         # C4: ONE frame per step for the whole job.  Every rank voxelizes + mips its Z-slab, one
         # all-gather of the finished slab-local levels, replicated top levels, then each rank traces
         # its band of image rows (no image gather: the bands stay on their GPUs).
         from cloud_renderer_b200 import sharding as sh
         z0, z1 = sh.z_slab(D, rank, world)
         r.set_z_slab(z0, z1)
-        r.set_tile_row_interleave(rank, world)              # balanced: 16-row tile rows dealt round-robin
         r.voxelize()                                        # allocates bits + chain
         torch.cuda.synchronize()
         tens = sh.chain_tensors(torch, r, L, dev)
@@ -268,7 +273,7 @@ def main():
         else:
             r.set_billboards(d_pos[i], d_scale)
         r.voxelize()
-        if slab_mode:
+        if gather_mode:
             sh.all_gather_levels(dist, views)
             if L > nloc:
                 r.finish_mips(nloc)
@@ -318,7 +323,7 @@ def main():
         r.set_camera(f.cam); r.set_sun(f.sun); r.set_trace_params(f.tp)
         r.set_billboards(h_pos[i].numpy(), h_scale.numpy())
         r.voxelize()
-        if slab_mode:
+        if gather_mode:
             sh.all_gather_levels(dist, views)
             if L > nloc:
                 r.finish_mips(nloc)
@@ -380,7 +385,8 @@ def main():
             "higher_is_better": True, "scaling": "strong" if slab_mode else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": workload_name(sc, args.config, frames[0].meta['radius_mode']),
-                "sharding": ("Z-slab voxelize+mips, one all-gather of the finished chain (NCCL), tile-row-interleaved trace" if slab_mode else
+                "sharding": ("Z-slab voxelize+mips, one all-gather of the finished chain (NCCL), tile-row-interleaved trace" if gather_mode else
+                             "voxelize+mips replicated on every rank (no collective), tile-row-interleaved trace" if slab_mode else
                              "frames round-robin over ranks, volume replicated, no collective" if world > 1 else "single GPU"),
                 "transmittance_cutoff": args.cutoff, "sampler": args.sampler, "skip_empty_space": not args.no_skip,
                 "l2": "none (back to back)" if args.no_flush else "256 MiB fill between steps, outside the per-step event pairs",
