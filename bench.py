@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--slab-exchange", default="chain", choices=["chain", "none"],
                     help="C4 with N>1: 'chain' = Z-slab voxelize+mips and ONE all-gather of the finished chain (north_star); "
                          "'none' = every rank voxelizes the whole volume (no collective), only the trace is sharded")
+    ap.add_argument("--volume-format", default="r8", choices=["r8", "r32f"], help="r8 = the shipped reference format")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="back-to-back steps (no L2 flush between them)")
     return ap.parse_args()
@@ -236,6 +237,7 @@ def main():
         f.tp.transmittanceCutoff = args.cutoff
         f.tp.sampler = pkg.SAMPLER_TEXTURE if args.sampler == "texture" else pkg.SAMPLER_EXPLICIT
         f.tp.skipEmptySpace = 0 if args.no_skip else 1
+        f.vol.format = pkg.VOLUME_R32F if args.volume_format == "r32f" else pkg.VOLUME_R8
     r.set_scene(frames[0])
 
     # resident inputs (value leg) and pinned host inputs (e2e leg)
@@ -389,6 +391,7 @@ def main():
                              "voxelize+mips replicated on every rank (no collective), tile-row-interleaved trace" if slab_mode else
                              "frames round-robin over ranks, volume replicated, no collective" if world > 1 else "single GPU"),
                 "transmittance_cutoff": args.cutoff, "sampler": args.sampler, "skip_empty_space": not args.no_skip,
+                "volume_format": args.volume_format,
                 "l2": "none (back to back)" if args.no_flush else "256 MiB fill between steps, outside the per-step event pairs",
             },
             "clocks": clocks,

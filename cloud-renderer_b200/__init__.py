@@ -293,7 +293,7 @@ class Renderer:
     # ---- inspection
     def read_volume(self, level=0):
         s = max(1, self.vol.dimension >> level)
-        out = np.empty((s, s, s), dtype=np.uint8)
+        out = np.empty((s, s, s), dtype=np.float32 if self.vol.format == VOLUME_R32F else np.uint8)
         self._ck(self.lib.crn_read_volume(self.h, level, out.ctypes.data))
         return out
 

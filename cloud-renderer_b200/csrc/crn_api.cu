@@ -153,7 +153,7 @@ struct crn_ctx {
 
     // texture-unit copies (CRN_SAMPLER_TEXTURE)
     cudaMipmappedArray_t volArray = nullptr;
-    int volArrayDim = 0, volArrayLevels = 0;
+    int volArrayDim = 0, volArrayLevels = 0, volArrayFormat = -1;
     cudaArray_t noiseArray = nullptr;
     TexSet ts{};
     bool texCurrent = false;             // the arrays hold the chain of the last voxelize
@@ -260,17 +260,20 @@ void free_vol_textures(crn_ctx *c) {
     if (c->ts.vol) cudaDestroyTextureObject(c->ts.vol);
     c->ts.vol = 0;
     if (c->volArray) cudaFreeMipmappedArray(c->volArray);
-    c->volArray = nullptr; c->volArrayDim = c->volArrayLevels = 0; c->ts.enabled = 0; c->texCurrent = false;
+    c->volArray = nullptr; c->volArrayDim = c->volArrayLevels = 0; c->volArrayFormat = -1; c->ts.enabled = 0; c->texCurrent = false;
 }
 
 // the R8 immutable 3D texture with `levels` mips of the reference (src/CloudVolume.cpp:18-23):
 // LINEAR within a level, CLAMP_TO_EDGE x3; the mip-linear blend is done in the kernel.
 int ensure_vol_textures(crn_ctx *c) {
     const int D = c->vol.dimension, L = c->vol.levels;
-    if (c->volArray && c->volArrayDim == D && c->volArrayLevels == L) return CRN_OK;
+    const bool f32 = c->vol.format == CRN_VOLUME_R32F;
+    if (c->volArray && c->volArrayDim == D && c->volArrayLevels == L && c->volArrayFormat == c->vol.format) return CRN_OK;
     CRN_CUDA(c, cudaStreamSynchronize(c->stream));
     free_vol_textures(c);
-    cudaChannelFormatDesc cd = cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned);
+    cudaChannelFormatDesc cd = f32 ? cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat)
+                                   : cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned);
+    const cudaTextureReadMode readMode = f32 ? cudaReadModeElementType : cudaReadModeNormalizedFloat;
     CRN_CUDA(c, cudaMallocMipmappedArray(&c->volArray, &cd, make_cudaExtent(D, D, D), L, cudaArraySurfaceLoadStore));
     for (int l = 0; l < L; l++) {
         cudaArray_t lvl = nullptr;
@@ -280,7 +283,7 @@ int ensure_vol_textures(crn_ctx *c) {
         CRN_CUDA(c, cudaCreateSurfaceObject(&c->ts.surf[l], &rd));
         cudaTextureDesc td{};
         td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
-        td.filterMode = cudaFilterModeLinear; td.readMode = cudaReadModeNormalizedFloat; td.normalizedCoords = 1;
+        td.filterMode = cudaFilterModeLinear; td.readMode = readMode; td.normalizedCoords = 1;
         CRN_CUDA(c, cudaCreateTextureObject(&c->ts.tex[l], &rd, &td, nullptr));
     }
     {   // one object over the whole chain for tex3DLod: LINEAR inside a level, POINT between levels
@@ -289,11 +292,11 @@ int ensure_vol_textures(crn_ctx *c) {
         cudaTextureDesc td{};
         td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
         td.filterMode = cudaFilterModeLinear; td.mipmapFilterMode = cudaFilterModePoint;
-        td.readMode = cudaReadModeNormalizedFloat; td.normalizedCoords = 1;
+        td.readMode = readMode; td.normalizedCoords = 1;
         td.minMipmapLevelClamp = 0.0f; td.maxMipmapLevelClamp = (float)(L - 1);
         CRN_CUDA(c, cudaCreateTextureObject(&c->ts.vol, &rd, &td, nullptr));
     }
-    c->volArrayDim = D; c->volArrayLevels = L; c->ts.enabled = 1; c->texCurrent = false;
+    c->volArrayDim = D; c->volArrayLevels = L; c->volArrayFormat = c->vol.format; c->ts.enabled = 1; c->texCurrent = false;
     return CRN_OK;
 }
 
@@ -305,7 +308,8 @@ int check_volume(crn_ctx *c, const crn_volume_desc *d) {
     if (d->levels < 1 || d->levels > maxL || d->levels > kMaxLevels) return fail(c, CRN_ERR_INVALID_ARG, "levels %d out of range [1,%d]", d->levels, maxL);
     if (!(d->xBounds[1] > d->xBounds[0] && d->yBounds[1] > d->yBounds[0] && d->zBounds[1] > d->zBounds[0]))
         return fail(c, CRN_ERR_INVALID_ARG, "bounds must satisfy min < max on every axis");
-    if (d->format != CRN_VOLUME_R8) return fail(c, CRN_ERR_UNSUPPORTED, "volume format %d: the render path is R8 (the shipped reference format)", d->format);
+    if (d->format != CRN_VOLUME_R8 && d->format != CRN_VOLUME_R32F) return fail(c, CRN_ERR_UNSUPPORTED, "unknown volume format %d", d->format);
+    if (d->format == CRN_VOLUME_R32F && D > 512) return fail(c, CRN_ERR_UNSUPPORTED, "R32F volumes are limited to 512^3 (32-bit level offsets)");
     return CRN_OK;
 }
 
@@ -319,11 +323,12 @@ void fill_vparams(crn_ctx *c) {
     const float fd = (float)d.dimension;
     const float rx = d.xBounds[1] - d.xBounds[0], ry = d.yBounds[1] - d.yBounds[0], rz = d.zBounds[1] - d.zBounds[0];
     v.stepSize = fminf(rx / fd, fminf(ry / fd, rz / fd));          // src/Shaders/VoxelizeShader.cpp:128
+    v.texelBytes = d.format == CRN_VOLUME_R32F ? 4 : 1;
     size_t off = 0; int s = d.dimension;
     for (int l = 0; l < kMaxLevels; l++) { v.levelOff[l] = 0; v.levelSize[l] = 0; }
     for (int l = 0; l < d.levels; l++) {
         v.levelOff[l] = (uint32_t)off; v.levelSize[l] = s;
-        off += ((size_t)s * s * s + 255) / 256 * 256;
+        off += ((size_t)s * s * s * v.texelBytes + 255) / 256 * 256;
         s = std::max(1, s / 2);
     }
     c->chainBytes = off;
@@ -643,7 +648,7 @@ void crn_default_trace_params(crn_trace_params *p) {          // src/Shaders/Con
 int crn_set_volume(crn_ctx *c, const crn_volume_desc *d) {
     if (!c || !d) return CRN_ERR_INVALID_ARG;
     int r = check_volume(c, d); if (r) return r;
-    if (c->haveVol && (c->vol.dimension != d->dimension || c->vol.levels != d->levels)) { c->voxelized = false; c->z1 = -1; c->z0 = 0; }
+    if (c->haveVol && (c->vol.dimension != d->dimension || c->vol.levels != d->levels || c->vol.format != d->format)) { c->voxelized = false; c->z1 = -1; c->z0 = 0; }
     c->vol = *d; c->haveVol = true;
     return CRN_OK;
 }
@@ -924,7 +929,7 @@ int crn_volume_level_ptr(crn_ctx *c, int32_t level, void **dev_ptr, size_t *byte
     if ((r = reserve(c, c->chain, c->chainBytes))) return r;
     const size_t s = c->vparams.levelSize[level];
     *dev_ptr = (char *)c->chain.p + c->vparams.levelOff[level];
-    *bytes = s * s * s;
+    *bytes = s * s * s * c->vparams.texelBytes;
     return CRN_OK;
 }
 
@@ -958,7 +963,8 @@ int crn_read_volume(crn_ctx *c, int32_t level, void *dst) {
     CRN_CUDA(c, cudaSetDevice(c->device));
     int r = settle(c, false, 0); if (r) return r;
     const size_t s = c->vparams.levelSize[level];
-    CRN_CUDA(c, cudaMemcpyAsync(dst, (char *)c->chain.p + c->vparams.levelOff[level], s * s * s, cudaMemcpyDeviceToHost, c->stream));
+    CRN_CUDA(c, cudaMemcpyAsync(dst, (char *)c->chain.p + c->vparams.levelOff[level], s * s * s * c->vparams.texelBytes, cudaMemcpyDeviceToHost,
+                                c->stream));
     CRN_CUDA(c, cudaStreamSynchronize(c->stream));
     return CRN_OK;
 }

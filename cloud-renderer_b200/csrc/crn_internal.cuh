@@ -48,6 +48,7 @@ struct VolumeParams {                 // uniforms of VoxelizeShader::bindVolume 
     uint32_t levelOff[kMaxLevels];    // byte offset of each level in the chain buffer
     int32_t levelSize[kMaxLevels];
     int32_t z0, z1;                   // slab (voxel slices) this context owns
+    int32_t texelBytes;               // 1: R8 (UNORM8, re-quantised mips)   4: R32F (float mips)
 };
 
 struct ConeStep {                     // traceCone's per-step constants (identical for every fragment)

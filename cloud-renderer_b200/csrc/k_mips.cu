@@ -181,6 +181,118 @@ __global__ void __launch_bounds__(256) mip_chain_kernel(MipArgs a) {
     if (tid == 0) *a.ticket = 0;                         // re-arm for the next frame
 }
 
+// ---- R32F variant (CRN_VOLUME_R32F): level 0 = 0.0/1.0, every coarser texel the plain mean of its 8 children ----
+// Same brick decomposition; this kernel is write-bound for real (4 B/voxel: 64 MB of level 0 at 256^3, 512 MB at 512^3).
+template <int WX>
+__global__ void __launch_bounds__(256) mip_chain_f32_kernel(MipArgs a) {
+    constexpr int BX = WX * 32;
+    __shared__ uint32_t sBits[256 * WX];
+    __shared__ float sL1[(BX / 2) * 8 * 8];
+    __shared__ float sL2[(BX / 4) * 4 * 4];
+    __shared__ float sL3[(BX / 8) * 2 * 2];
+    __shared__ float sL4[(BX / 16)];
+    __shared__ uint32_t sLast;
+    const int D = a.vol.dim, L = a.vol.levels;
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * BX, y0 = blockIdx.y * 16, z0 = (blockIdx.z + a.zBrick0) * 16;
+    const int wordsPerRow = D >> 5;
+    float *chain = reinterpret_cast<float *>(a.chain);
+    auto level = [&](int l) { return chain + a.vol.levelOff[l] / 4; };
+    {
+        const int y = tid & 15, z = tid >> 4;
+        const uint32_t *src = a.bits + ((size_t)(z0 + z) * D + (y0 + y)) * wordsPerRow + (x0 >> 5);
+#pragma unroll
+        for (int w = 0; w < WX; w++) sBits[tid * WX + w] = __ldg(src + w);
+    }
+    __syncthreads();
+    if (a.writeLevel0) {            // 4 voxels -> one 128-bit store; a warp writes 512 contiguous bytes
+        float *l0 = level(0);
+        constexpr int QUADS = BX / 4;                       // float4 per row
+        for (int s = tid; s < 256 * QUADS; s += 256) {
+            const int row = s / QUADS, q = s % QUADS;
+            const uint32_t nib = (sBits[row * WX + (q >> 3)] >> ((q & 7) * 4)) & 15u;
+            const float4 o = make_float4((nib & 1u) ? 1.0f : 0.0f, (nib & 2u) ? 1.0f : 0.0f, (nib & 4u) ? 1.0f : 0.0f, (nib & 8u) ? 1.0f : 0.0f);
+            const int y = row & 15, z = row >> 4;
+            *reinterpret_cast<float4 *>(l0 + ((size_t)(z0 + z) * D + (y0 + y)) * D + x0 + q * 4) = o;
+            if (a.useSurf) surf3Dwrite(o, a.surf[0], (x0 + q * 4) * 4, y0 + y, z0 + z);
+        }
+    }
+    if (L > 1) {                    // level 1 = (number of lit children) / 8, straight from the bits
+        const int D1 = D >> 1;
+        float *l1 = level(1);
+        for (int o = tid; o < (BX / 2) * 64; o += 256) {
+            const int x = o % (BX / 2), r1 = o / (BX / 2), y1 = r1 & 7, z1 = r1 >> 3;
+            uint32_t cnt = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t b = sBits[((2 * z1 + (k >> 1)) * 16 + (2 * y1 + (k & 1))) * WX + (x >> 4)];
+                cnt += (b >> ((2 * x) & 31)) & 1u;
+                cnt += (b >> ((2 * x + 1) & 31)) & 1u;
+            }
+            const float v = (float)cnt * 0.125f;
+            sL1[o] = v;
+            l1[((size_t)((z0 >> 1) + z1) * D1 + ((y0 >> 1) + y1)) * D1 + (x0 >> 1) + x] = v;
+            if (a.useSurf) surf3Dwrite(v, a.surf[1], ((x0 >> 1) + x) * 4, (y0 >> 1) + y1, (z0 >> 1) + z1);
+        }
+    }
+    __syncthreads();
+    auto reduce = [&](const float *src, float *dst, int sx, int sy, int lvl) {
+        const int dx = sx >> 1, dy = sy >> 1, n = dx * dy * dy, Dl = D >> lvl;
+        float *out = level(lvl);
+        for (int o = tid; o < n; o += 256) {
+            const int x = o % dx, y = (o / dx) % dy, z = o / (dx * dy);
+            auto S = [&](int ddx, int ddy, int ddz) { return src[((2 * z + ddz) * sy + (2 * y + ddy)) * sx + 2 * x + ddx]; };
+            const float v = (((S(0, 0, 0) + S(1, 0, 0)) + (S(0, 1, 0) + S(1, 1, 0))) + ((S(0, 0, 1) + S(1, 0, 1)) + (S(0, 1, 1) + S(1, 1, 1)))) * 0.125f;
+            dst[o] = v;
+            out[((size_t)((z0 >> lvl) + z) * Dl + ((y0 >> lvl) + y)) * Dl + (x0 >> lvl) + x] = v;
+            if (a.useSurf) surf3Dwrite(v, a.surf[lvl], ((x0 >> lvl) + x) * 4, (y0 >> lvl) + y, (z0 >> lvl) + z);
+        }
+    };
+    if (L > 2) { reduce(sL1, sL2, BX / 2, 8, 2); __syncthreads(); }
+    if (L > 3) { reduce(sL2, sL3, BX / 4, 4, 3); __syncthreads(); }
+    if (L > 4) { reduce(sL3, sL4, BX / 8, 2, 4); }
+    if (!a.tail || L <= 5) return;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) sLast = (atomicAdd(a.ticket, 1u) == gridDim.x * gridDim.y * gridDim.z - 1u) ? 1u : 0u;
+    __syncthreads();
+    if (!sLast) return;
+    __threadfence();
+    for (int lvl = 5; lvl < L; lvl++) {
+        const int Ds = D >> (lvl - 1), Dd = D >> lvl;
+        const float *src = level(lvl - 1);
+        float *dst = level(lvl);
+        for (int o = tid; o < Dd * Dd * Dd; o += 256) {
+            const int x = o % Dd, y = (o / Dd) % Dd, z = o / (Dd * Dd);
+            auto S = [&](int ddx, int ddy, int ddz) { return __ldcg(src + ((size_t)(2 * z + ddz) * Ds + (2 * y + ddy)) * Ds + 2 * x + ddx); };
+            const float v = (((S(0, 0, 0) + S(1, 0, 0)) + (S(0, 1, 0) + S(1, 1, 0))) + ((S(0, 0, 1) + S(1, 0, 1)) + (S(0, 1, 1) + S(1, 1, 1)))) * 0.125f;
+            dst[o] = v;
+            if (a.useSurf) surf3Dwrite(v, a.surf[lvl], x * 4, y, z);
+        }
+        __threadfence();
+        __syncthreads();
+    }
+    if (tid == 0) *a.ticket = 0;
+}
+
+__global__ void __launch_bounds__(256) mip_level_f32_kernel(const float *__restrict__ src, float *__restrict__ dst, int Ds) {
+    const int Dd = Ds >> 1;
+    const size_t n = (size_t)Dd * Dd * Dd;
+    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(o % Dd), y = (int)((o / Dd) % Dd), z = (int)(o / ((size_t)Dd * Dd));
+        auto S = [&](int ddx, int ddy, int ddz) { return src[((size_t)(2 * z + ddz) * Ds + (2 * y + ddy)) * Ds + 2 * x + ddx]; };
+        dst[o] = (((S(0, 0, 0) + S(1, 0, 0)) + (S(0, 1, 0) + S(1, 1, 0))) + ((S(0, 0, 1) + S(1, 0, 1)) + (S(0, 1, 1) + S(1, 1, 1)))) * 0.125f;
+    }
+}
+
+__global__ void __launch_bounds__(256) level_to_surface_f32_kernel(const float *__restrict__ src, cudaSurfaceObject_t surf, int n) {
+    const size_t total = (size_t)n * n * n;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(e % n), y = (int)((e / n) % n), z = (int)(e / ((size_t)n * n));
+        surf3Dwrite(src[e], surf, x * 4, y, z);
+    }
+}
+
 // one level from the previous one (used after a slab exchange, crn_finish_mips)
 __global__ void __launch_bounds__(256) mip_level_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int Ds) {
     const int Dd = Ds >> 1;
@@ -238,6 +350,12 @@ int launch_mips(cudaStream_t st, const VolumeParams &vol, const uint32_t *bits, 
     a.useSurf = (ts && ts->enabled) ? 1 : 0;
     for (int l = 0; l < kMaxLevels; l++) a.surf[l] = a.useSurf ? ts->surf[l] : 0;
     dim3 grid(vol.dim / a.bx, vol.dim / 16, (vol.z1 - vol.z0) / 16);
+    if (vol.texelBytes == 4) {
+        if (a.bx == 128) mip_chain_f32_kernel<4><<<grid, 256, 0, st>>>(a);
+        else if (a.bx == 64) mip_chain_f32_kernel<2><<<grid, 256, 0, st>>>(a);
+        else mip_chain_f32_kernel<1><<<grid, 256, 0, st>>>(a);
+        return 1;
+    }
     if (a.bx == 128) mip_chain_kernel<4><<<grid, 256, 0, st>>>(a);
     else if (a.bx == 64) mip_chain_kernel<2><<<grid, 256, 0, st>>>(a);
     else mip_chain_kernel<1><<<grid, 256, 0, st>>>(a);
@@ -250,7 +368,12 @@ int launch_chain_to_surfaces(cudaStream_t st, const VolumeParams &vol, const uin
         const int n = vol.levelSize[l];
         const size_t work = (size_t)n * n * n / (n >= 16 ? 16 : 1);
         const int blocks = (int)((work + 255) / 256 < 148 * 8 ? (work + 255) / 256 : 148 * 8);
-        level_to_surface_kernel<<<blocks, 256, 0, st>>>(chain + vol.levelOff[l], ts.surf[l], n);
+        if (vol.texelBytes == 4) {
+            const int b4 = (int)(((size_t)n * n * n + 255) / 256 < 148 * 8 ? ((size_t)n * n * n + 255) / 256 : 148 * 8);
+            level_to_surface_f32_kernel<<<b4, 256, 0, st>>>(reinterpret_cast<const float *>(chain + vol.levelOff[l]), ts.surf[l], n);
+        } else {
+            level_to_surface_kernel<<<blocks, 256, 0, st>>>(chain + vol.levelOff[l], ts.surf[l], n);
+        }
         launches++;
     }
     return launches;
@@ -262,7 +385,11 @@ int launch_finish_mips(cudaStream_t st, const VolumeParams &vol, uint8_t *chain,
         const int Ds = vol.levelSize[l - 1], Dd = Ds / 2;
         const size_t n = (size_t)Dd * Dd * Dd;
         const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
-        mip_level_kernel<<<blocks, 256, 0, st>>>(chain + vol.levelOff[l - 1], chain + vol.levelOff[l], Ds);
+        if (vol.texelBytes == 4)
+            mip_level_f32_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float *>(chain + vol.levelOff[l - 1]),
+                                                        reinterpret_cast<float *>(chain + vol.levelOff[l]), Ds);
+        else
+            mip_level_kernel<<<blocks, 256, 0, st>>>(chain + vol.levelOff[l - 1], chain + vol.levelOff[l], Ds);
         launches++;
     }
     return launches;

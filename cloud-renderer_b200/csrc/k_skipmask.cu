@@ -32,6 +32,7 @@ struct MaskArgs {
     uint32_t totalWords;
     const uint32_t *bits;          // level-0 occupancy
     const uint8_t *chain;
+    int texelBytes;
     uint32_t *nz;                  // non-zero bits, levels >= 1 (level 0 slot unused)
     uint32_t *dil;                 // S_l
     uint32_t *mask;                // M_l
@@ -53,9 +54,15 @@ __global__ void __launch_bounds__(256) nonzero_kernel(MaskArgs a) {
     int l, z, y, wx;
     if (!locate(a, w, l, z, y, wx)) return;
     const int n = a.size[l];
-    const uint8_t *row = a.chain + a.chainOff[l] + ((size_t)z * n + y) * n + wx * 32;
     const int cnt = min(32, n);
     uint32_t m = 0;
+    if (a.texelBytes == 4) {
+        const float *rowf = reinterpret_cast<const float *>(a.chain + a.chainOff[l]) + ((size_t)z * n + y) * n + wx * 32;
+        for (int k = 0; k < cnt; k++) m |= (rowf[k] != 0.0f ? 1u : 0u) << k;
+        a.nz[w] = m;
+        return;
+    }
+    const uint8_t *row = a.chain + a.chainOff[l] + ((size_t)z * n + y) * n + wx * 32;
     if (cnt == 32) {
         const uint4 v0 = *reinterpret_cast<const uint4 *>(row), v1 = *reinterpret_cast<const uint4 *>(row + 16);
         const uint32_t q[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
@@ -145,6 +152,7 @@ int launch_skipmask(cudaStream_t st, const VolumeParams &vol, const uint32_t *bi
     }
     a.totalWords = (uint32_t)skipmask_words(vol, a.off);
     a.bits = bits; a.chain = chain; a.nz = nz; a.dil = dil; a.mask = mask;
+    a.texelBytes = vol.texelBytes;
     int launches = 0;
     if (vol.levels > 1) {
         const uint32_t upper = a.totalWords - a.off[1];

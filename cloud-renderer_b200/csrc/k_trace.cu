@@ -120,9 +120,24 @@ __device__ __forceinline__ float sample_bytes(const uint8_t *__restrict__ t, int
     return lerpf(lerpf(c[0], c[1], Y.a), lerpf(c[2], c[3], Y.a), Z.a) * (1.0f / 255.0f);
 }
 
+// level >= 1 of an R32F chain
+__device__ __forceinline__ float sample_floats(const float *__restrict__ t, int n, float px, float py, float pz) {
+    const Lin X = clamp_axis(px, n), Y = clamp_axis(py, n), Z = clamp_axis(pz, n);
+    float c[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int y = (k & 1) ? Y.i1 : Y.i0, z = (k & 2) ? Z.i1 : Z.i0;
+        const float *row = t + (size_t)(z * n + y) * n;
+        c[k] = lerpf(__ldg(row + X.i0), __ldg(row + X.i1), X.a);
+    }
+    return lerpf(lerpf(c[0], c[1], Y.a), lerpf(c[2], c[3], Y.a), Z.a);
+}
+
 __device__ __forceinline__ float sample_level(const TraceArgs &a, int l, float px, float py, float pz) {
-    if (l == 0) return sample_bits(a.bits, a.vol.dim, px, py, pz);
+    if (l == 0) return sample_bits(a.bits, a.vol.dim, px, py, pz);          // level 0 is 0/1 in both formats
     const float s = 1.0f / (float)(1 << l);
+    if (a.vol.texelBytes == 4)
+        return sample_floats(reinterpret_cast<const float *>(a.chain + a.vol.levelOff[l]), a.vol.levelSize[l], px * s, py * s, pz * s);
     return sample_bytes(a.chain + a.vol.levelOff[l], a.vol.levelSize[l], px * s, py * s, pz * s);
 }
 

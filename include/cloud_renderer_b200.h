@@ -50,7 +50,7 @@ extern "C" {
 
 /* volume texel formats. R8 is the shipped reference format (src/CloudVolume.cpp:18). */
 #define CRN_VOLUME_R8      0
-#define CRN_VOLUME_R32F    1   /* mip chain only: same box filter without re-quantisation */
+#define CRN_VOLUME_R32F    1   /* float texels: level 0 = 0.0/1.0, mips = plain 2x2x2 means (no re-quantisation) */
 
 typedef struct crn_ctx crn_ctx;
 
@@ -236,7 +236,7 @@ int crn_finish_mips(crn_ctx *ctx, int32_t first_level);
 
 /* ---- inspection (the reference's debug views: src/Shaders/VoxelShader.cpp:102-133,
  *      src/main.cpp:172-198) ---------------------------------------------------------- */
-int crn_read_volume(crn_ctx *ctx, int32_t level, void *dst_host);          /* size_l^3 texels */
+int crn_read_volume(crn_ctx *ctx, int32_t level, void *dst_host);          /* size_l^3 texels (uint8 or float) */
 int crn_count_active_voxels(crn_ctx *ctx, uint64_t *count);                  /* "Voxels in scene" */
 int crn_keep_position_map(crn_ctx *ctx, int32_t enable);                    /* default off   */
 int crn_read_position_map(crn_ctx *ctx, float *dst_host_rgba32f);           /* W*H*4 floats  */

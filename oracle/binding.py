@@ -146,7 +146,7 @@ def cone_trace(scene, chain, quantize_fb8=False, rows=None, want_u8=True):
     u8 = np.zeros((H, W, 4), dtype=np.uint8) if want_u8 else None
     st = TraceStats()
     r0, r1 = rows if rows else (0, H)
-    ch = np.ascontiguousarray(chain, dtype=np.uint8)
+    ch = np.ascontiguousarray(chain, dtype=np.float32 if scene.vol.format == 1 else np.uint8)     # 1 = CRN_VOLUME_R32F
     lib().orc_cone_trace(C.byref(s), C.c_void_p(ch.ctypes.data), C.c_void_p(img.ctypes.data),
                          C.c_void_p(u8.ctypes.data if want_u8 else None), 1 if quantize_fb8 else 0, r0, r1, C.byref(st))
     return img, u8, st
@@ -165,7 +165,7 @@ def board_rects(scene, which):
 def conetrace_fragment(scene, chain, frag_pos, frag_tex, center, radius):
     s = _scene_struct(scene)
     col = (C.c_float * 4)()
-    ch = np.ascontiguousarray(chain, dtype=np.uint8)
+    ch = np.ascontiguousarray(chain, dtype=np.float32 if scene.vol.format == 1 else np.uint8)
     ok = lib().orc_conetrace_fragment(C.byref(s), C.c_void_p(ch.ctypes.data), (C.c_float * 3)(*frag_pos), (C.c_float * 2)(*frag_tex),
                                       (C.c_float * 3)(*center), C.c_float(radius), col)
     return bool(ok), np.array(col[:], dtype=np.float32)

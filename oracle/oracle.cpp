@@ -223,13 +223,17 @@ inline float board_radius(const crn_volume_desc &vol, float s) {
 // ---------------------------------------------------------------------------------
 // Texture sampling restated from GL 4.4 §8.14 (linear filter, §8.14.3 mipmapping).
 // ---------------------------------------------------------------------------------
-struct Chain {                  // R8 immutable 3D texture with `levels` mips (src/CloudVolume.cpp:18-23)
-    const uint8_t *data; int dim, levels;
-    size_t off[16]; int size[16];
+struct Chain {                  // R8 immutable 3D texture with `levels` mips (src/CloudVolume.cpp:18-23);
+    const uint8_t *data;        // or, for CRN_VOLUME_R32F, the same chain with float texels (fdata)
+    const float *fdata;
+    int dim, levels;
+    size_t off[16]; int size[16];   // element offsets
 };
 
-Chain make_chain(const uint8_t *data, int dim, int levels) {
-    Chain c; c.data = data; c.dim = dim; c.levels = levels;
+Chain make_chain(const void *data, int dim, int levels, bool is_float = false) {
+    Chain c; c.dim = dim; c.levels = levels;
+    c.data = is_float ? nullptr : (const uint8_t *)data;
+    c.fdata = is_float ? (const float *)data : nullptr;
     size_t o = 0; int s = dim;
     for (int l = 0; l < levels; l++) { c.off[l] = o; c.size[l] = s; o += (size_t)s * s * s; s = std::max(1, s / 2); }
     return c;
@@ -238,14 +242,18 @@ Chain make_chain(const uint8_t *data, int dim, int levels) {
 // LINEAR, CLAMP_TO_EDGE x3, UNORM8 decode c/255
 float sample_level(const Chain &c, int l, vec3 uvw) {
     int n = c.size[l];
-    const uint8_t *t = c.data + c.off[l];
+    const uint8_t *t = c.data ? c.data + c.off[l] : nullptr;
+    const float *tf = c.fdata ? c.fdata + c.off[l] : nullptr;
     float fx = uvw.x * (float)n - 0.5f, fy = uvw.y * (float)n - 0.5f, fz = uvw.z * (float)n - 0.5f;
     float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
     float ax = fx - flx, ay = fy - fly, az = fz - flz;
     // clamp in float: NaN/inf coordinates must not reach the int conversion
     auto cl = [n](float f) { f = fminf(fmaxf(f, -1.0f), (float)n); int i = (int)f; return std::min(std::max(i, 0), n - 1); };
     int x0 = cl(flx), x1 = cl(flx + 1.0f), y0 = cl(fly), y1 = cl(fly + 1.0f), z0 = cl(flz), z1 = cl(flz + 1.0f);
-    auto T = [&](int x, int y, int z) { return (float)t[((size_t)z * n + y) * n + x] / 255.0f; };
+    auto T = [&](int x, int y, int z) {
+        const size_t i = ((size_t)z * n + y) * n + x;
+        return tf ? tf[i] : (float)t[i] / 255.0f;                 // R32F texel, or UNORM8 decode
+    };
     float c00 = T(x0, y0, z0) * (1.0f - ax) + T(x1, y0, z0) * ax;
     float c10 = T(x0, y1, z0) * (1.0f - ax) + T(x1, y1, z0) * ax;
     float c01 = T(x0, y0, z1) * (1.0f - ax) + T(x1, y0, z1) * ax;
@@ -706,6 +714,8 @@ void orc_mips_f32(const float *level0, int32_t D, int32_t levels, float *chain) 
  * (src/main.cpp:116), then ConeTraceShader::coneTrace's instanced draw in ARRAY ORDER
  * (src/Shaders/ConeTraceShader.cpp:22-75; call orc_sort_boards first, as coneTrace does
  * at :20) with depth test off and alpha blending.
+ * chain_bytes: the mip chain, levels concatenated — uint8 texels, or float texels when vol.format is
+ * CRN_VOLUME_R32F (an extension: the shipped reference only has R8, src/CloudVolume.cpp:18).
  * image_f32: W*H*4 floats (always written).  image_u8: W*H*4 bytes or NULL.
  * quantize_fb8: write every blend result back through 8 bits like the window framebuffer.
  * rows [row0,row1) only (others left untouched) — lets the baseline time a crop. */
@@ -714,7 +724,7 @@ void orc_cone_trace(const orc_scene *sc, const uint8_t *chain_bytes, float *imag
     const int W = sc->width, H = sc->height;
     row0 = std::max(0, row0); row1 = std::min(H, row1);
     ViewBasis cam = make_basis(sc->cam.P, sc->cam.V);
-    Chain chain = make_chain(chain_bytes, sc->vol.dimension, sc->vol.levels);
+    Chain chain = make_chain(chain_bytes, sc->vol.dimension, sc->vol.levels, sc->vol.format == CRN_VOLUME_R32F);
     Noise nz = {sc->noise, sc->noise_dim};
     TraceUniforms u;
     u.p = sc->tp;
@@ -802,7 +812,7 @@ void orc_cone_lods(const crn_trace_params *tp, float *lods, float *heights) {
 int32_t orc_conetrace_fragment(const orc_scene *sc, const uint8_t *chain_bytes, const float fragPos[3],
                                const float fragTex[2], const float center[3], float radius, float color[4]) {
     ViewBasis cam = make_basis(sc->cam.P, sc->cam.V);
-    Chain chain = make_chain(chain_bytes, sc->vol.dimension, sc->vol.levels);
+    Chain chain = make_chain(chain_bytes, sc->vol.dimension, sc->vol.levels, sc->vol.format == CRN_VOLUME_R32F);
     Noise nz = {sc->noise, sc->noise_dim};
     TraceUniforms u;
     u.p = sc->tp;

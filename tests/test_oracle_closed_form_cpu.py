@@ -162,3 +162,20 @@ def test_empty_and_clipped_inputs(pkg, scenes, orc):
     img, _, st = orc.cone_trace(s, orc.mips(l0, 4))
     assert st.fragments == 0 or st.fragments < 200
     assert np.isfinite(img).all()
+
+
+def test_r32f_chain_in_the_oracle(pkg, scenes, orc):
+    """CRN_VOLUME_R32F (extension): a full float volume still sums to 8.5, and with 0/1 occupancy the float
+    mips are exact dyadic rationals (count / 8^l), so R8 and R32F traces agree to the R8 quantisation step"""
+    s = _probe_scene(pkg, scenes, False, True)
+    s.vol.format = pkg.VOLUME_R32F
+    full = np.ones(orc.chain_size(32, 4), np.float32)
+    centre = (25.0, 0.0, 0.0)
+    ok, col = orc.conetrace_fragment(s, full, centre, (0.5, 0.5), centre, 1.0)
+    assert ok and np.allclose(col, 8.5, rtol=1e-6)
+    rng = np.random.default_rng(2)
+    l0 = (rng.random((32, 32, 32)) < 0.2)
+    cf = orc.mips_f32(l0.astype(np.float32), 4)
+    assert np.array_equal(cf * 8.0 ** 3 % 1.0, np.zeros_like(cf)), "float mips of a 0/1 volume are multiples of 8^-3"
+    c8 = orc.mips((l0 * 255).astype(np.uint8), 4)
+    assert np.abs(cf - c8 / 255.0).max() <= 0.5 / 255 * 3 + 1e-6        # one rounding per level

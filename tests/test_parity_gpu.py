@@ -478,3 +478,36 @@ def test_c4_occupancy_exact(pkg, scenes, orc):
     r2.finish_mips(sh.slab_local_levels(s.vol.levels))
     assert np.array_equal(r2.read_chain(), ref), "slab-by-slab C4 chain differs"
     r.close(); r2.close()
+
+
+@pytest.mark.parametrize("name", ["small", "C1"])
+def test_r32f_volume_format(name, pkg, scenes, orc):
+    """CRN_VOLUME_R32F: float level 0 (0/1) and float box-filter mips, exact against the oracle's float chain;
+    images within PSNR >= 45 dB for both samplers; empty-space skipping stays exact"""
+    s = steady_state(scenes.make_scene(name), orc)
+    s.vol.format = pkg.VOLUME_R32F
+    r = pkg.Renderer(0)
+    r.set_scene(s)
+    r.voxelize()
+    _, _, l0 = orc.voxelize(s, want_posmap=False)
+    ref_chain = orc.mips_f32((l0 > 0).astype(np.float32), s.vol.levels)
+    got = r.read_chain()
+    assert got.dtype == np.float32 and np.array_equal(got, ref_chain), "float chain differs"
+    assert r.count_active_voxels() == int((l0 > 0).sum())
+    ref, _, _ = orc.cone_trace(s, ref_chain, want_u8=False)
+    for sampler, bar in ((pkg.SAMPLER_EXPLICIT, 90.0), (pkg.SAMPLER_TEXTURE, 45.0)):
+        imgs = []
+        for skip in (1, 0):
+            s.tp.sampler, s.tp.skipEmptySpace = sampler, skip
+            r.set_trace_params(s.tp)
+            imgs.append(r.cone_trace(fmt=pkg.IMAGE_RGBA32F).copy())
+        p = psnr(imgs[0], ref)
+        print(f"{name}/R32F/sampler{sampler}: PSNR {p:.1f} dB, max err {np.abs(imgs[0] - ref).max():.2e}")
+        assert p >= bar
+        assert np.array_equal(imgs[0].view(np.uint32), imgs[1].view(np.uint32)), "skipping changed an R32F image"
+    # and back to R8 on the same context
+    s.vol.format = pkg.VOLUME_R8
+    r.set_volume(s.vol)
+    r.voxelize()
+    assert np.array_equal(r.read_chain(), orc.mips(l0, s.vol.levels))
+    r.close()
