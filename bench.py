@@ -46,6 +46,8 @@ def parse():
                     help="C4 with N>1: 'chain' = Z-slab voxelize+mips and ONE all-gather of the finished chain (north_star); "
                          "'none' = every rank voxelizes the whole volume (no collective), only the trace is sharded")
     ap.add_argument("--volume-format", default="r8", choices=["r8", "r32f"], help="r8 = the shipped reference format")
+    ap.add_argument("--radius-mode", default="auto", choices=["auto", "fill", "reference"],
+                    help="billboard radii for N > 200: 'fill' keeps the cloud's fill (headline), 'reference' keeps U[1,2.5] (SURVEY 8d)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="back-to-back steps (no L2 flush between them)")
     return ap.parse_args()
@@ -127,16 +129,16 @@ def ncu_traffic(name):
         return None
 
 
-def frame_inputs(sc, config, n_frames, rank, world):
+def frame_inputs(sc, config, n_frames, rank, world, radius_mode="auto"):
     """billboard offsets for the frames this rank renders + the camera/sun of each"""
-    base = sc.make_scene(config, cutoff=0.0)
+    base = sc.make_scene(config, cutoff=0.0, radius_mode=radius_mode)
     frames = []
     for k in range(n_frames):
         g = k * world + rank                          # global frame id, round-robin over ranks
         if world > 1:
-            s = sc.make_scene(config, frame=g, view=g % 64)
+            s = sc.make_scene(config, frame=g, view=g % 64, radius_mode=radius_mode)
         else:
-            s = sc.make_scene(config, frame=g)
+            s = sc.make_scene(config, frame=g, radius_mode=radius_mode)
         frames.append(s)
     return base, frames
 
@@ -231,7 +233,7 @@ def main():
 
     K, Wm = args.steps, args.warmup
     slab = args.config == "C4" and world > 1
-    base, frames = frame_inputs(sc, args.config, K + Wm, 0 if slab else rank, 1 if slab else world)
+    base, frames = frame_inputs(sc, args.config, K + Wm, 0 if slab else rank, 1 if slab else world, args.radius_mode)
     D, L, N, Wd, Ht = sc.CONFIGS[args.config]
     for f in frames:
         f.tp.transmittanceCutoff = args.cutoff

@@ -163,6 +163,12 @@ struct crn_ctx {
     cudaStream_t copyStream = nullptr;
     cudaEvent_t evFrame[2] = {}, evCopy[2] = {};
     cudaEvent_t evBin[2] = {};           // bin cursors ready (light, camera): their read-back rides the copy stream
+    // the camera-side set-up (prep, sort, bin, tile order) depends only on the billboards and the camera, so it runs on
+    // a side stream and overlaps the voxelize + mip kernels of the same frame, which leave most SMs idle
+    cudaStream_t auxStream = nullptr;
+    cudaEvent_t evBoards = nullptr, evAuxDone = nullptr, evTraceEnd = nullptr, evAuxT[3] = {};
+    bool traceEndValid = false;
+    DevBuf sortTmpC;
     bool copyPending[2] = {false, false};
     int imgSel = 0;
 
@@ -193,6 +199,7 @@ int reserve(crn_ctx *c, DevBuf &b, size_t bytes) {
     if (bytes <= b.cap) return CRN_OK;
     CRN_CUDA(c, cudaStreamSynchronize(c->stream));
     if (c->copyStream) CRN_CUDA(c, cudaStreamSynchronize(c->copyStream));
+    if (c->auxStream) CRN_CUDA(c, cudaStreamSynchronize(c->auxStream));
     if (b.p) CRN_CUDA(c, cudaFree(b.p));
     b.p = nullptr; b.cap = 0;
     const size_t want = bytes + bytes / 4 + 256;
@@ -205,6 +212,7 @@ int reserve(crn_ctx *c, DevBuf &b, size_t bytes) {
 int alloc_u32(crn_ctx *c, uint32_t *&p, size_t &have, size_t want) {
     if (want <= have) return CRN_OK;
     CRN_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->auxStream) CRN_CUDA(c, cudaStreamSynchronize(c->auxStream));
     if (p) CRN_CUDA(c, cudaFree(p));
     p = nullptr; have = 0;
     CRN_CUDA(c, cudaMalloc(&p, want * sizeof(uint32_t)));
@@ -485,7 +493,7 @@ int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
     if ((r = reserve(c, c->recC, nn * sizeof(BoardRec)))) return r;
     if ((r = reserve(c, c->rectC, nn * sizeof(BoardRect)))) return r;
     if ((r = reserve(c, c->drawOrder, nn * 4))) return r;
-    if ((r = reserve(c, c->sortTmp, sort_tmp_bytes((int)nn) + 128))) return r;
+    if ((r = reserve(c, c->sortTmpC, sort_tmp_bytes((int)nn) + 128))) return r;
     if ((r = reserve(c, c->misc, 256))) return r;
     const size_t texel = format == CRN_IMAGE_RGBA32F ? 16 : 4;
     if ((r = reserve(c, img, (size_t)c->W * c->H * texel))) return r;
@@ -508,24 +516,34 @@ int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
     }
     unsigned long long *dStats = (unsigned long long *)((char *)c->misc.p + 64);
     if (c->statsOn) cudaMemsetAsync(dStats, 0, 8 * sizeof(unsigned long long), st);
-    if (c->timingOn) cudaEventRecord(c->evT[0], st);
+    // ---- camera-side set-up on the side stream: after the billboard upload and after the previous trace (which reads
+    //      the same records / bins), concurrently with whatever voxelize work is still queued on the main stream
+    cudaStream_t ax = c->auxStream;
+    cudaStreamWaitEvent(ax, c->evBoards, 0);
+    if (c->traceEndValid) cudaStreamWaitEvent(ax, c->evTraceEnd, 0);
+    if (c->timingOn) cudaEventRecord(c->evAuxT[0], ax);
     const float zero3[3] = {0, 0, 0};
-    c->launches += launch_prep_sort(st, (const float *)c->pos.p, (const float *)c->scale.p, n, c->vol.fluffiness, c->vol.position, cam,
+    c->launches += launch_prep_sort(ax, (const float *)c->pos.p, (const float *)c->scale.p, n, c->vol.fluffiness, c->vol.position, cam,
                                     zero3, 1.0f, cam, c->cam.position, false, true, nullptr, (uint32_t *)c->rankC.p, nullptr,
                                     (uint64_t *)c->keyC.p, nullptr, (BoardRec *)c->recTmpC.p, nullptr, (BoardRect *)c->rectTmpC.p,
                                     nullptr, nullptr, (BoardRec *)c->recC.p, nullptr, (BoardRect *)c->rectC.p, nullptr,
-                                    (int32_t *)c->drawOrder.p, c->sortTmp.p);
-    if (c->timingOn) cudaEventRecord(c->evT[1], st);
-    c->launches += launch_bin(st, (const BoardRect *)c->rectC.p, sort_tmp_bounds(c->sortTmp.p, (int)nn, 1), n, c->W, c->H, c->binsC);
-    cudaEventRecord(c->evBin[1], st);
+                                    (int32_t *)c->drawOrder.p, c->sortTmpC.p);
+    if (c->timingOn) cudaEventRecord(c->evAuxT[1], ax);
+    c->launches += launch_bin(ax, (const BoardRect *)c->rectC.p, sort_tmp_bounds(c->sortTmpC.p, (int)nn, 1), n, c->W, c->H, c->binsC);
+    cudaEventRecord(c->evBin[1], ax);
     cudaStreamWaitEvent(c->copyStream, c->evBin[1], 0);
     cudaMemcpyAsync(c->hCursors + 2, c->binsC.cursors, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->copyStream);
-    c->launches += launch_tile_order(st, c->binsC, (uint32_t *)c->tileOrder.p);
+    c->launches += launch_tile_order(ax, c->binsC, (uint32_t *)c->tileOrder.p);
+    if (c->timingOn) cudaEventRecord(c->evAuxT[2], ax);
+    cudaEventRecord(c->evAuxDone, ax);
+    cudaStreamWaitEvent(st, c->evAuxDone, 0);
     if (c->timingOn) cudaEventRecord(c->evT[2], st);
     c->launches += launch_trace(st, cam, c->vparams, tp, (const BoardRec *)c->recC.p, c->binsC, (const uint32_t *)c->bits.p,
                                 (const uint8_t *)c->chain.p, (const int8_t *)c->noise.p, useTex ? &c->ts : nullptr,
                                 c->tp.skipEmptySpace ? (const uint32_t *)c->mask.p : nullptr, (const uint32_t *)c->tileOrder.p,
                                 img.p, format, dStats);
+    cudaEventRecord(c->evTraceEnd, st);
+    c->traceEndValid = true;
     if (c->timingOn) { cudaEventRecord(c->evT[3], st); c->evTValid = true; }
     if (c->statsOn) cudaMemcpyAsync(c->hStats, dStats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
     CRN_CUDA(c, cudaGetLastError());
@@ -571,6 +589,11 @@ int crn_create(int device, void *stream, crn_ctx **out) {
     std::memset(c->hCursors, 0, 4 * sizeof(uint32_t));
     std::memset(c->hStats, 0, 8 * sizeof(unsigned long long));
     cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&c->auxStream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&c->evBoards, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->evAuxDone, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->evTraceEnd, cudaEventDisableTiming);
+    for (auto &ev : c->evAuxT) cudaEventCreate(&ev);
     for (int k = 0; k < 2; k++) {
         cudaEventCreateWithFlags(&c->evFrame[k], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&c->evCopy[k], cudaEventDisableTiming);
@@ -593,9 +616,10 @@ void crn_destroy(crn_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->copyStream) cudaStreamSynchronize(c->copyStream);
+    if (c->auxStream) cudaStreamSynchronize(c->auxStream);
     DevBuf *bufs[] = {&c->pos, &c->scale, &c->keyL, &c->keyC, &c->rankL, &c->rankC, &c->recTmpL, &c->recTmpC, &c->rectTmpL,
                       &c->rectTmpC, &c->lbTmp, &c->recL, &c->recC, &c->rectL, &c->rectC, &c->lbSorted, &c->drawOrder, &c->bits,
-                      &c->chain, &c->noise, &c->posmap, &c->image, &c->image2, &c->misc, &c->maskNz, &c->maskDil, &c->mask, &c->sortTmp, &c->tileOrder};
+                      &c->chain, &c->noise, &c->posmap, &c->image, &c->image2, &c->misc, &c->maskNz, &c->maskDil, &c->mask, &c->sortTmp, &c->sortTmpC, &c->tileOrder};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     free_bins(c->binsL); free_bins(c->binsC);
     free_vol_textures(c);
@@ -605,6 +629,11 @@ void crn_destroy(crn_ctx *c) {
     if (c->hStats) cudaFreeHost(c->hStats);
     for (auto &ev : c->evV) if (ev) cudaEventDestroy(ev);
     for (auto &ev : c->evT) if (ev) cudaEventDestroy(ev);
+    if (c->auxStream) {
+        cudaEventDestroy(c->evBoards); cudaEventDestroy(c->evAuxDone); cudaEventDestroy(c->evTraceEnd);
+        for (auto &ev : c->evAuxT) if (ev) cudaEventDestroy(ev);
+        cudaStreamDestroy(c->auxStream);
+    }
     if (c->copyStream) {
         cudaStreamSynchronize(c->copyStream);
         for (int k = 0; k < 2; k++) {
@@ -665,6 +694,7 @@ int crn_set_billboards(crn_ctx *c, const float *positions3, const float *scales,
         CRN_CUDA(c, cudaMemcpyAsync(c->pos.p, positions3, (size_t)count * 12, kind, c->stream));
         CRN_CUDA(c, cudaMemcpyAsync(c->scale.p, scales, (size_t)count * 4, kind, c->stream));
     }
+    CRN_CUDA(c, cudaEventRecord(c->evBoards, c->stream));
     c->nBoards = count;
     return CRN_OK;
 }
@@ -1081,9 +1111,10 @@ int crn_get_timings(crn_ctx *c, crn_timings *out) {
     }
     if (c->evTValid) {
         float t = 0;
-        CRN_CUDA(c, cudaEventElapsedTime(&t, c->evT[0], c->evT[1]));
+        CRN_CUDA(c, cudaStreamSynchronize(c->auxStream));
+        CRN_CUDA(c, cudaEventElapsedTime(&t, c->evAuxT[0], c->evAuxT[1]));        // side stream: overlaps the voxelize stage
         out->prepSortMs += t;
-        CRN_CUDA(c, cudaEventElapsedTime(&out->camBinMs, c->evT[1], c->evT[2]));
+        CRN_CUDA(c, cudaEventElapsedTime(&out->camBinMs, c->evAuxT[1], c->evAuxT[2]));
         CRN_CUDA(c, cudaEventElapsedTime(&out->traceMs, c->evT[2], c->evT[3]));
     }
     return CRN_OK;

@@ -346,8 +346,9 @@ def test_error_paths(pkg, scenes):
     bad.xBounds[:] = (5.0, -5.0)
     assert code(r.set_volume, bad) == pkg.CRN_ERR_INVALID_ARG
     bad.xBounds[:] = (-5.0, 5.0)
-    bad.format = pkg.VOLUME_R32F
-    assert code(r.set_volume, bad) == pkg.CRN_ERR_UNSUPPORTED
+    bad.format = 7
+    assert code(r.set_volume, bad) == pkg.CRN_ERR_UNSUPPORTED                      # unknown texel format
+    bad.format = pkg.VOLUME_R8
     tp = pkg.default_trace_params()
     tp.vctSteps = 1000
     assert code(r.set_trace_params, tp) == pkg.CRN_ERR_UNSUPPORTED
