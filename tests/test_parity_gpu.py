@@ -566,3 +566,17 @@ def test_random_scenes(seed, pkg, scenes, orc):
         print(f"seed {seed} sampler {sampler}: {W}x{H}, {s.n_boards} boards, {st.fragments} fragments, PSNR {p:.1f} dB, max err {np.abs(img - ref).max():.2e}")
         assert p >= bar
     r.close()
+
+
+def test_results_are_deterministic(pkg, scenes, renderer):
+    """no atomics or scheduling order leaks into the outputs: two runs of the same frame are bit-identical"""
+    s = scenes.make_scene("C1")
+    s.tp.sampler = pkg.SAMPLER_TEXTURE
+    outs = []
+    for _ in range(2):
+        renderer.set_scene(s)
+        renderer.voxelize()
+        img = renderer.cone_trace(fmt=pkg.IMAGE_RGBA32F).copy()
+        outs.append((img, renderer.read_chain(), renderer.read_sorted_order(s.n_boards), renderer.read_bins(1)["entries"].copy()))
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
