@@ -448,6 +448,7 @@ void build_trace_params(crn_ctx *c, const ViewParams &cam, TraceParams *tp) {
         if (!(lod > 0.0f)) { s.level0 = 0; s.frac = 0.0f; }
         else if (lod >= (float)(L - 1)) { s.level0 = L - 1; s.frac = 0.0f; }
         else { const float fl = floorf(lod); s.level0 = (int)fl; s.frac = lod - fl; }
+        s.lod0 = (float)s.level0; s.lod1 = (float)(s.level0 + 1);
         coneHeight += coneRadius;
     }
     // groups for the empty-space test: consecutive steps with the same lower level whose sample points

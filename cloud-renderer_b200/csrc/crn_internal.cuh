@@ -56,6 +56,7 @@ struct ConeStep {                     // traceCone's per-step constants (identic
     float weight;                     // float(i) / (steps * vctDownScaling)
     int32_t level0;                   // lower mip level sampled
     float frac;                       // blend toward level0+1 (0: single level)
+    float lod0, lod1;                 // level0 and level0+1 as floats (tex3DLod operands; saves a conversion per fetch)
 };
 
 struct ConeGroup {                    // consecutive cone steps decided by ONE empty-space lookup (k_skipmask.cu)

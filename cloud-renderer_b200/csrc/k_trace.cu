@@ -336,8 +336,8 @@ __global__ void __launch_bounds__(kTraceThreads, 2048 / kTraceThreads / 2) trace
                             const float sx = fmaf(st.height, ex, nx), sy = fmaf(st.height, ey, ny), sz = fmaf(st.height, ez, nz);
                             float s;
                             if constexpr (kTex) {
-                                s = tex3DLod<float>(ts.vol, sx, sy, sz, (float)st.level0);
-                                if (st.frac != 0.0f) s = lerpf(s, tex3DLod<float>(ts.vol, sx, sy, sz, (float)(st.level0 + 1)), st.frac);
+                                s = tex3DLod<float>(ts.vol, sx, sy, sz, st.lod0);
+                                if (st.frac != 0.0f) s = lerpf(s, tex3DLod<float>(ts.vol, sx, sy, sz, st.lod1), st.frac);
                             } else {
                                 const float fd = (float)D;
                                 s = sample_level(a, st.level0, sx * fd, sy * fd, sz * fd);
