@@ -62,6 +62,7 @@ class Timings(C.Structure):
 # every symbol include/cloud_renderer_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "crn_create", "crn_destroy", "crn_last_error", "crn_sync", "crn_set_volume", "crn_set_billboards", "crn_set_sun",
+    "crn_regenerate_billboards", "crn_animate_billboards", "crn_read_billboards",
     "crn_sun_update", "crn_set_camera", "crn_camera_update", "crn_set_window", "crn_set_trace_params",
     "crn_default_trace_params", "crn_set_noise", "crn_build_noise", "crn_voxelize", "crn_cone_trace", "crn_cone_trace_async",
     "crn_wait_images", "crn_set_row_range",
@@ -94,6 +95,9 @@ def load_library():
     lib.crn_sync.argtypes = [vp]
     lib.crn_set_volume.argtypes = [vp, C.POINTER(VolumeDesc)]
     lib.crn_set_billboards.argtypes = [vp, vp, vp, i32, i32]
+    lib.crn_regenerate_billboards.argtypes = [vp, i32, C.POINTER(f32 * 3), C.POINTER(f32 * 3), f32, f32, C.c_double, C.c_uint64]
+    lib.crn_animate_billboards.argtypes = [vp, C.c_double]
+    lib.crn_read_billboards.argtypes = [vp, vp, vp]
     lib.crn_set_sun.argtypes = [vp, C.POINTER(Sun)]
     lib.crn_sun_update.argtypes = [C.POINTER(VolumeDesc), C.POINTER(Sun), C.POINTER(SunDerived)]
     lib.crn_set_camera.argtypes = [vp, C.POINTER(Camera)]
@@ -215,6 +219,22 @@ class Renderer:
         assert mp == ms
         n = int(scales.shape[0])
         self._ck(self.lib.crn_set_billboards(self.h, p, s, n, mp))
+
+    def regenerate_billboards(self, count, min_offset, max_offset, min_scale, max_scale, radius_factor=1.0, seed=0):
+        """device-side CloudVolume::regenerateBillboards (src/CloudVolume.cpp:120-137); no host->device copy"""
+        lo, hi = (f32 * 3)(*min_offset), (f32 * 3)(*max_offset)
+        self._ck(self.lib.crn_regenerate_billboards(self.h, count, C.byref(lo), C.byref(hi), min_scale, max_scale,
+                                                    radius_factor, seed & ((1 << 64) - 1)))
+
+    def animate_billboards(self, angle):
+        """offsets = R_y(angle) * base offsets, on the device"""
+        self._ck(self.lib.crn_animate_billboards(self.h, float(angle)))
+
+    def read_billboards(self, count):
+        pos = np.empty((count, 3), np.float32)
+        scale = np.empty(count, np.float32)
+        self._ck(self.lib.crn_read_billboards(self.h, pos.ctypes.data, scale.ctypes.data))
+        return pos, scale
 
     def set_sun(self, sun):
         self._ck(self.lib.crn_set_sun(self.h, C.byref(sun)))

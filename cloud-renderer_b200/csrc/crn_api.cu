@@ -143,7 +143,8 @@ struct crn_ctx {
     VolumeParams vparams{};
     size_t chainBytes = 0;
 
-    DevBuf pos, scale, keyL, keyC, rankL, rankC, recTmpL, recTmpC, rectTmpL, rectTmpC, lbTmp, recL, recC, rectL, rectC,
+    bool havePos0 = false;               // pos0 holds the un-advected offsets of the current billboard set
+    DevBuf pos0, pos, scale, keyL, keyC, rankL, rankC, recTmpL, recTmpC, rectTmpL, rectTmpC, lbTmp, recL, recC, rectL, rectC,
         lbSorted, drawOrder, bits, chain, noise, posmap, image, misc, maskNz, maskDil, mask, sortTmp, tileOrder;
     bool maskCurrent = false;
     size_t poolMin = (size_t)1 << 20;    // initial bin-pool entries (CRN_BIN_POOL_MIN overrides: tests force the growth path)
@@ -697,6 +698,51 @@ int crn_set_billboards(crn_ctx *c, const float *positions3, const float *scales,
     }
     CRN_CUDA(c, cudaEventRecord(c->evBoards, c->stream));
     c->nBoards = count;
+    c->havePos0 = false;
+    return CRN_OK;
+}
+
+int crn_regenerate_billboards(crn_ctx *c, int32_t count, const float minOffset[3], const float maxOffset[3], float minScale,
+                              float maxScale, double radiusFactor, uint64_t seed) {   // src/CloudVolume.cpp:120-137
+    if (!c || count < 0 || !minOffset || !maxOffset) return fail(c, CRN_ERR_INVALID_ARG, "bad generator arguments");
+    CRN_CUDA(c, cudaSetDevice(c->device));
+    int r;
+    if ((r = reserve(c, c->pos0, (size_t)std::max(count, 1) * 12))) return r;
+    if ((r = reserve(c, c->pos, (size_t)std::max(count, 1) * 12))) return r;
+    if ((r = reserve(c, c->scale, (size_t)std::max(count, 1) * 4))) return r;
+    c->launches += launch_generate_boards(c->stream, count, minOffset, maxOffset, minScale, maxScale, radiusFactor, seed,
+                                          (float *)c->pos0.p, (float *)c->pos.p, (float *)c->scale.p);
+    CRN_CUDA(c, cudaGetLastError());
+    CRN_CUDA(c, cudaEventRecord(c->evBoards, c->stream));
+    c->nBoards = count;
+    c->havePos0 = true;
+    return CRN_OK;
+}
+
+int crn_animate_billboards(crn_ctx *c, double angle) {
+    if (!c) return CRN_ERR_INVALID_ARG;
+    CRN_CUDA(c, cudaSetDevice(c->device));
+    const int n = c->nBoards;
+    if (!c->havePos0) {                                  // first advection of an uploaded set: keep its base offsets
+        int r;
+        if ((r = reserve(c, c->pos0, (size_t)std::max(n, 1) * 12))) return r;
+        if (n) CRN_CUDA(c, cudaMemcpyAsync(c->pos0.p, c->pos.p, (size_t)n * 12, cudaMemcpyDeviceToDevice, c->stream));
+        c->havePos0 = true;
+    }
+    c->launches += launch_rotate_boards(c->stream, n, (const float *)c->pos0.p, (float *)c->pos.p, (float)std::cos(angle),
+                                        (float)std::sin(angle));
+    CRN_CUDA(c, cudaGetLastError());
+    CRN_CUDA(c, cudaEventRecord(c->evBoards, c->stream));
+    return CRN_OK;
+}
+
+int crn_read_billboards(crn_ctx *c, float *positions3_host, float *scales_host) {
+    if (!c) return CRN_ERR_INVALID_ARG;
+    CRN_CUDA(c, cudaSetDevice(c->device));
+    const size_t n = (size_t)c->nBoards;
+    if (n && positions3_host) CRN_CUDA(c, cudaMemcpyAsync(positions3_host, c->pos.p, n * 12, cudaMemcpyDeviceToHost, c->stream));
+    if (n && scales_host) CRN_CUDA(c, cudaMemcpyAsync(scales_host, c->scale.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CRN_CUDA(c, cudaStreamSynchronize(c->stream));
     return CRN_OK;
 }
 

@@ -136,6 +136,9 @@ int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol
 size_t skipmask_words(const VolumeParams &vol, uint32_t *off);
 int launch_skipmask(cudaStream_t st, const VolumeParams &vol, const uint32_t *bits, const uint8_t *chain, uint32_t *nz,
                     uint32_t *dil, uint32_t *mask);
+int launch_generate_boards(cudaStream_t st, int n, const float minOff[3], const float maxOff[3], float minScale,
+                           float maxScale, double radiusFactor, uint64_t seed, float *pos0, float *pos, float *scale);
+int launch_rotate_boards(cudaStream_t st, int n, const float *pos0, float *pos, float c, float s);
 int launch_count_bits(cudaStream_t st, const uint32_t *bits, size_t words, unsigned long long *out);
 
 } // namespace crn

@@ -175,6 +175,25 @@ int crn_set_billboards(crn_ctx *ctx, const float *positions3, const float *scale
 /* replaces the Sun statics + Sun::update(volume) (src/Sun.hpp:26-43); the derived light
  * camera is recomputed from the current volume at every crn_voxelize. */
 int crn_set_sun(crn_ctx *ctx, const crn_sun *sun);
+/* Device-side CloudVolume::regenerateBillboards (src/CloudVolume.cpp:120-137): `count`
+ * billboards with offsets uniform in [minOffset, maxOffset) per axis and scales uniform in
+ * [minScale, maxScale) times `radiusFactor` (1 = the reference's distribution), written
+ * straight into the context's arrays - nothing crosses PCIe.  The reference's rand() stream
+ * (seeded with time(0), src/main.cpp:70) is not reproducible; the stream here is
+ * counter-based splitmix64 of `seed` (billboard i uses counters 4i+1..4i+4; float64
+ * u*(max-min)+min rounded to float32), bit-identical to cloud-renderer_b200/scene.py. */
+int crn_regenerate_billboards(crn_ctx *ctx, int32_t count, const float minOffset[3],
+                              const float maxOffset[3], float minScale, float maxScale,
+                              double radiusFactor, uint64_t seed);
+/* Advect the current billboard set on the device: offsets = R_y(angle) * base offsets, where
+ * the base is what crn_regenerate_billboards / crn_set_billboards last installed (absolute
+ * angle, not incremental; float32 c*x+s*z, -s*x+c*z with c,s = (float)cos/sin(angle)).
+ * This is the analytic animation field of the benchmark configs; it replaces the per-frame
+ * host update + glBufferData re-upload of src/CloudVolume.cpp:139-164. */
+int crn_animate_billboards(crn_ctx *ctx, double angle);
+/* current billboard arrays (after generation / advection); either pointer may be NULL */
+int crn_read_billboards(crn_ctx *ctx, float *positions3_host, float *scales_host);
+
 /* the pure function behind Sun::update, exported so callers can inspect it */
 int crn_sun_update(const crn_volume_desc *vol, const crn_sun *sun, crn_sun_derived *out);
 /* replaces Camera::getP()/getV()/getPosition() as read by ConeTraceShader::coneTrace

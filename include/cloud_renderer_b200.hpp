@@ -114,6 +114,14 @@ public:
             addCloudBoard(p, s);
         }
     }
+    // Device-side variant (§8 f3): same distribution, generated where it is consumed from a counter-based
+    // splitmix64 stream; the host arrays are refreshed from the device so caller code can still read them.
+    void regenerateBillboardsOnDevice(int count, vec3 minOffset, vec3 maxOffset, float minScale, float maxScale, uint64_t seed) {
+        billboards.minOffset = minOffset; billboards.maxOffset = maxOffset; billboards.minScale = minScale; billboards.maxScale = maxScale;
+        check(ctx, crn_regenerate_billboards(ctx, count, &minOffset.x, &maxOffset.x, minScale, maxScale, 1.0, seed));
+        billboards.positions.resize(count); billboards.scales.resize(count); billboards.count = count;
+        if (count) check(ctx, crn_read_billboards(ctx, &billboards.positions[0].x, billboards.scales.data()));
+    }
     void resetBillboards() { regenerateBillboards(billboards.count, billboards.minOffset, billboards.maxOffset, billboards.minScale, billboards.maxScale); }
 
     ivec3 get3DIndices(const int index) const {          // src/CloudVolume.cpp:103-110

@@ -580,3 +580,36 @@ def test_results_are_deterministic(pkg, scenes, renderer):
         outs.append((img, renderer.read_chain(), renderer.read_sorted_order(s.n_boards), renderer.read_bins(1)["entries"].copy()))
     for a, b in zip(outs[0], outs[1]):
         assert np.array_equal(a, b)
+
+
+def test_device_scene_generation_and_animation(pkg, scenes, renderer):
+    """§8 f3: crn_regenerate_billboards / crn_animate_billboards produce, on the device, the very bytes the numpy
+    fixtures hold (regenerateBillboards src/CloudVolume.cpp:120-137; the C3 rotation field), so a frame rendered from
+    them equals one rendered from uploaded arrays."""
+    for name, n in (("C1", 200), ("C2", 4000)):
+        s = scenes.make_scene(name)
+        factor = (200.0 / n) ** (1.0 / 3.0) if s.meta["radius_mode"] == "fill" else 1.0
+        renderer.set_scene(s)
+        renderer.regenerate_billboards(n, (-2.5,) * 3, (2.5,) * 3, 1.0, 2.5, factor, scenes.SEED ^ 0xB0A2D5)
+        pos, scale = renderer.read_billboards(n)
+        assert np.array_equal(pos.view(np.uint32), s.board_pos.view(np.uint32))
+        assert np.array_equal(scale.view(np.uint32), s.board_scale.view(np.uint32))
+        for frame in (7, 123):
+            renderer.animate_billboards(0.2 * frame / 60.0)
+            pos, _ = renderer.read_billboards(n)
+            want = scenes.animate(s.board_pos, frame)
+            assert np.array_equal(pos.view(np.uint32), want.view(np.uint32))
+    # rendering from generated + advected boards == rendering from the uploaded fixture of that frame
+    s7 = scenes.make_scene("C1", frame=7)
+    renderer.set_scene(s7); renderer.voxelize()
+    ref_img = renderer.cone_trace().copy(); ref_chain = renderer.read_chain()
+    renderer.regenerate_billboards(200, (-2.5,) * 3, (2.5,) * 3, 1.0, 2.5, 1.0, scenes.SEED ^ 0xB0A2D5)
+    renderer.animate_billboards(0.2 * 7 / 60.0)
+    renderer.voxelize()
+    assert np.array_equal(renderer.cone_trace(), ref_img)
+    assert np.array_equal(renderer.read_chain(), ref_chain)
+    # advecting an uploaded set keeps its base offsets
+    renderer.set_billboards(s7.board_pos, s7.board_scale)
+    renderer.animate_billboards(0.5); renderer.animate_billboards(0.0)
+    pos, _ = renderer.read_billboards(200)
+    assert np.array_equal(pos, s7.board_pos)
