@@ -45,7 +45,8 @@ def parse():
     ap.add_argument("--slab-exchange", default="chain", choices=["chain", "none"],
                     help="C4 with N>1: 'chain' = Z-slab voxelize+mips and ONE all-gather of the finished chain (north_star); "
                          "'none' = every rank voxelizes the whole volume (no collective), only the trace is sharded")
-    ap.add_argument("--volume-format", default="r8", choices=["r8", "r32f"], help="r8 = the shipped reference format")
+    ap.add_argument("--volume-format", default="r8", choices=["r8", "r32f", "rg8"],
+                    help="r8 = the shipped reference format; rg8 = the paper variant with the occupancy channel")
     ap.add_argument("--radius-mode", default="auto", choices=["auto", "fill", "reference"],
                     help="billboard radii for N > 200: 'fill' keeps the cloud's fill (headline), 'reference' keeps U[1,2.5] (SURVEY 8d)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -239,7 +240,7 @@ def main():
         f.tp.transmittanceCutoff = args.cutoff
         f.tp.sampler = pkg.SAMPLER_TEXTURE if args.sampler == "texture" else pkg.SAMPLER_EXPLICIT
         f.tp.skipEmptySpace = 0 if args.no_skip else 1
-        f.vol.format = pkg.VOLUME_R32F if args.volume_format == "r32f" else pkg.VOLUME_R8
+        f.vol.format = {"r8": pkg.VOLUME_R8, "r32f": pkg.VOLUME_R32F, "rg8": pkg.VOLUME_RG8}[args.volume_format]
     r.set_scene(frames[0])
 
     # resident inputs (value leg) and pinned host inputs (e2e leg)

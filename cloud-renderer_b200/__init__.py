@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libcloud_renderer_b200.so")
 CRN_OK, CRN_ERR_INVALID_ARG, CRN_ERR_CUDA, CRN_ERR_STATE, CRN_ERR_UNSUPPORTED, CRN_ERR_NO_DEVICE = range(6)
 MEM_HOST, MEM_DEVICE = 0, 1
 IMAGE_RGBA8, IMAGE_RGBA32F = 0, 1
-VOLUME_R8, VOLUME_R32F = 0, 1
+VOLUME_R8, VOLUME_R32F, VOLUME_RG8 = 0, 1, 2
 SAMPLER_EXPLICIT, SAMPLER_TEXTURE = 0, 1
 
 f32, i32, u64 = C.c_float, C.c_int32, C.c_uint64
@@ -62,7 +62,7 @@ class Timings(C.Structure):
 # every symbol include/cloud_renderer_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "crn_create", "crn_destroy", "crn_last_error", "crn_sync", "crn_set_volume", "crn_set_billboards", "crn_set_sun",
-    "crn_regenerate_billboards", "crn_animate_billboards", "crn_read_billboards",
+    "crn_regenerate_billboards", "crn_animate_billboards", "crn_read_billboards", "crn_read_volume_alpha",
     "crn_sun_update", "crn_set_camera", "crn_camera_update", "crn_set_window", "crn_set_trace_params",
     "crn_default_trace_params", "crn_set_noise", "crn_build_noise", "crn_voxelize", "crn_cone_trace", "crn_cone_trace_async",
     "crn_wait_images", "crn_set_row_range",
@@ -119,6 +119,7 @@ def load_library():
     lib.crn_volume_bits_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     lib.crn_finish_mips.argtypes = [vp, i32]
     lib.crn_read_volume.argtypes = [vp, i32, vp]
+    lib.crn_read_volume_alpha.argtypes = [vp, i32, vp]
     lib.crn_count_active_voxels.argtypes = [vp, C.POINTER(u64)]
     lib.crn_keep_position_map.argtypes = [vp, i32]
     lib.crn_read_position_map.argtypes = [vp, vp]
@@ -319,6 +320,16 @@ class Renderer:
 
     def read_chain(self):
         return np.concatenate([self.read_volume(l).ravel() for l in range(self.vol.levels)])
+
+    def read_volume_alpha(self, level=0):
+        """CRN_VOLUME_RG8: one level of the occupancy (alpha) channel"""
+        s = max(1, self.vol.dimension >> level)
+        out = np.empty((s, s, s), dtype=np.uint8)
+        self._ck(self.lib.crn_read_volume_alpha(self.h, level, out.ctypes.data))
+        return out
+
+    def read_chain_alpha(self):
+        return np.concatenate([self.read_volume_alpha(l).ravel() for l in range(self.vol.levels)])
 
     def count_active_voxels(self):
         n = u64()

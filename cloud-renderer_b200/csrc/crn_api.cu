@@ -144,6 +144,7 @@ struct crn_ctx {
     size_t chainBytes = 0;
 
     bool havePos0 = false;               // pos0 holds the un-advected offsets of the current billboard set
+    DevBuf bitsA, chainA;                // CRN_VOLUME_RG8: the occupancy (alpha) channel's level-0 set and R8 chain
     DevBuf pos0, pos, scale, keyL, keyC, rankL, rankC, recTmpL, recTmpC, rectTmpL, rectTmpC, lbTmp, recL, recC, rectL, rectC,
         lbSorted, drawOrder, bits, chain, noise, posmap, image, misc, maskNz, maskDil, mask, sortTmp, tileOrder;
     bool maskCurrent = false;
@@ -153,7 +154,8 @@ struct crn_ctx {
     unsigned long long *hStats = nullptr;
 
     // texture-unit copies (CRN_SAMPLER_TEXTURE)
-    cudaMipmappedArray_t volArray = nullptr;
+    cudaMipmappedArray_t volArray = nullptr, volArrayA = nullptr;
+    TexSet tsA{};                        // CRN_VOLUME_RG8: texture-unit copy of the occupancy chain
     int volArrayDim = 0, volArrayLevels = 0, volArrayFormat = -1;
     cudaArray_t noiseArray = nullptr;
     TexSet ts{};
@@ -260,52 +262,72 @@ int grow_if_overflowed(crn_ctx *c, Bins &b, const uint32_t *cur, bool *grew) {
     return CRN_OK;
 }
 
-void free_vol_textures(crn_ctx *c) {
+void free_chain_textures(cudaMipmappedArray_t &arr, TexSet &ts) {
     for (int l = 0; l < kMaxLevels; l++) {
-        if (c->ts.tex[l]) cudaDestroyTextureObject(c->ts.tex[l]);
-        if (c->ts.surf[l]) cudaDestroySurfaceObject(c->ts.surf[l]);
-        c->ts.tex[l] = 0; c->ts.surf[l] = 0;
+        if (ts.tex[l]) cudaDestroyTextureObject(ts.tex[l]);
+        if (ts.surf[l]) cudaDestroySurfaceObject(ts.surf[l]);
+        ts.tex[l] = 0; ts.surf[l] = 0;
     }
-    if (c->ts.vol) cudaDestroyTextureObject(c->ts.vol);
-    c->ts.vol = 0;
-    if (c->volArray) cudaFreeMipmappedArray(c->volArray);
-    c->volArray = nullptr; c->volArrayDim = c->volArrayLevels = 0; c->volArrayFormat = -1; c->ts.enabled = 0; c->texCurrent = false;
+    if (ts.vol) cudaDestroyTextureObject(ts.vol);
+    ts.vol = 0;
+    if (arr) cudaFreeMipmappedArray(arr);
+    arr = nullptr;
+}
+
+void free_vol_textures(crn_ctx *c) {
+    free_chain_textures(c->volArray, c->ts);
+    free_chain_textures(c->volArrayA, c->tsA);
+    c->ts.volA = 0; c->tsA.enabled = 0;
+    c->volArrayDim = c->volArrayLevels = 0; c->volArrayFormat = -1; c->ts.enabled = 0; c->texCurrent = false;
 }
 
 // the R8 immutable 3D texture with `levels` mips of the reference (src/CloudVolume.cpp:18-23):
 // LINEAR within a level, CLAMP_TO_EDGE x3; the mip-linear blend is done in the kernel.
+int create_chain_textures(crn_ctx *c, cudaMipmappedArray_t &arr, TexSet &ts);
+
 int ensure_vol_textures(crn_ctx *c) {
     const int D = c->vol.dimension, L = c->vol.levels;
-    const bool f32 = c->vol.format == CRN_VOLUME_R32F;
     if (c->volArray && c->volArrayDim == D && c->volArrayLevels == L && c->volArrayFormat == c->vol.format) return CRN_OK;
     CRN_CUDA(c, cudaStreamSynchronize(c->stream));
     free_vol_textures(c);
+    int r;
+    if ((r = create_chain_textures(c, c->volArray, c->ts))) return r;
+    if (c->vol.format == CRN_VOLUME_RG8) {
+        if ((r = create_chain_textures(c, c->volArrayA, c->tsA))) return r;
+        c->ts.volA = c->tsA.vol; c->tsA.enabled = 1;
+    }
+    c->volArrayDim = D; c->volArrayLevels = L; c->volArrayFormat = c->vol.format; c->ts.enabled = 1; c->texCurrent = false;
+    return CRN_OK;
+}
+
+int create_chain_textures(crn_ctx *c, cudaMipmappedArray_t &arr, TexSet &ts) {
+    const int D = c->vol.dimension, L = c->vol.levels;
+    const bool f32 = c->vol.format == CRN_VOLUME_R32F;
     cudaChannelFormatDesc cd = f32 ? cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat)
                                    : cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned);
     const cudaTextureReadMode readMode = f32 ? cudaReadModeElementType : cudaReadModeNormalizedFloat;
-    CRN_CUDA(c, cudaMallocMipmappedArray(&c->volArray, &cd, make_cudaExtent(D, D, D), L, cudaArraySurfaceLoadStore));
+    CRN_CUDA(c, cudaMallocMipmappedArray(&arr, &cd, make_cudaExtent(D, D, D), L, cudaArraySurfaceLoadStore));
     for (int l = 0; l < L; l++) {
         cudaArray_t lvl = nullptr;
-        CRN_CUDA(c, cudaGetMipmappedArrayLevel(&lvl, c->volArray, l));
+        CRN_CUDA(c, cudaGetMipmappedArrayLevel(&lvl, arr, l));
         cudaResourceDesc rd{};
         rd.resType = cudaResourceTypeArray; rd.res.array.array = lvl;
-        CRN_CUDA(c, cudaCreateSurfaceObject(&c->ts.surf[l], &rd));
+        CRN_CUDA(c, cudaCreateSurfaceObject(&ts.surf[l], &rd));
         cudaTextureDesc td{};
         td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
         td.filterMode = cudaFilterModeLinear; td.readMode = readMode; td.normalizedCoords = 1;
-        CRN_CUDA(c, cudaCreateTextureObject(&c->ts.tex[l], &rd, &td, nullptr));
+        CRN_CUDA(c, cudaCreateTextureObject(&ts.tex[l], &rd, &td, nullptr));
     }
     {   // one object over the whole chain for tex3DLod: LINEAR inside a level, POINT between levels
         cudaResourceDesc rd{};
-        rd.resType = cudaResourceTypeMipmappedArray; rd.res.mipmap.mipmap = c->volArray;
+        rd.resType = cudaResourceTypeMipmappedArray; rd.res.mipmap.mipmap = arr;
         cudaTextureDesc td{};
         td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
         td.filterMode = cudaFilterModeLinear; td.mipmapFilterMode = cudaFilterModePoint;
         td.readMode = readMode; td.normalizedCoords = 1;
         td.minMipmapLevelClamp = 0.0f; td.maxMipmapLevelClamp = (float)(L - 1);
-        CRN_CUDA(c, cudaCreateTextureObject(&c->ts.vol, &rd, &td, nullptr));
+        CRN_CUDA(c, cudaCreateTextureObject(&ts.vol, &rd, &td, nullptr));
     }
-    c->volArrayDim = D; c->volArrayLevels = L; c->volArrayFormat = c->vol.format; c->ts.enabled = 1; c->texCurrent = false;
     return CRN_OK;
 }
 
@@ -317,7 +339,7 @@ int check_volume(crn_ctx *c, const crn_volume_desc *d) {
     if (d->levels < 1 || d->levels > maxL || d->levels > kMaxLevels) return fail(c, CRN_ERR_INVALID_ARG, "levels %d out of range [1,%d]", d->levels, maxL);
     if (!(d->xBounds[1] > d->xBounds[0] && d->yBounds[1] > d->yBounds[0] && d->zBounds[1] > d->zBounds[0]))
         return fail(c, CRN_ERR_INVALID_ARG, "bounds must satisfy min < max on every axis");
-    if (d->format != CRN_VOLUME_R8 && d->format != CRN_VOLUME_R32F) return fail(c, CRN_ERR_UNSUPPORTED, "unknown volume format %d", d->format);
+    if (d->format != CRN_VOLUME_R8 && d->format != CRN_VOLUME_R32F && d->format != CRN_VOLUME_RG8) return fail(c, CRN_ERR_UNSUPPORTED, "unknown volume format %d", d->format);
     if (d->format == CRN_VOLUME_R32F && D > 512) return fail(c, CRN_ERR_UNSUPPORTED, "R32F volumes are limited to 512^3 (32-bit level offsets)");
     return CRN_OK;
 }
@@ -382,6 +404,13 @@ int enqueue_voxelize(crn_ctx *c) {
     const size_t D = c->vol.dimension;
     if ((r = reserve(c, c->bits, D * D * D / 8))) return r;
     if ((r = reserve(c, c->chain, c->chainBytes))) return r;
+    const bool paper = c->vol.format == CRN_VOLUME_RG8;
+    if (paper) {
+        if (c->vparams.z0 != 0 || c->vparams.z1 != c->vol.dimension)
+            return fail(c, CRN_ERR_UNSUPPORTED, "CRN_VOLUME_RG8 (paper variant) does not support Z-slab sharding");
+        if ((r = reserve(c, c->bitsA, D * D * D / 8))) return r;
+        if ((r = reserve(c, c->chainA, c->chainBytes))) return r;
+    }
     if ((r = reserve(c, c->misc, 256))) return r;
     if (c->keepPosmap && (r = reserve(c, c->posmap, (size_t)c->W * c->H * 16))) return r;
     if ((r = ensure_bins(c, c->binsL, c->W, c->H, n))) return r;
@@ -406,10 +435,13 @@ int enqueue_voxelize(crn_ctx *c) {
     if (c->timingOn) cudaEventRecord(c->evV[2], st);
     c->launches += launch_voxelize(st, light, c->vparams, sd.nearPlane, sd.clipDistance, (const BoardRec *)c->recL.p,
                                    (const float *)c->lbSorted.p, c->binsL, (uint32_t *)c->bits.p,
-                                   c->keepPosmap ? (float4 *)c->posmap.p : nullptr);
+                                   c->keepPosmap ? (float4 *)c->posmap.p : nullptr, paper ? (uint32_t *)c->bitsA.p : nullptr);
     if (c->timingOn) cudaEventRecord(c->evV[3], st);
     c->launches += launch_mips(st, c->vparams, (const uint32_t *)c->bits.p, (uint8_t *)c->chain.p, (uint32_t *)c->misc.p, true,
                                toTex ? &c->ts : nullptr);
+    if (paper)
+        c->launches += launch_mips(st, c->vparams, (const uint32_t *)c->bitsA.p, (uint8_t *)c->chainA.p, (uint32_t *)c->misc.p + 8,
+                                   true, toTex ? &c->tsA : nullptr);
     const bool whole = c->vparams.z0 == 0 && c->vparams.z1 == c->vol.dimension;
     c->texCurrent = toTex && whole;
     c->maskCurrent = false;
@@ -513,6 +545,8 @@ int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
         if ((r = ensure_vol_textures(c))) return r;
         if (!c->texCurrent) {           // sampler switched after voxelize, or the chain came from an exchange
             c->launches += launch_chain_to_surfaces(st, c->vparams, (const uint8_t *)c->chain.p, c->ts, 0);
+            if (c->vol.format == CRN_VOLUME_RG8)
+                c->launches += launch_chain_to_surfaces(st, c->vparams, (const uint8_t *)c->chainA.p, c->tsA, 0);
             c->texCurrent = true;
         }
     }
@@ -541,7 +575,8 @@ int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
     cudaStreamWaitEvent(st, c->evAuxDone, 0);
     if (c->timingOn) cudaEventRecord(c->evT[2], st);
     c->launches += launch_trace(st, cam, c->vparams, tp, (const BoardRec *)c->recC.p, c->binsC, (const uint32_t *)c->bits.p,
-                                (const uint8_t *)c->chain.p, (const int8_t *)c->noise.p, useTex ? &c->ts : nullptr,
+                                (const uint8_t *)c->chain.p, c->vol.format == CRN_VOLUME_RG8 ? (const uint32_t *)c->bitsA.p : nullptr,
+                                (const uint8_t *)c->chainA.p, (const int8_t *)c->noise.p, useTex ? &c->ts : nullptr,
                                 c->tp.skipEmptySpace ? (const uint32_t *)c->mask.p : nullptr, (const uint32_t *)c->tileOrder.p,
                                 img.p, format, dStats);
     cudaEventRecord(c->evTraceEnd, st);
@@ -1042,6 +1077,19 @@ int crn_read_volume(crn_ctx *c, int32_t level, void *dst) {
     const size_t s = c->vparams.levelSize[level];
     CRN_CUDA(c, cudaMemcpyAsync(dst, (char *)c->chain.p + c->vparams.levelOff[level], s * s * s * c->vparams.texelBytes, cudaMemcpyDeviceToHost,
                                 c->stream));
+    CRN_CUDA(c, cudaStreamSynchronize(c->stream));
+    return CRN_OK;
+}
+
+int crn_read_volume_alpha(crn_ctx *c, int32_t level, void *dst) {
+    if (!c || !dst) return CRN_ERR_INVALID_ARG;
+    if (!c->voxelized) return fail(c, CRN_ERR_STATE, "no volume has been produced yet");
+    if (c->vol.format != CRN_VOLUME_RG8) return fail(c, CRN_ERR_STATE, "the volume has no occupancy channel (format is not CRN_VOLUME_RG8)");
+    if (level < 0 || level >= c->vol.levels) return fail(c, CRN_ERR_INVALID_ARG, "level %d out of range", level);
+    CRN_CUDA(c, cudaSetDevice(c->device));
+    int r = settle(c, false, 0); if (r) return r;
+    const size_t s = c->vparams.levelSize[level];
+    CRN_CUDA(c, cudaMemcpyAsync(dst, (char *)c->chainA.p + c->vparams.levelOff[level], s * s * s, cudaMemcpyDeviceToHost, c->stream));
     CRN_CUDA(c, cudaStreamSynchronize(c->stream));
     return CRN_OK;
 }

@@ -115,12 +115,13 @@ int launch_tile_order(cudaStream_t st, const Bins &b, uint32_t *order);     // o
 const int32_t *sort_tmp_bounds(const void *sortTmp, int n, int pass);   // rect bounds written by prep_kernel (pass 0 light, 1 camera)
 int launch_voxelize(cudaStream_t st, const ViewParams &light, const VolumeParams &vol, const float nearPlane[3],
                     float clip, const BoardRec *recs, const float *lbSorted, const Bins &b, uint32_t *bits,
-                    float4 *posmap);
+                    float4 *posmap, uint32_t *bitsA);
 // texture-unit view of the chain + noise (CRN_SAMPLER_TEXTURE)
 struct TexSet {
     cudaSurfaceObject_t surf[kMaxLevels];   // one per level, written by the mip kernel
     cudaTextureObject_t tex[kMaxLevels];    // one per level: LINEAR, CLAMP, normalized coords, UNORM8 -> float
     cudaTextureObject_t vol;                // the whole mipmapped array: LINEAR in-level, POINT between levels (tex3DLod)
+    cudaTextureObject_t volA;               // CRN_VOLUME_RG8: the occupancy channel's chain, same sampling state
     cudaTextureObject_t noise;              // RGBA8_SNORM, LINEAR, REPEAT
     int32_t enabled;
 };
@@ -131,7 +132,7 @@ int launch_chain_to_surfaces(cudaStream_t st, const VolumeParams &vol, const uin
 int launch_finish_mips(cudaStream_t st, const VolumeParams &vol, uint8_t *chain, int firstLevel);
 int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol, const TraceParams &tp,
                  const BoardRec *recs, const Bins &b, const uint32_t *bits, const uint8_t *chain,
-                 const int8_t *noise, const TexSet *ts, const uint32_t *skipMask, const uint32_t *tileOrder, void *image,
+                 const uint32_t *bitsA, const uint8_t *chainA, const int8_t *noise, const TexSet *ts, const uint32_t *skipMask, const uint32_t *tileOrder, void *image,
                  int format, unsigned long long *stats);
 size_t skipmask_words(const VolumeParams &vol, uint32_t *off);
 int launch_skipmask(cudaStream_t st, const VolumeParams &vol, const uint32_t *bits, const uint8_t *chain, uint32_t *nz,

@@ -35,6 +35,8 @@ struct TraceArgs {
     int tilesX, tilesY;
     const uint32_t *bits;
     const uint8_t *chain;
+    const uint32_t *bitsA;        // CRN_VOLUME_RG8: occupancy channel (level 0 bits + R8 chain), else nullptr
+    const uint8_t *chainA;
     const float2 *noise;          // (g, a) decoded, dim^3
     void *image;
     int format;
@@ -133,12 +135,13 @@ __device__ __forceinline__ float sample_floats(const float *__restrict__ t, int 
     return lerpf(lerpf(c[0], c[1], Y.a), lerpf(c[2], c[3], Y.a), Z.a);
 }
 
-__device__ __forceinline__ float sample_level(const TraceArgs &a, int l, float px, float py, float pz) {
-    if (l == 0) return sample_bits(a.bits, a.vol.dim, px, py, pz);          // level 0 is 0/1 in both formats
+__device__ __forceinline__ float sample_level(const TraceArgs &a, const uint32_t *__restrict__ bits, const uint8_t *__restrict__ chain,
+                                              int l, float px, float py, float pz) {
+    if (l == 0) return sample_bits(bits, a.vol.dim, px, py, pz);            // level 0 is 0/1 in every format
     const float s = 1.0f / (float)(1 << l);
     if (a.vol.texelBytes == 4)
-        return sample_floats(reinterpret_cast<const float *>(a.chain + a.vol.levelOff[l]), a.vol.levelSize[l], px * s, py * s, pz * s);
-    return sample_bytes(a.chain + a.vol.levelOff[l], a.vol.levelSize[l], px * s, py * s, pz * s);
+        return sample_floats(reinterpret_cast<const float *>(chain + a.vol.levelOff[l]), a.vol.levelSize[l], px * s, py * s, pz * s);
+    return sample_bytes(chain + a.vol.levelOff[l], a.vol.levelSize[l], px * s, py * s, pz * s);
 }
 
 // texture(noiseMap, uvw): green and alpha channels only (the shader uses nothing else)
@@ -184,7 +187,8 @@ __device__ __forceinline__ bool sun_fragment(const TraceParams &tp, const ViewPa
 // kTex = false: explicit filtering (CRN_SAMPLER_EXPLICIT);  kTex = true: texture units (CRN_SAMPLER_TEXTURE)
 constexpr int kTraceThreads = 64;     // 2 warp patches per CTA: measured best (256: 5.87 ms, 128: 5.83, 64: 5.79 at C3)
 
-template <bool kTex, bool kStats>
+// kGate: the paper variant's `if (sampleColor.a > 0)` on a second (occupancy) chain, CRN_VOLUME_RG8 only
+template <bool kTex, bool kStats, bool kGate>
 __global__ void __launch_bounds__(kTraceThreads, 2048 / kTraceThreads / 2) trace_kernel(const __grid_constant__ TraceArgs a, const __grid_constant__ ViewParams cam,
                                                     const __grid_constant__ TraceParams tp, const __grid_constant__ TexSet ts) {
     // a 16x16 tile is 8 warp patches; a CTA carries kTraceThreads/32 of them, so a slow patch holds up fewer warps
@@ -340,8 +344,21 @@ __global__ void __launch_bounds__(kTraceThreads, 2048 / kTraceThreads / 2) trace
                                 if (st.frac != 0.0f) s = lerpf(s, tex3DLod<float>(ts.vol, sx, sy, sz, st.lod1), st.frac);
                             } else {
                                 const float fd = (float)D;
-                                s = sample_level(a, st.level0, sx * fd, sy * fd, sz * fd);
-                                if (st.frac != 0.0f) s = lerpf(s, sample_level(a, st.level0 + 1, sx * fd, sy * fd, sz * fd), st.frac);
+                                s = sample_level(a, a.bits, a.chain, st.level0, sx * fd, sy * fd, sz * fd);
+                                if (st.frac != 0.0f) s = lerpf(s, sample_level(a, a.bits, a.chain, st.level0 + 1, sx * fd, sy * fd, sz * fd), st.frac);
+                            }
+                            if constexpr (kGate) {                      // paper/tex/conetracing.tex:36-39
+                                float al;
+                                if constexpr (kTex) {
+                                    al = tex3DLod<float>(ts.volA, sx, sy, sz, st.lod0);
+                                    if (st.frac != 0.0f) al = lerpf(al, tex3DLod<float>(ts.volA, sx, sy, sz, st.lod1), st.frac);
+                                } else {
+                                    const float fd = (float)D;
+                                    al = sample_level(a, a.bitsA, a.chainA, st.level0, sx * fd, sy * fd, sz * fd);
+                                    if (st.frac != 0.0f) al = lerpf(al, sample_level(a, a.bitsA, a.chainA, st.level0 + 1, sx * fd, sy * fd, sz * fd), st.frac);
+                                }
+                                if (!(al > 0.0f)) s = 0.0f;
+                                if (kStats) nFetch += st.frac != 0.0f ? 2 : 1;
                             }
                             indirect = fmaf(s, st.weight, indirect);
                             if (kStats) nFetch += st.frac != 0.0f ? 2 : 1;
@@ -405,14 +422,14 @@ __global__ void __launch_bounds__(kTraceThreads, 2048 / kTraceThreads / 2) trace
 
 int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol, const TraceParams &tp,
                  const BoardRec *recs, const Bins &b, const uint32_t *bits, const uint8_t *chain,
-                 const int8_t *noise, const TexSet *ts, const uint32_t *skipMask, const uint32_t *tileOrder, void *image,
+                 const uint32_t *bitsA, const uint8_t *chainA, const int8_t *noise, const TexSet *ts, const uint32_t *skipMask, const uint32_t *tileOrder, void *image,
                  int format, unsigned long long *stats) {
     TraceArgs a;
     a.vol = vol;
     a.recs = recs;
     a.tileOff = b.tileOff; a.tileCnt = b.tileCnt; a.tileList = b.tileList;
     a.tilesX = b.tilesX; a.tilesY = b.tilesY;
-    a.bits = bits; a.chain = chain;
+    a.bits = bits; a.chain = chain; a.bitsA = bitsA; a.chainA = chainA;
     a.noise = reinterpret_cast<const float2 *>(noise);
     a.image = image; a.format = format; a.stats = stats;
     a.mask = (skipMask && tp.p.skipEmptySpace) ? skipMask : nullptr;
@@ -424,10 +441,17 @@ int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol
     TexSet none{};
     const bool useTex = ts && ts->enabled && tp.p.sampler == CRN_SAMPLER_TEXTURE;
     const int grid = b.tilesX * b.tilesY * (256 / kTraceThreads);
-    if (useTex && tp.stats) trace_kernel<true, true><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, *ts);
-    else if (useTex) trace_kernel<true, false><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, *ts);
-    else if (tp.stats) trace_kernel<false, true><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, none);
-    else trace_kernel<false, false><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, none);
+    const bool gate = bitsA != nullptr;
+    if (gate) {                                                   // opt-in paper variant: stats variant only when asked
+        if (useTex && tp.stats) trace_kernel<true, true, true><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, *ts);
+        else if (useTex) trace_kernel<true, false, true><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, *ts);
+        else if (tp.stats) trace_kernel<false, true, true><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, none);
+        else trace_kernel<false, false, true><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, none);
+    }
+    else if (useTex && tp.stats) trace_kernel<true, true, false><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, *ts);
+    else if (useTex) trace_kernel<true, false, false><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, *ts);
+    else if (tp.stats) trace_kernel<false, true, false><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, none);
+    else trace_kernel<false, false, false><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, none);
     return 1;
 }
 

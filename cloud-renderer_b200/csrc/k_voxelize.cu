@@ -38,6 +38,7 @@ struct VoxArgs {
     const uint32_t *tileOff, *tileCnt, *tileList;
     int tilesX;
     uint32_t *bits;
+    uint32_t *bitsA;              // CRN_VOLUME_RG8: the occupancy (alpha) set also receives the lit stores, else nullptr
     float4 *posmap;
 };
 
@@ -139,7 +140,100 @@ __global__ void __launch_bounds__(256) voxelize_kernel(VoxArgs a, ViewParams lp)
         }
         const uint32_t peers = __match_any_sync(0xFFFFFFFFu, word);
         const uint32_t merged = __reduce_or_sync(peers, bit);
-        if (ok && lane == __ffs(peers) - 1) atomicOr(&a.bits[word], merged);
+        if (ok && lane == __ffs(peers) - 1) {
+            atomicOr(&a.bits[word], merged);
+            if (a.bitsA) atomicOr(&a.bitsA[word], merged);      // (1,1,1,1): the lit shell is occupied too
+        }
+    }
+}
+
+// Paper variant, first-pass interior march (res/first_voxelize.glsl:53-58, live in
+// paper/tex/voxelization.tex:13-27): EVERY non-discarded fragment of EVERY billboard (image
+// stores are not depth-tested, so there is no front-to-back early-out here) walks the chord of
+// its sphere along the light direction in steps of stepSize and marks the voxels it lands in.
+// Same tiling as voxelize_kernel; a warp's 8x4 texel patch spans about one voxel, so per step
+// the 32 lanes hit 1-4 distinct words: match.any/redux.or merges them and the leader skips the
+// atomic when the word already holds the bits it stored on the previous step.
+__global__ void __launch_bounds__(256) interior_kernel(VoxArgs a, ViewParams lp) {
+    const int tile = blockIdx.x;
+    const uint32_t cnt = a.tileCnt[tile];
+    if (cnt == 0) return;
+    const uint32_t off = a.tileOff[tile];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tx = tile % a.tilesX, ty = tile / a.tilesX;
+    const int px = tx * kTile + (warp & 1) * 8 + (lane & 7);
+    const int py = ty * kTile + (warp >> 1) * 4 + (lane >> 3);
+    const bool valid = px < lp.W && py < lp.H;
+    const float ndcx = ((float)px + 0.5f) / (float)lp.W * 2.0f - 1.0f;
+    const float ndcy = ((float)py + 0.5f) / (float)lp.H * 2.0f - 1.0f;
+    const float xv = (ndcx - lp.P[12]) / lp.P[0];
+    const float yv = (ndcy - lp.P[13]) / lp.P[5];
+    const int D = a.vol.dim;
+    const float fd = (float)D;
+    const float rangeX = a.vol.xB[1] - a.vol.xB[0], rangeY = a.vol.yB[1] - a.vol.yB[0], rangeZ = a.vol.zB[1] - a.vol.zB[0];
+    const int wordsPerRow = D >> 5;
+    const float step = a.vol.stepSize;
+    const float kx = fd / rangeX, ky = fd / rangeY, kz = fd / rangeZ;      // approximate index scale (prefilter only)
+    uint32_t lastWord = 0xFFFFFFFFu, lastBits = 0;
+
+    for (uint32_t e = 0; e < cnt; e++) {
+        const uint32_t k = a.tileList[off + e];
+        const float4 r0 = *reinterpret_cast<const float4 *>(&a.recs[k].cx);
+        const float4 r1 = *reinterpret_cast<const float4 *>(&a.recs[k].xv);
+        const float radius = r0.w;
+        const float u = xv - r1.x, v = yv - r1.y;
+        bool act = valid && fabsf(u) < radius && fabsf(v) < radius;
+        float two = 0.0f, sx = 0.0f, sy = 0.0f, sz = 0.0f;
+        if (act) {
+            const float fx = r0.x + (u * lp.right[0] + v * lp.up[0]);
+            const float fy = r0.y + (u * lp.right[1] + v * lp.up[1]);
+            const float fz = r0.z + (u * lp.right[2] + v * lp.up[2]);
+            const float dx = fx - r0.x, dy = fy - r0.y, dz = fz - r0.z;
+            float sc = sqrtf((dx * dx + dy * dy) + dz * dz) / radius;
+            sc = sqrtf(fmaxf(0.0f, 1.0f - sc * sc));
+            act = !(sc < 0.01f);                                            // discard
+            const float dist = radius * sc;
+            two = 2.0f * dist;
+            sx = fx - lp.nrm[0] * dist; sy = fy - lp.nrm[1] * dist; sz = fz - lp.nrm[2] * dist;   // start
+        }
+        float s = 0.0f;
+        while (__any_sync(0xFFFFFFFFu, act && s < two)) {
+            bool ok = act && s < two;
+            uint32_t word = 0xFFFFFFFFu, bit = 0;
+            if (ok) {
+                const float qx = sx + lp.nrm[0] * s, qy = sy + lp.nrm[1] * s, qz = sz + lp.nrm[2] * s;
+                // one multiply per axis gives the voxel coordinate to ~4 ulp; only when that lands within 1e-3 of an
+                // integer (where truncation could differ) is the shader's own divide-then-scale evaluated
+                float vx = (qx - a.vol.xB[0]) * kx, vy = (qy - a.vol.yB[0]) * ky, vz = (qz - a.vol.zB[0]) * kz;
+                const float nearInt = fminf(fminf(fabsf(vx - rintf(vx)), fabsf(vy - rintf(vy))), fabsf(vz - rintf(vz)));
+                if (nearInt < 1.0e-3f) {
+                    vx = fd * ((qx - a.vol.xB[0]) / rangeX);
+                    vy = fd * ((qy - a.vol.yB[0]) / rangeY);
+                    vz = fd * ((qz - a.vol.zB[0]) / rangeZ);
+                }
+                ok = vx > -1.0f && vx < fd && vy > -1.0f && vy < fd && vz > -1.0f && vz < fd;
+                if (ok) {
+                    const int ix = (int)vx, iy = (int)vy, iz = (int)vz;
+                    ok = iz >= a.vol.z0 && iz < a.vol.z1;
+                    if (ok) {
+                        word = (uint32_t)((iz * D + iy) * wordsPerRow + (ix >> 5));
+                        bit = 1u << (ix & 31);
+                    }
+                }
+            }
+            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, word);
+            const uint32_t merged = __reduce_or_sync(peers, bit);
+            if (ok && lane == __ffs(peers) - 1) {
+                if (word != lastWord || (merged & ~lastBits)) {
+                    // overlapping spheres and neighbouring patches have usually set these bits already: a plain
+                    // (possibly stale, hence only ever pessimistic) load saves the contended atomic
+                    if ((a.bitsA[word] & merged) != merged) atomicOr(&a.bitsA[word], merged);
+                    lastBits = (word == lastWord ? lastBits : 0u) | merged;
+                    lastWord = word;
+                }
+            }
+            s += step;
+        }
     }
 }
 
@@ -147,21 +241,25 @@ __global__ void __launch_bounds__(256) voxelize_kernel(VoxArgs a, ViewParams lp)
 
 int launch_voxelize(cudaStream_t st, const ViewParams &light, const VolumeParams &vol, const float nearPlane[3],
                     float clip, const BoardRec *recs, const float *lbSorted, const Bins &b, uint32_t *bits,
-                    float4 *posmap) {
+                    float4 *posmap, uint32_t *bitsA) {
     VoxArgs a;
     a.vol = vol;
     for (int k = 0; k < 3; k++) a.nearPlane[k] = nearPlane[k];
     a.clip = clip;
     a.recs = recs; a.lb = lbSorted;
     a.tileOff = b.tileOff; a.tileCnt = b.tileCnt; a.tileList = b.tileList; a.tilesX = b.tilesX;
-    a.bits = bits; a.posmap = posmap;
+    a.bits = bits; a.posmap = posmap; a.bitsA = bitsA;
     const size_t words = (size_t)vol.dim * vol.dim * vol.dim / 32;
     const size_t w0 = (size_t)vol.z0 * vol.dim * (vol.dim / 32), w1 = (size_t)vol.z1 * vol.dim * (vol.dim / 32);
     (void)words;
     cudaMemsetAsync(bits + w0, 0, (w1 - w0) * sizeof(uint32_t), st);       // CloudVolume::clearGPU for the owned slab
     if (posmap) cudaMemsetAsync(posmap, 0, (size_t)light.W * light.H * sizeof(float4), st);   // clearPositionMap
+    if (bitsA) {
+        cudaMemsetAsync(bitsA + w0, 0, (w1 - w0) * sizeof(uint32_t), st);
+        interior_kernel<<<b.tilesX * b.tilesY, 256, 0, st>>>(a, light);
+    }
     voxelize_kernel<<<b.tilesX * b.tilesY, 256, 0, st>>>(a, light);
-    return 1;
+    return bitsA ? 2 : 1;
 }
 
 } // namespace crn

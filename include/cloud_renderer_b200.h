@@ -51,6 +51,11 @@ extern "C" {
 /* volume texel formats. R8 is the shipped reference format (src/CloudVolume.cpp:18). */
 #define CRN_VOLUME_R8      0
 #define CRN_VOLUME_R32F    1   /* float texels: level 0 = 0.0/1.0, mips = plain 2x2x2 means (no re-quantisation) */
+#define CRN_VOLUME_RG8     2   /* paper variant (opt-in): channel 0 = the lit shell (the paper's rgb), channel 1 = its
+                                * alpha = every voxel inside a billboard sphere (first-pass interior march,
+                                * res/first_voxelize.glsl:53-58 as in paper/tex/voxelization.tex:13-27) | lit;
+                                * two planar R8 chains; the cone sum is gated by alpha > 0
+                                * (paper/tex/conetracing.tex:36-39) */
 
 typedef struct crn_ctx crn_ctx;
 
@@ -256,6 +261,9 @@ int crn_finish_mips(crn_ctx *ctx, int32_t first_level);
 /* ---- inspection (the reference's debug views: src/Shaders/VoxelShader.cpp:102-133,
  *      src/main.cpp:172-198) ---------------------------------------------------------- */
 int crn_read_volume(crn_ctx *ctx, int32_t level, void *dst_host);          /* size_l^3 texels (uint8 or float) */
+/* CRN_VOLUME_RG8 only: one level of the occupancy (alpha) channel, s^3 bytes, same order as
+ * crn_read_volume (what the reference's debug voxel view draws as black cubes) */
+int crn_read_volume_alpha(crn_ctx *ctx, int32_t level, void *dst_host);
 int crn_count_active_voxels(crn_ctx *ctx, uint64_t *count);                  /* "Voxels in scene" */
 int crn_keep_position_map(crn_ctx *ctx, int32_t enable);                    /* default off   */
 int crn_read_position_map(crn_ctx *ctx, float *dst_host_rgba32f);           /* W*H*4 floats  */

@@ -83,7 +83,7 @@ public:
         d.position[0] = position.x; d.position[1] = position.y; d.position[2] = position.z;
         d.xBounds[0] = xBounds.x; d.xBounds[1] = xBounds.y; d.yBounds[0] = yBounds.x; d.yBounds[1] = yBounds.y;
         d.zBounds[0] = zBounds.x; d.zBounds[1] = zBounds.y;
-        d.fluffiness = fluffiness; d.format = CRN_VOLUME_R8;
+        d.fluffiness = fluffiness; d.format = format;
         check(ctx, crn_set_volume(ctx, &d));
     }
     void clearGPU() {}                                   // the clear is part of crn_voxelize (src/CloudVolume.cpp:96-100)
@@ -149,6 +149,7 @@ public:
     int levels;
     Billboards billboards;
     float fluffiness = 1.f;
+    int format = CRN_VOLUME_R8;          // CRN_VOLUME_R32F / CRN_VOLUME_RG8 (paper variant) are opt-in extensions
     crn_ctx *ctx = nullptr;                              // replaces volId / instancedQuad VBOs
 };
 

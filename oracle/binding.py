@@ -111,6 +111,16 @@ def voxelize(scene, want_posmap=True):
     return posmap, depth, level0
 
 
+def voxelize_paper(scene):
+    """paper variant (CRN_VOLUME_RG8): -> (level0 rgb (D,D,D) u8, level0 alpha (D,D,D) u8)"""
+    s = _scene_struct(scene)
+    D = scene.vol.dimension
+    level0 = np.zeros((D, D, D), dtype=np.uint8)
+    alpha0 = np.zeros((D, D, D), dtype=np.uint8)
+    lib().orc_voxelize_paper(C.byref(s), C.c_void_p(level0.ctypes.data), C.c_void_p(alpha0.ctypes.data))
+    return level0, alpha0
+
+
 def chain_size(D, levels):
     return sum(max(1, D >> l) ** 3 for l in range(levels))
 

@@ -226,16 +226,28 @@ inline float board_radius(const crn_volume_desc &vol, float s) {
 struct Chain {                  // R8 immutable 3D texture with `levels` mips (src/CloudVolume.cpp:18-23);
     const uint8_t *data;        // or, for CRN_VOLUME_R32F, the same chain with float texels (fdata)
     const float *fdata;
+    const uint8_t *alpha;       // CRN_VOLUME_RG8 (paper variant): the occupancy channel's own R8 chain, else NULL
     int dim, levels;
     size_t off[16]; int size[16];   // element offsets
 };
 
 Chain make_chain(const void *data, int dim, int levels, bool is_float = false) {
-    Chain c; c.dim = dim; c.levels = levels;
+    Chain c; c.dim = dim; c.levels = levels; c.alpha = nullptr;
     c.data = is_float ? nullptr : (const uint8_t *)data;
     c.fdata = is_float ? (const float *)data : nullptr;
     size_t o = 0; int s = dim;
     for (int l = 0; l < levels; l++) { c.off[l] = o; c.size[l] = s; o += (size_t)s * s * s; s = std::max(1, s / 2); }
+    return c;
+}
+
+// the chain a scene's cone trace reads; CRN_VOLUME_RG8 is planar: the rgb chain, then the alpha chain
+Chain scene_chain(const crn_volume_desc &vol, const uint8_t *chain_bytes) {
+    Chain c = make_chain(chain_bytes, vol.dimension, vol.levels, vol.format == CRN_VOLUME_R32F);
+    if (vol.format == CRN_VOLUME_RG8) {
+        size_t total = 0;
+        for (int l = 0; l < c.levels; l++) total += (size_t)c.size[l] * c.size[l] * c.size[l];
+        c.alpha = chain_bytes + total;
+    }
     return c;
 }
 
@@ -353,6 +365,11 @@ float trace_cone(const Chain &c, const TraceUniforms &u, vec3 position, vec3 dir
         float lod = log2f(fmaxf(1.0f, 2.0f * coneRadius));
         float s = texture_lod(c, position + direction * coneHeight, lod + u.p.vctLodOffset);
         (*taps)++;
+        if (c.alpha) {                                   // paper/tex/conetracing.tex:36-39: if (sampleColor.a > 0.f)
+            Chain ca = c; ca.data = c.alpha; ca.fdata = nullptr; ca.alpha = nullptr;
+            float al = texture_lod(ca, position + direction * coneHeight, lod + u.p.vctLodOffset);
+            if (!(al > 0.0f)) s = 0.0f;
+        }
         color += s * (float)i / ((float)steps * u.p.vctDownScaling);
         coneHeight += coneRadius;
     }
@@ -600,7 +617,21 @@ void orc_build_noise(const int8_t *alpha, int32_t dim, int8_t *rgba) {
  * GL_DEPTH_COMPONENT); GL_LESS against a 1.0 clear, so equal depths keep the earlier
  * instance and a clamped depth of 1 never lands; ivec3() truncates toward zero;
  * imageStore outside [0,D)^3 is dropped (GL 4.4 §8.26). */
+static void voxelize_impl(const orc_scene *sc, float *posmap_out, float *depth_out, uint8_t *level0, uint8_t *alpha0);
 void orc_voxelize(const orc_scene *sc, float *posmap_out, float *depth_out, uint8_t *level0) {
+    voxelize_impl(sc, posmap_out, depth_out, level0, nullptr);
+}
+
+/* Paper variant (opt-in, CRN_VOLUME_RG8).  The shipped first pass has its interior march commented
+ * out (res/first_voxelize.glsl:53-58); paper/tex/voxelization.tex:13-27 describes it live: every non-discarded
+ * fragment of every billboard (image stores are not depth-tested) walks the chord of its sphere from the far side
+ * towards the light in steps of `stepSize` and stores (0,0,0,1); pass 2 then stores (1,1,1,1) on the lit shell.
+ * level0: the rgb channel (identical to orc_voxelize's), alpha0: the a channel = interior | lit, both D^3 bytes. */
+void orc_voxelize_paper(const orc_scene *sc, uint8_t *level0, uint8_t *alpha0) {
+    voxelize_impl(sc, nullptr, nullptr, level0, alpha0);
+}
+
+static void voxelize_impl(const orc_scene *sc, float *posmap_out, float *depth_out, uint8_t *level0, uint8_t *alpha0) {
     const int W = sc->width, H = sc->height, D = sc->vol.dimension;
     crn_sun_derived sd;
     orc_sun_update(&sc->vol, &sc->sun, &sd);
@@ -610,6 +641,7 @@ void orc_voxelize(const orc_scene *sc, float *posmap_out, float *depth_out, uint
     float clip = sd.clipDistance;
     vec3 vp = v3(sc->vol.position);
 
+    if (alpha0) std::memset(alpha0, 0, (size_t)D * D * D);
     std::vector<float> posmap((size_t)W * H * 4, 0.0f);       // glClearColor(0,0,0,0)
     std::vector<float> depth((size_t)W * H, 1.0f);            // glClear depth = 1
     std::vector<QuadSetup> quads(sc->n_boards);
@@ -630,6 +662,15 @@ void orc_voxelize(const orc_scene *sc, float *posmap_out, float *depth_out, uint
                 if (sphereContrib < 0.01f) continue;            // discard
                 vec3 dir = lb.nrm;
                 float dist = radius * sphereContrib;
+                if (alpha0) {                                   // res/first_voxelize.glsl:53-58 (commented out as shipped)
+                    vec3 start = fragPos - dir * dist;
+                    for (float s = 0.0f; s < 2.0f * dist; s += vu.stepSize) {
+                        vec3 f = voxel_lerp(vu, start + dir * s);
+                        if (!(f.x > -1.0f && f.x < (float)D && f.y > -1.0f && f.y < (float)D && f.z > -1.0f && f.z < (float)D)) continue;
+                        // every thread stores the same constant: the race is benign (and is the shader's own)
+                        alpha0[((size_t)(int)f.z * D + (int)f.y) * D + (int)f.x] = 255;
+                    }
+                }
                 vec3 worldPos = fragPos + dir * dist;
                 float d = distance(nearP, worldPos) / clip;
                 d = saturate(d);
@@ -652,6 +693,7 @@ void orc_voxelize(const orc_scene *sc, float *posmap_out, float *depth_out, uint
         if (!(f.x > -1.0f && f.x < (float)D && f.y > -1.0f && f.y < (float)D && f.z > -1.0f && f.z < (float)D)) return;
         int x = (int)f.x, y = (int)f.y, z = (int)f.z;
         level0[((size_t)z * D + y) * D + x] = 255;
+        if (alpha0) alpha0[((size_t)z * D + y) * D + x] = 255;             // (1,1,1,1)
     };
     for (size_t t = 0; t < (size_t)W * H; t++) {
         if (!(posmap[4 * t + 3] > 0.0f)) continue;
@@ -724,7 +766,7 @@ void orc_cone_trace(const orc_scene *sc, const uint8_t *chain_bytes, float *imag
     const int W = sc->width, H = sc->height;
     row0 = std::max(0, row0); row1 = std::min(H, row1);
     ViewBasis cam = make_basis(sc->cam.P, sc->cam.V);
-    Chain chain = make_chain(chain_bytes, sc->vol.dimension, sc->vol.levels, sc->vol.format == CRN_VOLUME_R32F);
+    Chain chain = scene_chain(sc->vol, chain_bytes);
     Noise nz = {sc->noise, sc->noise_dim};
     TraceUniforms u;
     u.p = sc->tp;
@@ -812,7 +854,7 @@ void orc_cone_lods(const crn_trace_params *tp, float *lods, float *heights) {
 int32_t orc_conetrace_fragment(const orc_scene *sc, const uint8_t *chain_bytes, const float fragPos[3],
                                const float fragTex[2], const float center[3], float radius, float color[4]) {
     ViewBasis cam = make_basis(sc->cam.P, sc->cam.V);
-    Chain chain = make_chain(chain_bytes, sc->vol.dimension, sc->vol.levels, sc->vol.format == CRN_VOLUME_R32F);
+    Chain chain = scene_chain(sc->vol, chain_bytes);
     Noise nz = {sc->noise, sc->noise_dim};
     TraceUniforms u;
     u.p = sc->tp;

@@ -179,3 +179,35 @@ def test_r32f_chain_in_the_oracle(pkg, scenes, orc):
     assert np.array_equal(cf * 8.0 ** 3 % 1.0, np.zeros_like(cf)), "float mips of a 0/1 volume are multiples of 8^-3"
     c8 = orc.mips((l0 * 255).astype(np.uint8), 4)
     assert np.abs(cf - c8 / 255.0).max() <= 0.5 / 255 * 3 + 1e-6        # one rounding per level
+
+
+def test_paper_variant_fills_the_sphere(pkg, scenes, orc):
+    """§8 f2 (CRN_VOLUME_RG8): one billboard of radius 2 — the occupancy channel is the solid sphere (chords marched
+    in steps of one voxel), the lit channel is unchanged and contained in it, and the alpha gate leaves the image alone."""
+    s = scenes.make_scene("tiny", boards=1)
+    s.board_pos[:] = 0.0
+    s.board_scale[:] = 2.0
+    s.sun.position[:] = (125.0, 0.0, 0.0)
+    s.width, s.height = 256, 256
+    _, _, l0 = orc.voxelize(s, want_posmap=False)
+    l0p, a0 = orc.voxelize_paper(s)
+    assert np.array_equal(l0p, l0)
+    assert (a0 >= l0).all()
+    D, vox = 32, 10.0 / 32
+    z, y, x = np.indices((D, D, D))
+    rad = np.linalg.norm((np.stack([x, y, z], -1) + 0.5) * vox - 5.0, axis=-1)
+    inside = a0 > 0
+    assert inside[rad < 2.0 - vox].all(), "a voxel well inside the sphere is not marked"
+    # outside the sphere only the lit shell's +-stepSize/sqrt(3) neighbours (second pass) may be marked
+    assert not inside[rad > 2.0 + vox * (np.sqrt(3) / 2 + 1.0) + 1e-6].any()
+    vol = inside.sum() * vox ** 3                                # every voxel the solid sphere touches: r .. r + ~1 voxel
+    assert 4.0 / 3.0 * np.pi * 2.0 ** 3 < vol < 4.0 / 3.0 * np.pi * (2.0 + 1.2 * vox) ** 3
+    chain, chain_a = orc.mips(l0, s.vol.levels), orc.mips(a0, s.vol.levels)
+    assert (chain_a >= chain).all()                              # box filter + round-half-up are monotone
+    s = scenes.make_scene("tiny")
+    l0, a0 = orc.voxelize_paper(s)
+    chain, chain_a = orc.mips(l0, s.vol.levels), orc.mips(a0, s.vol.levels)
+    plain, _, _ = orc.cone_trace(s, chain, want_u8=False)
+    s.vol.format = pkg.VOLUME_RG8
+    gated, _, _ = orc.cone_trace(s, np.concatenate([chain, chain_a]), want_u8=False)
+    assert np.array_equal(plain.view(np.uint32), gated.view(np.uint32))
