@@ -654,7 +654,7 @@ void crn_destroy(crn_ctx *c) {
     cudaStreamSynchronize(c->stream);
     if (c->copyStream) cudaStreamSynchronize(c->copyStream);
     if (c->auxStream) cudaStreamSynchronize(c->auxStream);
-    DevBuf *bufs[] = {&c->pos, &c->scale, &c->keyL, &c->keyC, &c->rankL, &c->rankC, &c->recTmpL, &c->recTmpC, &c->rectTmpL,
+    DevBuf *bufs[] = {&c->pos0, &c->bitsA, &c->chainA, &c->pos, &c->scale, &c->keyL, &c->keyC, &c->rankL, &c->rankC, &c->recTmpL, &c->recTmpC, &c->rectTmpL,
                       &c->rectTmpC, &c->lbTmp, &c->recL, &c->recC, &c->rectL, &c->rectC, &c->lbSorted, &c->drawOrder, &c->bits,
                       &c->chain, &c->noise, &c->posmap, &c->image, &c->image2, &c->misc, &c->maskNz, &c->maskDil, &c->mask, &c->sortTmp, &c->sortTmpC, &c->tileOrder};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
