@@ -175,7 +175,18 @@ struct crn_ctx {
     bool copyPending[2] = {false, false};
     int imgSel = 0;
 
-    cudaEvent_t evV[5] = {}, evT[4] = {};
+    // the light-side set-up of frame k+1 (billboard upload, prep, sort, bin, voxelize kernel) touches nothing the trace of
+    // frame k reads (texture sampler: texture arrays + masks; the occupancy bits are consumed by the mip/mask kernels
+    // before the trace starts), so it runs on its own stream and overlaps that trace; the mip + mask kernels, which
+    // overwrite what the trace samples, stay on the caller's stream behind it
+    cudaStream_t lightStream = nullptr;
+    cudaEvent_t evLightDone = nullptr, evBitsFree = nullptr, evMainMark = nullptr;
+    bool bitsFreeValid = false, auxDoneValid = false;
+    cudaEvent_t evCur[2] = {};           // cursor read-back done (light, camera): the next bin pass resets the cursors
+    bool curValid[2] = {false, false};
+    bool bitsExposed = false;            // crn_volume_bits_ptr handed the set to the caller: keep strict stream order
+
+    cudaEvent_t evV[6] = {}, evT[4] = {};
     bool evVValid = false, evTValid = false;
 };
 
@@ -203,11 +214,13 @@ int reserve(crn_ctx *c, DevBuf &b, size_t bytes) {
     CRN_CUDA(c, cudaStreamSynchronize(c->stream));
     if (c->copyStream) CRN_CUDA(c, cudaStreamSynchronize(c->copyStream));
     if (c->auxStream) CRN_CUDA(c, cudaStreamSynchronize(c->auxStream));
+    if (c->lightStream) CRN_CUDA(c, cudaStreamSynchronize(c->lightStream));
     if (b.p) CRN_CUDA(c, cudaFree(b.p));
     b.p = nullptr; b.cap = 0;
     const size_t want = bytes + bytes / 4 + 256;
     CRN_CUDA(c, cudaMalloc(&b.p, want));
     CRN_CUDA(c, cudaMemsetAsync(b.p, 0, want, c->stream));      // tickets / counters start at zero
+    CRN_CUDA(c, cudaStreamSynchronize(c->stream));              // the first user may be another of the context's streams
     b.cap = want;
     return CRN_OK;
 }
@@ -216,6 +229,7 @@ int alloc_u32(crn_ctx *c, uint32_t *&p, size_t &have, size_t want) {
     if (want <= have) return CRN_OK;
     CRN_CUDA(c, cudaStreamSynchronize(c->stream));
     if (c->auxStream) CRN_CUDA(c, cudaStreamSynchronize(c->auxStream));
+    if (c->lightStream) CRN_CUDA(c, cudaStreamSynchronize(c->lightStream));
     if (p) CRN_CUDA(c, cudaFree(p));
     p = nullptr; have = 0;
     CRN_CUDA(c, cudaMalloc(&p, want * sizeof(uint32_t)));
@@ -234,7 +248,7 @@ int ensure_bins(crn_ctx *c, Bins &b, int W, int H, int n) {
         b.tilesAlloc = tiles;
     }
     (void)coarse;
-    if (!b.cursors) { CRN_CUDA(c, cudaMalloc(&b.cursors, 4 * sizeof(uint32_t))); CRN_CUDA(c, cudaMemsetAsync(b.cursors, 0, 4 * sizeof(uint32_t), c->stream)); }
+    if (!b.cursors) { CRN_CUDA(c, cudaMalloc(&b.cursors, 4 * sizeof(uint32_t))); CRN_CUDA(c, cudaMemsetAsync(b.cursors, 0, 4 * sizeof(uint32_t), c->stream)); CRN_CUDA(c, cudaStreamSynchronize(c->stream)); }
     const bool forced = c->poolMin != ((size_t)1 << 20);
     int r = alloc_u32(c, b.coarseList, b.coarseCap, 4 * (forced ? c->poolMin : std::max<size_t>((size_t)1 << 16, (size_t)n * 8))); if (r) return r;   // uint4 entries
     // first guess: ~100 tiles per billboard, or 32 entries per tile, whichever is larger; grown on demand
@@ -367,6 +381,20 @@ void fill_vparams(crn_ctx *c) {
     v.z1 = c->z1 < 0 ? d.dimension : c->z1;
 }
 
+// Billboard arrays are written on the light stream, so the upload of frame k+1 does not queue behind the trace of
+// frame k.  It has to follow (a) the camera-side set-up of the last trace, which reads the arrays on the side stream,
+// (b) the light-side set-up of the last voxelize (same stream: in order) and (c), for a device-resident source,
+// whatever the caller queued on their stream to produce it.
+cudaStream_t upload_stream(crn_ctx *c, bool sourceOnCallerStream) {
+    cudaStream_t up = c->lightStream;
+    if (c->auxDoneValid) cudaStreamWaitEvent(up, c->evAuxDone, 0);
+    if (sourceOnCallerStream) {
+        cudaEventRecord(c->evMainMark, c->stream);
+        cudaStreamWaitEvent(up, c->evMainMark, 0);
+    }
+    return up;
+}
+
 int require(crn_ctx *c, bool ok, const char *what) {
     return ok ? CRN_OK : fail(c, CRN_ERR_STATE, "%s has not been set", what);
 }
@@ -417,7 +445,15 @@ int enqueue_voxelize(crn_ctx *c) {
     const bool toTex = c->tp.sampler == CRN_SAMPLER_TEXTURE;
     if (toTex && (r = ensure_vol_textures(c))) return r;
 
-    cudaStream_t st = c->stream;
+    // ---- light stream: everything up to the occupancy bits
+    cudaStream_t st = c->lightStream;
+    cudaStreamWaitEvent(st, c->evBoards, 0);
+    if (c->bitsFreeValid) cudaStreamWaitEvent(st, c->evBitsFree, 0);     // last readers of the previous frame's bits
+    if (c->bitsExposed) {                                                // the caller may have queued work on the bits
+        cudaEventRecord(c->evMainMark, c->stream);
+        cudaStreamWaitEvent(st, c->evMainMark, 0);
+    }
+    if (c->curValid[0]) cudaStreamWaitEvent(st, c->evCur[0], 0);
     if (c->timingOn) cudaEventRecord(c->evV[0], st);
     const float zero3[3] = {0, 0, 0};
     c->launches += launch_prep_sort(st, (const float *)c->pos.p, (const float *)c->scale.p, n, c->vol.fluffiness, c->vol.position,
@@ -432,11 +468,17 @@ int enqueue_voxelize(crn_ctx *c) {
     cudaEventRecord(c->evBin[0], st);
     cudaStreamWaitEvent(c->copyStream, c->evBin[0], 0);
     cudaMemcpyAsync(c->hCursors, c->binsL.cursors, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->copyStream);
+    cudaEventRecord(c->evCur[0], c->copyStream); c->curValid[0] = true;
     if (c->timingOn) cudaEventRecord(c->evV[2], st);
     c->launches += launch_voxelize(st, light, c->vparams, sd.nearPlane, sd.clipDistance, (const BoardRec *)c->recL.p,
                                    (const float *)c->lbSorted.p, c->binsL, (uint32_t *)c->bits.p,
                                    c->keepPosmap ? (float4 *)c->posmap.p : nullptr, paper ? (uint32_t *)c->bitsA.p : nullptr);
     if (c->timingOn) cudaEventRecord(c->evV[3], st);
+    cudaEventRecord(c->evLightDone, st);
+    // ---- caller's stream: expand the bits into the chain / textures / masks the trace samples
+    st = c->stream;
+    cudaStreamWaitEvent(st, c->evLightDone, 0);
+    if (c->timingOn) cudaEventRecord(c->evV[5], st);
     c->launches += launch_mips(st, c->vparams, (const uint32_t *)c->bits.p, (uint8_t *)c->chain.p, (uint32_t *)c->misc.p, true,
                                toTex ? &c->ts : nullptr);
     if (paper)
@@ -449,6 +491,8 @@ int enqueue_voxelize(crn_ctx *c) {
         if ((r = build_masks(c))) return r;
     }
     if (c->timingOn) { cudaEventRecord(c->evV[4], st); c->evVValid = true; }
+    cudaEventRecord(c->evBitsFree, st);
+    c->bitsFreeValid = true;
     CRN_CUDA(c, cudaGetLastError());
     c->voxelized = true;
     return CRN_OK;
@@ -537,8 +581,10 @@ int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
     TraceParams tp;
     build_trace_params(c, cam, &tp);
     cudaStream_t st = c->stream;
+    bool readsBits = c->tp.sampler != CRN_SAMPLER_TEXTURE;          // the explicit sampler reads level 0 from the bits
     if (c->tp.skipEmptySpace && !c->maskCurrent) {     // chain came from an exchange, or the option was just switched on
         if ((r = build_masks(c))) return r;
+        readsBits = true;
     }
     const bool useTex = c->tp.sampler == CRN_SAMPLER_TEXTURE;
     if (useTex) {
@@ -557,6 +603,7 @@ int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
     cudaStream_t ax = c->auxStream;
     cudaStreamWaitEvent(ax, c->evBoards, 0);
     if (c->traceEndValid) cudaStreamWaitEvent(ax, c->evTraceEnd, 0);
+    if (c->curValid[1]) cudaStreamWaitEvent(ax, c->evCur[1], 0);
     if (c->timingOn) cudaEventRecord(c->evAuxT[0], ax);
     const float zero3[3] = {0, 0, 0};
     c->launches += launch_prep_sort(ax, (const float *)c->pos.p, (const float *)c->scale.p, n, c->vol.fluffiness, c->vol.position, cam,
@@ -569,6 +616,7 @@ int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
     cudaEventRecord(c->evBin[1], ax);
     cudaStreamWaitEvent(c->copyStream, c->evBin[1], 0);
     cudaMemcpyAsync(c->hCursors + 2, c->binsC.cursors, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->copyStream);
+    cudaEventRecord(c->evCur[1], c->copyStream); c->curValid[1] = true;
     c->launches += launch_tile_order(ax, c->binsC, (uint32_t *)c->tileOrder.p);
     if (c->timingOn) cudaEventRecord(c->evAuxT[2], ax);
     cudaEventRecord(c->evAuxDone, ax);
@@ -581,6 +629,11 @@ int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
                                 img.p, format, dStats);
     cudaEventRecord(c->evTraceEnd, st);
     c->traceEndValid = true;
+    c->auxDoneValid = true;
+    if (readsBits) {                                   // the next voxelize must not clear the bits under this trace
+        cudaEventRecord(c->evBitsFree, st);
+        c->bitsFreeValid = true;
+    }
     if (c->timingOn) { cudaEventRecord(c->evT[3], st); c->evTValid = true; }
     if (c->statsOn) cudaMemcpyAsync(c->hStats, dStats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
     CRN_CUDA(c, cudaGetLastError());
@@ -627,6 +680,11 @@ int crn_create(int device, void *stream, crn_ctx **out) {
     std::memset(c->hStats, 0, 8 * sizeof(unsigned long long));
     cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&c->auxStream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&c->lightStream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&c->evLightDone, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->evBitsFree, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->evMainMark, cudaEventDisableTiming);
+    for (auto &ev : c->evCur) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->evBoards, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->evAuxDone, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->evTraceEnd, cudaEventDisableTiming);
@@ -654,6 +712,7 @@ void crn_destroy(crn_ctx *c) {
     cudaStreamSynchronize(c->stream);
     if (c->copyStream) cudaStreamSynchronize(c->copyStream);
     if (c->auxStream) cudaStreamSynchronize(c->auxStream);
+    if (c->lightStream) cudaStreamSynchronize(c->lightStream);
     DevBuf *bufs[] = {&c->pos0, &c->bitsA, &c->chainA, &c->pos, &c->scale, &c->keyL, &c->keyC, &c->rankL, &c->rankC, &c->recTmpL, &c->recTmpC, &c->rectTmpL,
                       &c->rectTmpC, &c->lbTmp, &c->recL, &c->recC, &c->rectL, &c->rectC, &c->lbSorted, &c->drawOrder, &c->bits,
                       &c->chain, &c->noise, &c->posmap, &c->image, &c->image2, &c->misc, &c->maskNz, &c->maskDil, &c->mask, &c->sortTmp, &c->sortTmpC, &c->tileOrder};
@@ -680,6 +739,11 @@ void crn_destroy(crn_ctx *c) {
         }
         cudaStreamDestroy(c->copyStream);
     }
+    if (c->lightStream) {
+        cudaEventDestroy(c->evLightDone); cudaEventDestroy(c->evBitsFree); cudaEventDestroy(c->evMainMark);
+        for (auto &ev : c->evCur) if (ev) cudaEventDestroy(ev);
+        cudaStreamDestroy(c->lightStream);
+    }
     if (c->ownStream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -690,6 +754,7 @@ int crn_sync(crn_ctx *c) {
     if (!c) return CRN_ERR_INVALID_ARG;
     CRN_CUDA(c, cudaSetDevice(c->device));
     if (c->voxelized) return settle(c, false, 0);           // also re-runs a voxelize whose bin pool was too small
+    if (c->lightStream) CRN_CUDA(c, cudaStreamSynchronize(c->lightStream));
     CRN_CUDA(c, cudaStreamSynchronize(c->stream));
     if (c->copyStream) CRN_CUDA(c, cudaStreamSynchronize(c->copyStream));
     return CRN_OK;
@@ -726,12 +791,13 @@ int crn_set_billboards(crn_ctx *c, const float *positions3, const float *scales,
     int r;
     if ((r = reserve(c, c->pos, (size_t)std::max(count, 1) * 12))) return r;
     if ((r = reserve(c, c->scale, (size_t)std::max(count, 1) * 4))) return r;
+    cudaStream_t up = upload_stream(c, mem == CRN_MEM_DEVICE);
     if (count) {
         const cudaMemcpyKind kind = mem == CRN_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
-        CRN_CUDA(c, cudaMemcpyAsync(c->pos.p, positions3, (size_t)count * 12, kind, c->stream));
-        CRN_CUDA(c, cudaMemcpyAsync(c->scale.p, scales, (size_t)count * 4, kind, c->stream));
+        CRN_CUDA(c, cudaMemcpyAsync(c->pos.p, positions3, (size_t)count * 12, kind, up));
+        CRN_CUDA(c, cudaMemcpyAsync(c->scale.p, scales, (size_t)count * 4, kind, up));
     }
-    CRN_CUDA(c, cudaEventRecord(c->evBoards, c->stream));
+    CRN_CUDA(c, cudaEventRecord(c->evBoards, up));
     c->nBoards = count;
     c->havePos0 = false;
     return CRN_OK;
@@ -745,10 +811,11 @@ int crn_regenerate_billboards(crn_ctx *c, int32_t count, const float minOffset[3
     if ((r = reserve(c, c->pos0, (size_t)std::max(count, 1) * 12))) return r;
     if ((r = reserve(c, c->pos, (size_t)std::max(count, 1) * 12))) return r;
     if ((r = reserve(c, c->scale, (size_t)std::max(count, 1) * 4))) return r;
-    c->launches += launch_generate_boards(c->stream, count, minOffset, maxOffset, minScale, maxScale, radiusFactor, seed,
+    cudaStream_t up = upload_stream(c, false);
+    c->launches += launch_generate_boards(up, count, minOffset, maxOffset, minScale, maxScale, radiusFactor, seed,
                                           (float *)c->pos0.p, (float *)c->pos.p, (float *)c->scale.p);
     CRN_CUDA(c, cudaGetLastError());
-    CRN_CUDA(c, cudaEventRecord(c->evBoards, c->stream));
+    CRN_CUDA(c, cudaEventRecord(c->evBoards, up));
     c->nBoards = count;
     c->havePos0 = true;
     return CRN_OK;
@@ -761,13 +828,14 @@ int crn_animate_billboards(crn_ctx *c, double angle) {
     if (!c->havePos0) {                                  // first advection of an uploaded set: keep its base offsets
         int r;
         if ((r = reserve(c, c->pos0, (size_t)std::max(n, 1) * 12))) return r;
-        if (n) CRN_CUDA(c, cudaMemcpyAsync(c->pos0.p, c->pos.p, (size_t)n * 12, cudaMemcpyDeviceToDevice, c->stream));
+        if (n) CRN_CUDA(c, cudaMemcpyAsync(c->pos0.p, c->pos.p, (size_t)n * 12, cudaMemcpyDeviceToDevice, c->lightStream));
         c->havePos0 = true;
     }
-    c->launches += launch_rotate_boards(c->stream, n, (const float *)c->pos0.p, (float *)c->pos.p, (float)std::cos(angle),
+    cudaStream_t up = upload_stream(c, false);
+    c->launches += launch_rotate_boards(up, n, (const float *)c->pos0.p, (float *)c->pos.p, (float)std::cos(angle),
                                         (float)std::sin(angle));
     CRN_CUDA(c, cudaGetLastError());
-    CRN_CUDA(c, cudaEventRecord(c->evBoards, c->stream));
+    CRN_CUDA(c, cudaEventRecord(c->evBoards, up));
     return CRN_OK;
 }
 
@@ -775,9 +843,9 @@ int crn_read_billboards(crn_ctx *c, float *positions3_host, float *scales_host) 
     if (!c) return CRN_ERR_INVALID_ARG;
     CRN_CUDA(c, cudaSetDevice(c->device));
     const size_t n = (size_t)c->nBoards;
-    if (n && positions3_host) CRN_CUDA(c, cudaMemcpyAsync(positions3_host, c->pos.p, n * 12, cudaMemcpyDeviceToHost, c->stream));
-    if (n && scales_host) CRN_CUDA(c, cudaMemcpyAsync(scales_host, c->scale.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
-    CRN_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (n && positions3_host) CRN_CUDA(c, cudaMemcpyAsync(positions3_host, c->pos.p, n * 12, cudaMemcpyDeviceToHost, c->lightStream));
+    if (n && scales_host) CRN_CUDA(c, cudaMemcpyAsync(scales_host, c->scale.p, n * 4, cudaMemcpyDeviceToHost, c->lightStream));
+    CRN_CUDA(c, cudaStreamSynchronize(c->lightStream));
     return CRN_OK;
 }
 
@@ -929,6 +997,7 @@ static int copy_image(crn_ctx *c, void *out, cudaMemcpyKind kind, int format, co
 // make sure neither pass ran with a truncated bin pool; re-run what did
 static int settle(crn_ctx *c, bool haveTrace, int format) {
     for (int attempt = 0; attempt < 4; attempt++) {
+        CRN_CUDA(c, cudaStreamSynchronize(c->lightStream));
         CRN_CUDA(c, cudaStreamSynchronize(c->stream));
         CRN_CUDA(c, cudaStreamSynchronize(c->copyStream));         // the cursors travel on the copy stream
         bool grewL = false, grewC = false;
@@ -937,7 +1006,7 @@ static int settle(crn_ctx *c, bool haveTrace, int format) {
         if (haveTrace && (r = grow_if_overflowed(c, c->binsC, c->hCursors + 2, &grewC))) return r;
         if (!grewL && !grewC) return CRN_OK;
         // the truncated attempt left the sticky overflow flag behind; this frame is being redone, so clear it
-        if (grewL) CRN_CUDA(c, cudaMemsetAsync(c->binsL.cursors + 2, 0, sizeof(uint32_t), c->stream));
+        if (grewL) CRN_CUDA(c, cudaMemsetAsync(c->binsL.cursors + 2, 0, sizeof(uint32_t), c->lightStream));
         if (grewC) CRN_CUDA(c, cudaMemsetAsync(c->binsC.cursors + 2, 0, sizeof(uint32_t), c->stream));
         if (grewL && (r = enqueue_voxelize(c))) return r;
         if (haveTrace && (r = enqueue_trace(c, format))) return r;
@@ -1051,6 +1120,7 @@ int crn_volume_bits_ptr(crn_ctx *c, void **dev_ptr, size_t *bytes) {
     const size_t D = c->vol.dimension;
     if ((r = reserve(c, c->bits, D * D * D / 8))) return r;
     *dev_ptr = c->bits.p; *bytes = D * D * D / 8;
+    c->bitsExposed = true;
     return CRN_OK;
 }
 
@@ -1202,7 +1272,7 @@ int crn_get_timings(crn_ctx *c, crn_timings *out) {
         CRN_CUDA(c, cudaEventElapsedTime(&out->prepSortMs, c->evV[0], c->evV[1]));
         CRN_CUDA(c, cudaEventElapsedTime(&out->lightBinMs, c->evV[1], c->evV[2]));
         CRN_CUDA(c, cudaEventElapsedTime(&out->voxelizeMs, c->evV[2], c->evV[3]));
-        CRN_CUDA(c, cudaEventElapsedTime(&out->mipMs, c->evV[3], c->evV[4]));
+        CRN_CUDA(c, cudaEventElapsedTime(&out->mipMs, c->evV[5], c->evV[4]));
     }
     if (c->evTValid) {
         float t = 0;
