@@ -174,7 +174,13 @@ int  crn_sync(crn_ctx *ctx);
 int crn_set_volume(crn_ctx *ctx, const crn_volume_desc *desc);
 /* replaces CloudVolume::uploadBillboards() (src/CloudVolume.cpp:139-164): positions are
  * offsets relative to the volume position, scales are un-fluffed radii; array order is
- * the instance order of the voxelize draw. Data is copied (stream-ordered). */
+ * the instance order of the voxelize draw. Data is copied asynchronously: a CRN_MEM_DEVICE
+ * source is read in the order of the context's stream (after whatever the caller queued
+ * there to produce it); a CRN_MEM_HOST source is read on an internal stream so that the
+ * upload of the next frame does not wait for the trace of the current one - a pinned host
+ * array must stay unchanged until the crn_voxelize that follows has completed (crn_sync,
+ * or a synchronisation of the context's stream after that crn_voxelize); pageable memory
+ * is staged before the call returns. */
 int crn_set_billboards(crn_ctx *ctx, const float *positions3, const float *scales,
                        int32_t count, int32_t mem);
 /* replaces the Sun statics + Sun::update(volume) (src/Sun.hpp:26-43); the derived light
