@@ -658,3 +658,45 @@ def test_paper_variant_occupancy_channel(name, pkg, scenes, orc):
     with pytest.raises(pkg.CrnError):
         r.voxelize()
     r.close()
+
+
+@pytest.mark.parametrize("sampler,fmt", [(1, 0), (0, 0), (1, 2)])
+def test_frame_overlap_is_invisible(sampler, fmt, pkg, scenes):
+    """The light-side set-up of frame k+1 runs on its own stream under the trace of frame k (pinned host uploads,
+    device-side animation): a pipelined burst of C2-sized frames must equal the same frames rendered one by one,
+    for the texture sampler, the explicit sampler (whose trace reads the occupancy bits) and the paper variant."""
+    import torch
+    n = 6
+    base = scenes.make_scene("C2", size=(960, 540))
+    base.tp.sampler = sampler
+    base.vol.format = fmt
+    pos = [scenes.animate(base.board_pos, 25 * k) for k in range(n)]
+    r = pkg.Renderer(0)
+    r.set_scene(base)
+    want = []
+    for k in range(n):
+        r.set_billboards(pos[k], base.board_scale)
+        r.voxelize()
+        want.append(r.cone_trace().copy())
+        r.sync()
+    h_pos = [torch.from_numpy(p).pin_memory() for p in pos]
+    h_scale = torch.from_numpy(base.board_scale).pin_memory()
+    outs = [torch.empty((base.height, base.width, 4), dtype=torch.uint8).pin_memory() for _ in range(n)]
+    for rep in range(2):                                   # twice: the second burst starts with every stream warm
+        for k in range(n):
+            r.set_billboards(h_pos[k].numpy(), h_scale.numpy())
+            r.voxelize()
+            r.cone_trace_async(outs[k].numpy())
+        r.wait_images()
+        for k in range(n):
+            assert np.array_equal(want[k], outs[k].numpy()), f"burst {rep}, frame {k} differs"
+    # the same frames from the device-side rotation field, again pipelined
+    r.set_billboards(base.board_pos, base.board_scale)
+    for k in range(n):
+        r.animate_billboards(0.2 * 25 * k / 60.0)
+        r.voxelize()
+        r.cone_trace_async(outs[k].numpy())
+    r.wait_images()
+    for k in range(n):
+        assert np.array_equal(want[k], outs[k].numpy()), f"animated frame {k} differs"
+    r.close()
