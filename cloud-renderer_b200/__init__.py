@@ -62,7 +62,7 @@ class Timings(C.Structure):
 # every symbol include/cloud_renderer_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "crn_create", "crn_destroy", "crn_last_error", "crn_sync", "crn_set_volume", "crn_set_billboards", "crn_set_sun",
-    "crn_regenerate_billboards", "crn_animate_billboards", "crn_read_billboards", "crn_read_volume_alpha",
+    "crn_regenerate_billboards", "crn_animate_billboards", "crn_read_billboards", "crn_read_volume_alpha", "crn_export_voxels",
     "crn_sun_update", "crn_set_camera", "crn_camera_update", "crn_set_window", "crn_set_trace_params",
     "crn_default_trace_params", "crn_set_noise", "crn_build_noise", "crn_voxelize", "crn_cone_trace", "crn_cone_trace_async",
     "crn_wait_images", "crn_set_row_range",
@@ -120,6 +120,7 @@ def load_library():
     lib.crn_finish_mips.argtypes = [vp, i32]
     lib.crn_read_volume.argtypes = [vp, i32, vp]
     lib.crn_read_volume_alpha.argtypes = [vp, i32, vp]
+    lib.crn_export_voxels.argtypes = [vp, i32, vp, C.c_uint64, C.POINTER(C.c_uint64)]
     lib.crn_count_active_voxels.argtypes = [vp, C.POINTER(u64)]
     lib.crn_keep_position_map.argtypes = [vp, i32]
     lib.crn_read_position_map.argtypes = [vp, vp]
@@ -330,6 +331,15 @@ class Renderer:
 
     def read_chain_alpha(self):
         return np.concatenate([self.read_volume_alpha(l).ravel() for l in range(self.vol.levels)])
+
+    def export_voxels(self, channel=0):
+        """VoxelShader::updateVoxelData: (n,4) float32 rows = world position of each non-empty voxel + its value"""
+        n = u64()
+        self._ck(self.lib.crn_export_voxels(self.h, channel, None, 0, C.byref(n)))
+        out = np.empty((n.value, 4), dtype=np.float32)
+        if n.value:
+            self._ck(self.lib.crn_export_voxels(self.h, channel, out.ctypes.data, n.value, C.byref(n)))
+        return out
 
     def count_active_voxels(self):
         n = u64()

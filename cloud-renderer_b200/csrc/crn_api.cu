@@ -144,6 +144,7 @@ struct crn_ctx {
     size_t chainBytes = 0;
 
     bool havePos0 = false;               // pos0 holds the un-advected offsets of the current billboard set
+    DevBuf exportTmp, exportOut;         // crn_export_voxels scratch
     DevBuf bitsA, chainA;                // CRN_VOLUME_RG8: the occupancy (alpha) channel's level-0 set and R8 chain
     DevBuf pos0, pos, scale, keyL, keyC, rankL, rankC, recTmpL, recTmpC, rectTmpL, rectTmpC, lbTmp, recL, recC, rectL, rectC,
         lbSorted, drawOrder, bits, chain, noise, posmap, image, misc, maskNz, maskDil, mask, sortTmp, tileOrder;
@@ -713,7 +714,7 @@ void crn_destroy(crn_ctx *c) {
     if (c->copyStream) cudaStreamSynchronize(c->copyStream);
     if (c->auxStream) cudaStreamSynchronize(c->auxStream);
     if (c->lightStream) cudaStreamSynchronize(c->lightStream);
-    DevBuf *bufs[] = {&c->pos0, &c->bitsA, &c->chainA, &c->pos, &c->scale, &c->keyL, &c->keyC, &c->rankL, &c->rankC, &c->recTmpL, &c->recTmpC, &c->rectTmpL,
+    DevBuf *bufs[] = {&c->exportTmp, &c->exportOut, &c->pos0, &c->bitsA, &c->chainA, &c->pos, &c->scale, &c->keyL, &c->keyC, &c->rankL, &c->rankC, &c->recTmpL, &c->recTmpC, &c->rectTmpL,
                       &c->rectTmpC, &c->lbTmp, &c->recL, &c->recC, &c->rectL, &c->rectC, &c->lbSorted, &c->drawOrder, &c->bits,
                       &c->chain, &c->noise, &c->posmap, &c->image, &c->image2, &c->misc, &c->maskNz, &c->maskDil, &c->mask, &c->sortTmp, &c->sortTmpC, &c->tileOrder};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
@@ -1176,6 +1177,35 @@ int crn_count_active_voxels(crn_ctx *c, uint64_t *count) {
     CRN_CUDA(c, cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, c->stream));
     CRN_CUDA(c, cudaStreamSynchronize(c->stream));
     *count = h;
+    return CRN_OK;
+}
+
+int crn_export_voxels(crn_ctx *c, int32_t channel, float *dst_host_xyzw, uint64_t capacity, uint64_t *count) {
+    if (!c || !count || (capacity && !dst_host_xyzw)) return CRN_ERR_INVALID_ARG;
+    if (!c->voxelized) return fail(c, CRN_ERR_STATE, "no volume has been produced yet");
+    if (channel != 0 && channel != 1) return fail(c, CRN_ERR_INVALID_ARG, "channel must be 0 (lit) or 1 (occupancy)");
+    if (channel == 1 && c->vol.format != CRN_VOLUME_RG8) return fail(c, CRN_ERR_STATE, "the volume has no occupancy channel (format is not CRN_VOLUME_RG8)");
+    CRN_CUDA(c, cudaSetDevice(c->device));
+    int r = settle(c, false, 0); if (r) return r;
+    const size_t D = c->vol.dimension, words = D * D * D / 32;
+    if ((r = reserve(c, c->exportTmp, export_scratch_words(words) * 4 + 64))) return r;
+    if (capacity && (r = reserve(c, c->exportOut, (size_t)capacity * 16))) return r;
+    unsigned long long *dTotal = (unsigned long long *)((char *)c->exportTmp.p + (export_scratch_words(words) * 4 + 15) / 16 * 16);
+    const float lo[3] = {c->vol.xBounds[0], c->vol.yBounds[0], c->vol.zBounds[0]};
+    const float range[3] = {c->vol.xBounds[1] - c->vol.xBounds[0], c->vol.yBounds[1] - c->vol.yBounds[0], c->vol.zBounds[1] - c->vol.zBounds[0]};
+    const uint32_t *which = (const uint32_t *)(channel == 1 ? c->bitsA.p : c->bits.p);
+    c->launches += launch_export_voxels(c->stream, which, (const uint32_t *)c->bits.p, words, (int)D, c->vol.position, lo, range,
+                                        (uint32_t *)c->exportTmp.p, dTotal, capacity ? (float4 *)c->exportOut.p : nullptr, capacity);
+    CRN_CUDA(c, cudaGetLastError());
+    unsigned long long h = 0;
+    CRN_CUDA(c, cudaMemcpyAsync(&h, dTotal, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CRN_CUDA(c, cudaStreamSynchronize(c->stream));
+    *count = h;
+    const uint64_t n = std::min<uint64_t>(h, capacity);
+    if (n) {
+        CRN_CUDA(c, cudaMemcpyAsync(dst_host_xyzw, c->exportOut.p, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
+        CRN_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
     return CRN_OK;
 }
 

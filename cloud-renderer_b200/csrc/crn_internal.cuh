@@ -139,6 +139,10 @@ int launch_skipmask(cudaStream_t st, const VolumeParams &vol, const uint32_t *bi
                     uint32_t *dil, uint32_t *mask);
 int launch_generate_boards(cudaStream_t st, int n, const float minOff[3], const float maxOff[3], float minScale,
                            float maxScale, double radiusFactor, uint64_t seed, float *pos0, float *pos, float *scale);
+size_t export_scratch_words(size_t words);
+int launch_export_voxels(cudaStream_t st, const uint32_t *bits, const uint32_t *lit, size_t words, int D, const float pos[3],
+                         const float lo[3], const float range[3], uint32_t *blockScratch, unsigned long long *total, float4 *out,
+                         unsigned long long capacity);
 int launch_rotate_boards(cudaStream_t st, int n, const float *pos0, float *pos, float c, float s);
 int launch_count_bits(cudaStream_t st, const uint32_t *bits, size_t words, unsigned long long *out);
 

@@ -271,6 +271,14 @@ int crn_read_volume(crn_ctx *ctx, int32_t level, void *dst_host);          /* si
  * crn_read_volume (what the reference's debug voxel view draws as black cubes) */
 int crn_read_volume_alpha(crn_ctx *ctx, int32_t level, void *dst_host);
 int crn_count_active_voxels(crn_ctx *ctx, uint64_t *count);                  /* "Voxels in scene" */
+/* VoxelShader::updateVoxelData (src/Shaders/VoxelShader.cpp:102-133): the cubes of the debug
+ * voxel view.  For every non-empty level-0 texel, in ascending linear index (x fastest), one
+ * float4 = (position + reverseVoxelIndex(x,y,z) [src/CloudVolume.cpp:112-118], value).
+ * channel 0: lit voxels (value 1).  channel 1 (CRN_VOLUME_RG8): occupied voxels, value 1 where
+ * lit else 0 (the paper's black interior cubes).  *count receives the total; at most
+ * `capacity` entries are written (call with capacity 0 to size the buffer). */
+int crn_export_voxels(crn_ctx *ctx, int32_t channel, float *dst_host_xyzw, uint64_t capacity,
+                      uint64_t *count);
 int crn_keep_position_map(crn_ctx *ctx, int32_t enable);                    /* default off   */
 int crn_read_position_map(crn_ctx *ctx, float *dst_host_rgba32f);           /* W*H*4 floats  */
 /* draw order of the last crn_cone_trace: indices into the billboard arrays, far -> near

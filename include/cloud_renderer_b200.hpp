@@ -141,6 +141,15 @@ public:
         return v;
     }
     uint64_t activeVoxels() const { uint64_t n = 0; check(ctx, crn_count_active_voxels(ctx, &n)); return n; }
+    // voxelPositions / voxelData of the debug voxel view, compacted on the device: (x, y, z, value) per non-empty voxel
+    struct Voxel { float x, y, z, value; };
+    std::vector<Voxel> exportVoxels(int channel = 0) const {
+        uint64_t n = 0;
+        check(ctx, crn_export_voxels(ctx, channel, nullptr, 0, &n));
+        std::vector<Voxel> v(n);
+        if (n) check(ctx, crn_export_voxels(ctx, channel, &v[0].x, n, &n));
+        return v;
+    }
 
     vec3 position;
     vec2 xBounds, yBounds, zBounds;

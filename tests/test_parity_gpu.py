@@ -700,3 +700,40 @@ def test_frame_overlap_is_invisible(sampler, fmt, pkg, scenes):
     for k in range(n):
         assert np.array_equal(want[k], outs[k].numpy()), f"animated frame {k} differs"
     r.close()
+
+
+def test_voxel_export(pkg, scenes, orc):
+    """crn_export_voxels = VoxelShader::updateVoxelData (src/Shaders/VoxelShader.cpp:102-133): every non-empty level-0
+    texel in ascending linear index with position + reverseVoxelIndex (src/CloudVolume.cpp:112-118), bit-exact"""
+    f32 = np.float32
+
+    def expected(mask, lit, vol):
+        z, y, x = np.nonzero(mask)                                  # C order of a (z,y,x) array = ascending linear index
+        D = f32(vol.dimension)
+        cols = []
+        for idx, b, p in ((x, vol.xBounds, vol.position[0]), (y, vol.yBounds, vol.position[1]), (z, vol.zBounds, vol.position[2])):
+            rng = f32(b[1]) - f32(b[0])
+            cols.append(f32(p) + ((idx.astype(f32) * rng) / D + f32(b[0])))
+        cols.append(lit[z, y, x].astype(f32))
+        return np.stack(cols, axis=1).astype(f32)
+
+    r = pkg.Renderer(0)
+    for name in ("tiny", "C1", "C2"):
+        s = scenes.make_scene(name)
+        s.vol.position[:] = (25.0, -1.5, 0.25)
+        s.vol.yBounds[:] = (-4.0, 6.0)
+        r.set_scene(s); r.voxelize()
+        l0 = r.read_volume(0)
+        got = r.export_voxels(0)
+        want = expected(l0 > 0, l0 > 0, s.vol)
+        assert got.shape == want.shape and got.shape[0] == r.count_active_voxels()
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), name
+    s = scenes.make_scene("small")
+    s.vol.format = pkg.VOLUME_RG8
+    r.set_scene(s); r.voxelize()
+    l0, a0 = r.read_volume(0), r.read_volume_alpha(0)
+    got = r.export_voxels(1)
+    want = expected(a0 > 0, l0 > 0, s.vol)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert 0 < got[:, 3].sum() == (l0 > 0).sum() < got.shape[0]
+    r.close()
