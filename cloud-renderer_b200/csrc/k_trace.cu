@@ -17,11 +17,17 @@
 // cloud — hundreds of layers of overdraw at 20k billboards — is never shaded.  With
 // cutoff = 0 every fragment is shaded, as in the reference.
 //
-// Sampling is explicit (no texture units): the volume's level 0 is read from the 1-bit
-// occupancy set (2 MB at 256^3), coarser levels from the R8 chain, the 32^3 noise texture from
-// a pre-decoded (g,a) float2 copy; trilinear / mip-linear weights follow GL 4.4 §8.14 in full
-// float precision.  traceCone's per-step height, LOD split and weight are identical for every
-// fragment and are precomputed on the host (TraceParams::steps).
+// Two samplers, chosen per frame (crn_trace_params.sampler):
+//   CRN_SAMPLER_TEXTURE  the texture units: one mipmapped R8/R32F texture sampled with tex3DLod at the
+//                        two integer LODs of a step (LINEAR in-level, the mip blend in the kernel) and
+//                        the RGBA8_SNORM noise texture; the kernel is bound by the texture pipe.
+//   CRN_SAMPLER_EXPLICIT no texture units: level 0 is read from the 1-bit occupancy set (2 MB at
+//                        256^3), coarser levels from the linear chain, the noise from a pre-decoded
+//                        (g,a) float2 copy; trilinear / mip-linear weights follow GL 4.4 §8.14 in full
+//                        float precision (134 dB against the oracle, 3x slower: issue-bound).
+// traceCone's per-step height, LOD split and weight are identical for every fragment and are
+// precomputed on the host (TraceParams::steps); consecutive steps are grouped and a group whose
+// conservative empty-space mask (k_skipmask.cu) is clear is skipped exactly.
 #include "crn_internal.cuh"
 
 namespace crn {
