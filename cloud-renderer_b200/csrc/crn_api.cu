@@ -333,12 +333,12 @@ int create_chain_textures(crn_ctx *c, cudaMipmappedArray_t &arr, TexSet &ts) {
         td.filterMode = cudaFilterModeLinear; td.readMode = readMode; td.normalizedCoords = 1;
         CRN_CUDA(c, cudaCreateTextureObject(&ts.tex[l], &rd, &td, nullptr));
     }
-    {   // one object over the whole chain for tex3DLod: LINEAR inside a level, POINT between levels
+    {   // one object over the whole chain for tex3DLod: LINEAR inside a level and between levels (LINEAR_MIPMAP_LINEAR)
         cudaResourceDesc rd{};
         rd.resType = cudaResourceTypeMipmappedArray; rd.res.mipmap.mipmap = arr;
         cudaTextureDesc td{};
         td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
-        td.filterMode = cudaFilterModeLinear; td.mipmapFilterMode = cudaFilterModePoint;
+        td.filterMode = cudaFilterModeLinear; td.mipmapFilterMode = cudaFilterModeLinear;
         td.readMode = readMode; td.normalizedCoords = 1;
         td.minMipmapLevelClamp = 0.0f; td.maxMipmapLevelClamp = (float)(L - 1);
         CRN_CUDA(c, cudaCreateTextureObject(&ts.vol, &rd, &td, nullptr));
@@ -526,7 +526,7 @@ void build_trace_params(crn_ctx *c, const ViewParams &cam, TraceParams *tp) {
         if (!(lod > 0.0f)) { s.level0 = 0; s.frac = 0.0f; }
         else if (lod >= (float)(L - 1)) { s.level0 = L - 1; s.frac = 0.0f; }
         else { const float fl = floorf(lod); s.level0 = (int)fl; s.frac = lod - fl; }
-        s.lod0 = (float)s.level0; s.lod1 = (float)(s.level0 + 1);
+        s.lod0 = (float)s.level0; s.lod1 = (float)(s.level0 + 1); s.lod = s.lod0 + s.frac;
         coneHeight += coneRadius;
     }
     // groups for the empty-space test: consecutive steps with the same lower level whose sample points

@@ -56,7 +56,8 @@ struct ConeStep {                     // traceCone's per-step constants (identic
     float weight;                     // float(i) / (steps * vctDownScaling)
     int32_t level0;                   // lower mip level sampled
     float frac;                       // blend toward level0+1 (0: single level)
-    float lod0, lod1;                 // level0 and level0+1 as floats (tex3DLod operands; saves a conversion per fetch)
+    float lod0, lod1;                 // level0 and level0+1 as floats
+    float lod;                        // level0 + frac: the tex3DLod operand (mip-linear blend in the texture unit)
 };
 
 struct ConeGroup {                    // consecutive cone steps decided by ONE empty-space lookup (k_skipmask.cu)
@@ -120,7 +121,7 @@ int launch_voxelize(cudaStream_t st, const ViewParams &light, const VolumeParams
 struct TexSet {
     cudaSurfaceObject_t surf[kMaxLevels];   // one per level, written by the mip kernel
     cudaTextureObject_t tex[kMaxLevels];    // one per level: LINEAR, CLAMP, normalized coords, UNORM8 -> float
-    cudaTextureObject_t vol;                // the whole mipmapped array: LINEAR in-level, POINT between levels (tex3DLod)
+    cudaTextureObject_t vol;                // the whole mipmapped array: LINEAR in-level and between levels (tex3DLod)
     cudaTextureObject_t volA;               // CRN_VOLUME_RG8: the occupancy channel's chain, same sampling state
     cudaTextureObject_t noise;              // RGBA8_SNORM, LINEAR, REPEAT
     int32_t enabled;

@@ -19,8 +19,9 @@
 //
 // Two samplers, chosen per frame (crn_trace_params.sampler):
 //   CRN_SAMPLER_TEXTURE  the texture units: one mipmapped R8/R32F texture sampled with tex3DLod at the
-//                        two integer LODs of a step (LINEAR in-level, the mip blend in the kernel) and
-//                        the RGBA8_SNORM noise texture; the kernel is bound by the texture pipe.
+//                        step's fractional LOD (LINEAR_MIPMAP_LINEAR, as the reference's sampler state,
+//                        src/CloudVolume.cpp:19-23) and the RGBA8_SNORM noise texture; the kernel is
+//                        bound by the texture pipe.
 //   CRN_SAMPLER_EXPLICIT no texture units: level 0 is read from the 1-bit occupancy set (2 MB at
 //                        256^3), coarser levels from the linear chain, the noise from a pre-decoded
 //                        (g,a) float2 copy; trilinear / mip-linear weights follow GL 4.4 §8.14 in full
@@ -346,8 +347,7 @@ __global__ void __launch_bounds__(kTraceThreads, 2048 / kTraceThreads / 2) trace
                             const float sx = fmaf(st.height, ex, nx), sy = fmaf(st.height, ey, ny), sz = fmaf(st.height, ez, nz);
                             float s;
                             if constexpr (kTex) {
-                                s = tex3DLod<float>(ts.vol, sx, sy, sz, st.lod0);
-                                if (st.frac != 0.0f) s = lerpf(s, tex3DLod<float>(ts.vol, sx, sy, sz, st.lod1), st.frac);
+                                s = tex3DLod<float>(ts.vol, sx, sy, sz, st.lod);        // quadrilinear in one fetch
                             } else {
                                 const float fd = (float)D;
                                 s = sample_level(a, a.bits, a.chain, st.level0, sx * fd, sy * fd, sz * fd);
@@ -356,8 +356,7 @@ __global__ void __launch_bounds__(kTraceThreads, 2048 / kTraceThreads / 2) trace
                             if constexpr (kGate) {                      // paper/tex/conetracing.tex:36-39
                                 float al;
                                 if constexpr (kTex) {
-                                    al = tex3DLod<float>(ts.volA, sx, sy, sz, st.lod0);
-                                    if (st.frac != 0.0f) al = lerpf(al, tex3DLod<float>(ts.volA, sx, sy, sz, st.lod1), st.frac);
+                                    al = tex3DLod<float>(ts.volA, sx, sy, sz, st.lod);
                                 } else {
                                     const float fd = (float)D;
                                     al = sample_level(a, a.bitsA, a.chainA, st.level0, sx * fd, sy * fd, sz * fd);
