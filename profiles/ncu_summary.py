@@ -13,7 +13,7 @@ KEYS = [
     "sm__inst_executed_pipe_tex.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
     "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__t_sector_hit_rate.pct", "l1tex__texin_sm2tex_req_cycles_active.avg.pct_of_peak_sustained_elapsed",
     "l1tex__f_tex2sm_cycles_active.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed",
-    "l1tex__data_pipe_tex_wavefronts.sum.pct_of_peak_sustained_elapsed", "l1tex__t_requests_pipe_tex.sum", "l1tex__t_sectors_pipe_tex.sum",
+    "l1tex__data_pipe_tex_wavefronts.sum.pct_of_peak_sustained_elapsed", "l1tex__f_wavefronts.sum.pct_of_peak_sustained_elapsed", "l1tex__t_requests_pipe_tex.sum", "l1tex__t_sectors_pipe_tex.sum",
     "sm__inst_executed_pipe_tex.sum", "smsp__inst_executed_op_texture.sum",
     "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum", "dram__bytes_write.sum",
     "dram__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes.sum", "lts__t_bytes.sum",
