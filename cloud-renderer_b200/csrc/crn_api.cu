@@ -509,6 +509,7 @@ void build_trace_params(crn_ctx *c, const ViewParams &cam, TraceParams *tp) {
     host_quad(cam, c->sun.position, c->sun.outerRadius, &tp->sunRec, &tp->sunRect);
     tp->nSteps = c->tp.vctSteps;
     tp->noiseDim = c->noiseDim;
+    tp->noiseMask = (c->noiseDim & (c->noiseDim - 1)) == 0 ? c->noiseDim - 1 : -1;
     tp->row0 = std::max(0, c->row0); tp->row1 = std::min(c->H, c->row1);
     tp->ilvIndex = c->ilvIndex; tp->ilvCount = c->ilvCount;
     tp->active = (c->tp.doConeTrace || c->tp.doNoiseSample || c->tp.showQuad) ? 1 : 0;   // ConeTraceShader.cpp:16-18
@@ -554,6 +555,8 @@ void build_trace_params(crn_ctx *c, const ViewParams &cam, TraceParams *tp) {
     for (int o = 0; o < kMaxOctaves; o++) {
         tp->octFreq[o] = freq; tp->octPers[o] = pers;
         tp->octBias[o] = (o < 3 ? tp->octaveOffsets[o] : 0.0f) * freq;
+        tp->octFreqZ[o] = tp->octFreq[o] * (float)c->noiseDim;
+        tp->octBiasZ[o] = tp->octBias[o] * (float)c->noiseDim - 0.5f;
         freq *= c->tp.freqStep; pers *= c->tp.persStep;
     }
 }
@@ -937,13 +940,25 @@ int crn_set_noise(crn_ctx *c, const int8_t *rgba, int32_t dim) {
     int r = reserve(c, c->noise, n * 8); if (r) return r;
     CRN_CUDA(c, cudaMemcpyAsync(c->noise.p, ga.data(), n * 8, cudaMemcpyHostToDevice, c->stream));
     CRN_CUDA(c, cudaStreamSynchronize(c->stream));
-    // texture-unit copy: GL_RGBA8_SNORM, REPEAT x3, LINEAR, no mips (src/Shaders/ConeTraceShader.cpp:152-158)
+    // texture-unit copy of the GL_RGBA8_SNORM, REPEAT x3, LINEAR, no-mips texture (src/Shaders/ConeTraceShader.cpp:152-158).
+    // A 3D LINEAR fetch costs the texture unit two bilinear passes; only .g and .a are ever read, so the texture is
+    // stored as a LAYERED 2D array whose layer z holds (g_z, a_z, g_z+1, a_z+1) (z+1 wrapped): one bilinear pass
+    // returns both slices, the kernel blends them with the z weight in full float precision.  Same texel bytes, same
+    // SNORM8 decode, REPEAT in x and y by the sampler, in z by the layer index.
     if (c->ts.noise) { cudaDestroyTextureObject(c->ts.noise); c->ts.noise = 0; }
     if (c->noiseArray) { cudaFreeArray(c->noiseArray); c->noiseArray = nullptr; }
+    std::vector<int8_t> pairs(n * 4);
+    for (int z = 0; z < dim; z++) {
+        const size_t z0 = (size_t)z * dim * dim, z1 = (size_t)((z + 1) % dim) * dim * dim;
+        for (size_t i = 0; i < (size_t)dim * dim; i++) {
+            pairs[4 * (z0 + i) + 0] = rgba[4 * (z0 + i) + 1]; pairs[4 * (z0 + i) + 1] = rgba[4 * (z0 + i) + 3];
+            pairs[4 * (z0 + i) + 2] = rgba[4 * (z1 + i) + 1]; pairs[4 * (z0 + i) + 3] = rgba[4 * (z1 + i) + 3];
+        }
+    }
     cudaChannelFormatDesc cd = cudaCreateChannelDesc(8, 8, 8, 8, cudaChannelFormatKindSigned);
-    CRN_CUDA(c, cudaMalloc3DArray(&c->noiseArray, &cd, make_cudaExtent(dim, dim, dim)));
+    CRN_CUDA(c, cudaMalloc3DArray(&c->noiseArray, &cd, make_cudaExtent(dim, dim, dim), cudaArrayLayered));
     cudaMemcpy3DParms cp{};
-    cp.srcPtr = make_cudaPitchedPtr((void *)rgba, (size_t)dim * 4, dim, dim);
+    cp.srcPtr = make_cudaPitchedPtr((void *)pairs.data(), (size_t)dim * 4, dim, dim);
     cp.dstArray = c->noiseArray; cp.extent = make_cudaExtent(dim, dim, dim); cp.kind = cudaMemcpyHostToDevice;
     CRN_CUDA(c, cudaMemcpy3D(&cp));
     cudaResourceDesc rd{};

@@ -88,6 +88,9 @@ struct TraceParams {
     float octFreq[kMaxOctaves];       // freq of octave o (freqStep^o)
     float octBias[kMaxOctaves];       // octaveOffsets[o] * freq: uv*freq + bias == (uv + offset)*freq
     float octPers[kMaxOctaves];       // persStep^o
+    float octFreqZ[kMaxOctaves];      // freq * noiseDim and bias * noiseDim - 0.5: the z texel coordinate of the layered
+    float octBiasZ[kMaxOctaves];      //   noise texture (z filtered in the kernel, see TexSet::noise)
+    int32_t noiseMask;                // noiseDim - 1 if noiseDim is a power of two, else -1
     ConeStep steps[kMaxConeSteps];
     ConeGroup groups[kMaxConeSteps];
 };
@@ -123,7 +126,7 @@ struct TexSet {
     cudaTextureObject_t tex[kMaxLevels];    // one per level: LINEAR, CLAMP, normalized coords, UNORM8 -> float
     cudaTextureObject_t vol;                // the whole mipmapped array: LINEAR in-level and between levels (tex3DLod)
     cudaTextureObject_t volA;               // CRN_VOLUME_RG8: the occupancy channel's chain, same sampling state
-    cudaTextureObject_t noise;              // RGBA8_SNORM, LINEAR, REPEAT
+    cudaTextureObject_t noise;              // layered 2D RGBA8_SNORM, LINEAR, REPEAT: layer z holds (g_z, a_z, g_z+1, a_z+1)
     int32_t enabled;
 };
 

@@ -32,6 +32,21 @@ __global__ void __launch_bounds__(256) tex_noise_kernel(cudaTextureObject_t tex,
     if (acc.x + acc.y + acc.z + acc.w == 12345.678f) out[0] = acc.x;
 }
 
+// bilinear fetch from a layered 2D RGBA8_SNORM texture (the noise texture's layout in the trace kernel)
+__global__ void __launch_bounds__(256) tex_layered_kernel(cudaTextureObject_t tex, float *out, float step) {
+    const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    float u = (lane & 7) * 0.006f + warp * 0.013f, v = (lane >> 3) * 0.006f + warp * 0.007f;
+    int layer = warp & 31;
+    float4 acc = make_float4(0, 0, 0, 0);
+#pragma unroll 8
+    for (int i = 0; i < kIters; i++) {
+        const float4 t = tex2DLayered<float4>(tex, u, v, layer);
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        u += step; v += step * 0.7f; layer = (layer + (i & 1)) & 31;
+    }
+    if (acc.x + acc.y + acc.z + acc.w == 12345.678f) out[0] = acc.x;
+}
+
 __global__ void __launch_bounds__(256) tex_vol_kernel(cudaTextureObject_t tex, float *out, float step) {
     const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     float u = 0.1f + (lane & 7) * 0.0008f + (warp % 97) * 0.008f, v = 0.1f + (lane >> 3) * 0.0012f + (warp % 89) * 0.009f,
@@ -151,6 +166,21 @@ extern "C" int crn_microbench(int device, int which, double *gops) {
         cudaTextureObject_t tex = make_tex(arr, which == 0);
         if (which == 0) ms = time_ms([&] { tex_noise_kernel<<<blocks, threads>>>(tex, dOut, 0.004f); }, 5);
         else ms = time_ms([&] { tex_vol_kernel<<<blocks, threads>>>(tex, dOut, 0.0009f); }, 5);
+        cudaDestroyTextureObject(tex);
+        cudaFreeArray(arr);
+    } else if (which == 6) {
+        const int n = 32;
+        cudaChannelFormatDesc cd = cudaCreateChannelDesc(8, 8, 8, 8, cudaChannelFormatKindSigned);
+        cudaArray_t arr = nullptr;
+        cudaMalloc3DArray(&arr, &cd, make_cudaExtent(n, n, n), cudaArrayLayered);
+        std::vector<uint8_t> h((size_t)n * n * n * 4);
+        for (size_t i = 0; i < h.size(); i++) h[i] = (uint8_t)(i * 2654435761u >> 24);
+        cudaMemcpy3DParms cp{};
+        cp.srcPtr = make_cudaPitchedPtr(h.data(), n * 4, n, n);
+        cp.dstArray = arr; cp.extent = make_cudaExtent(n, n, n); cp.kind = cudaMemcpyHostToDevice;
+        cudaMemcpy3D(&cp);
+        cudaTextureObject_t tex = make_tex(arr, true);
+        ms = time_ms([&] { tex_layered_kernel<<<blocks, threads>>>(tex, dOut, 0.004f); }, 5);
         cudaDestroyTextureObject(tex);
         cudaFreeArray(arr);
     } else if (which == 2) {

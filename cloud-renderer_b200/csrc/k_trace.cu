@@ -296,8 +296,14 @@ __global__ void __launch_bounds__(kTraceThreads, 2048 / kTraceThreads / 2) trace
                             const float f = tp.octFreq[o], b = tp.octBias[o];
                             float2 s;
                             if constexpr (kTex) {
-                                const float4 t = tex3D<float4>(ts.noise, fmaf(tx, f, b), fmaf(tyy, f, b), fmaf(tz, f, b));
-                                s = make_float2(t.y, t.w);
+                                // one bilinear pass on layer floor(z) returns (g,a) of slices z and z+1; blend them here
+                                const float wz = fmaf(tz, tp.octFreqZ[o], tp.octBiasZ[o]);
+                                const float fl = floorf(wz), az = wz - fl;
+                                int layer = (int)fl;
+                                if (tp.noiseMask >= 0) layer &= tp.noiseMask;
+                                else { layer %= nzDim; if (layer < 0) layer += nzDim; }
+                                const float4 t = tex2DLayered<float4>(ts.noise, fmaf(tx, f, b), fmaf(tyy, f, b), layer);
+                                s = make_float2(fmaf(az, t.z - t.x, t.x), fmaf(az, t.w - t.y, t.y));
                             } else {
                                 s = sample_noise(a.noise, nzDim, fmaf(tx, f, b), fmaf(tyy, f, b), fmaf(tz, f, b));
                             }
