@@ -195,7 +195,9 @@ __device__ __forceinline__ bool sun_fragment(const TraceParams &tp, const ViewPa
 constexpr int kTraceThreads = 64;     // 2 warp patches per CTA: measured best (256: 5.87 ms, 128: 5.83, 64: 5.79 at C3)
 
 // kGate: the paper variant's `if (sampleColor.a > 0)` on a second (occupancy) chain, CRN_VOLUME_RG8 only
-template <bool kTex, bool kStats, bool kGate>
+// kOct4: the reference's noise configuration (numOctaves == 4, 32^3 texture) with the octave loop unrolled, so the
+//        per-octave constants become immediate operands instead of indexed constant loads
+template <bool kTex, bool kStats, bool kGate, bool kOct4>
 __global__ void __launch_bounds__(kTraceThreads, 2048 / kTraceThreads / 2) trace_kernel(const __grid_constant__ TraceArgs a, const __grid_constant__ ViewParams cam,
                                                     const __grid_constant__ TraceParams tp, const __grid_constant__ TexSet ts) {
     // a 16x16 tile is 8 warp patches; a CTA carries kTraceThreads/32 of them, so a slow patch holds up fewer warps
@@ -292,6 +294,24 @@ __global__ void __launch_bounds__(kTraceThreads, 2048 / kTraceThreads / 2) trace
                 for (int i = 0; i < nMax; i++) {
                     if (i < nIter) {
                         float ng = 0.0f, na = 0.0f;
+                        if constexpr (kTex && kOct4) {
+#pragma unroll
+                            for (int o = 0; o < 4; o++) {
+                                // layer = floor(z texel coordinate) as round-to-nearest of (z - 0.5) through the 1.5*2^23
+                                // trick (FADD pipe only); at an exact integer either neighbour gives the same blend
+                                const float zc = fmaf(tz, tp.octFreqZ[o], tp.octBiasZh[o]);
+                                const float m = __fadd_rn(zc, 12582912.0f);
+                                const float az = __fadd_rn(__fadd_rn(zc, -__fadd_rn(m, -12582912.0f)), 0.5f);
+                                const int layer = __float_as_int(m) & 31;
+                                float4 t;                              // tex2DLayered without the header's 16-bit layer clamp
+                                asm("tex.a2d.v4.f32.f32 {%0, %1, %2, %3}, [%4, {%5, %6, %7, %7}];"
+                                    : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                                    : "l"(ts.noise), "r"(layer), "f"(fmaf(tx, tp.octFreq[o], tp.octBias[o])),
+                                      "f"(fmaf(tyy, tp.octFreq[o], tp.octBias[o])));
+                                ng = fmaf(tp.octPers[o], fmaf(az, t.z - t.x, t.x), ng);
+                                na = fmaf(tp.octPers[o], fmaf(az, t.w - t.y, t.y), na);
+                            }
+                        } else
                         for (int o = 0; o < tp.p.numOctaves; o++) {     // noise3D, :103-120: texture(noiseMap, (uv + offset_o) * freq_o) * pers_o
                             const float f = tp.octFreq[o], b = tp.octBias[o];
                             float2 s;
@@ -453,16 +473,18 @@ int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol
     const bool useTex = ts && ts->enabled && tp.p.sampler == CRN_SAMPLER_TEXTURE;
     const int grid = b.tilesX * b.tilesY * (256 / kTraceThreads);
     const bool gate = bitsA != nullptr;
+    const bool oct4 = tp.p.numOctaves == 4 && tp.noiseDim == 32;     // the reference's configuration: unrolled octave loop
     if (gate) {                                                   // opt-in paper variant: stats variant only when asked
-        if (useTex && tp.stats) trace_kernel<true, true, true><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, *ts);
-        else if (useTex) trace_kernel<true, false, true><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, *ts);
-        else if (tp.stats) trace_kernel<false, true, true><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, none);
-        else trace_kernel<false, false, true><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, none);
+        if (useTex && tp.stats) trace_kernel<true, true, true, false><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, *ts);
+        else if (useTex) trace_kernel<true, false, true, false><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, *ts);
+        else if (tp.stats) trace_kernel<false, true, true, false><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, none);
+        else trace_kernel<false, false, true, false><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, none);
     }
-    else if (useTex && tp.stats) trace_kernel<true, true, false><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, *ts);
-    else if (useTex) trace_kernel<true, false, false><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, *ts);
-    else if (tp.stats) trace_kernel<false, true, false><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, none);
-    else trace_kernel<false, false, false><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, none);
+    else if (useTex && tp.stats) trace_kernel<true, true, false, false><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, *ts);
+    else if (useTex && oct4) trace_kernel<true, false, false, true><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, *ts);
+    else if (useTex) trace_kernel<true, false, false, false><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, *ts);
+    else if (tp.stats) trace_kernel<false, true, false, false><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, none);
+    else trace_kernel<false, false, false, false><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, none);
     return 1;
 }
 
