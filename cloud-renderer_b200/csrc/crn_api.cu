@@ -407,7 +407,8 @@ int build_masks(crn_ctx *c) {
     if ((r = reserve(c, c->maskDil, words * 4))) return r;
     if ((r = reserve(c, c->mask, words * 4))) return r;
     c->launches += launch_skipmask(c->stream, c->vparams, (const uint32_t *)c->bits.p, (const uint8_t *)c->chain.p,
-                                   (uint32_t *)c->maskNz.p, (uint32_t *)c->maskDil.p, (uint32_t *)c->mask.p);
+                                   (uint32_t *)c->maskNz.p, (uint32_t *)c->maskDil.p, (uint32_t *)c->mask.p,
+                                   (uint32_t *)((char *)c->misc.p + 192));
     c->maskCurrent = true;
     return CRN_OK;
 }
@@ -548,6 +549,7 @@ void build_trace_params(crn_ctx *c, const ViewParams &cam, TraceParams *tp) {
         g.wpr = g.size >= 32 ? g.size / 32 : 1;
         g.maskOff = maskOff[l];
         g.first = i; g.count = j - i + 1;
+        g.level = l; g.total = (uint32_t)g.size * g.size * g.size;
         i = j + 1;
     }
     // noise3D's per-octave constants (res/conetrace_frag.glsl:107-114)
@@ -630,7 +632,8 @@ int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
     c->launches += launch_trace(st, cam, c->vparams, tp, (const BoardRec *)c->recC.p, c->binsC, (const uint32_t *)c->bits.p,
                                 (const uint8_t *)c->chain.p, c->vol.format == CRN_VOLUME_RG8 ? (const uint32_t *)c->bitsA.p : nullptr,
                                 (const uint8_t *)c->chainA.p, (const int8_t *)c->noise.p, useTex ? &c->ts : nullptr,
-                                c->tp.skipEmptySpace ? (const uint32_t *)c->mask.p : nullptr, (const uint32_t *)c->tileOrder.p,
+                                c->tp.skipEmptySpace ? (const uint32_t *)c->mask.p : nullptr,
+                                (const uint32_t *)((char *)c->misc.p + 192), (const uint32_t *)c->tileOrder.p,
                                 img.p, format, dStats);
     cudaEventRecord(c->evTraceEnd, st);
     c->traceEndValid = true;

@@ -68,6 +68,8 @@ struct ConeGroup {                    // consecutive cone steps decided by ONE e
     int32_t wpr;                      // mask words per row
     uint32_t maskOff;                 // word offset of M_level
     int32_t first, count;             // steps [first, first+count)
+    int32_t level;                    // mip level of the mask
+    uint32_t total;                   // texels of that level
 };
 
 struct TraceParams {
@@ -137,11 +139,11 @@ int launch_chain_to_surfaces(cudaStream_t st, const VolumeParams &vol, const uin
 int launch_finish_mips(cudaStream_t st, const VolumeParams &vol, uint8_t *chain, int firstLevel);
 int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol, const TraceParams &tp,
                  const BoardRec *recs, const Bins &b, const uint32_t *bits, const uint8_t *chain,
-                 const uint32_t *bitsA, const uint8_t *chainA, const int8_t *noise, const TexSet *ts, const uint32_t *skipMask, const uint32_t *tileOrder, void *image,
+                 const uint32_t *bitsA, const uint8_t *chainA, const int8_t *noise, const TexSet *ts, const uint32_t *skipMask, const uint32_t *maskFill, const uint32_t *tileOrder, void *image,
                  int format, unsigned long long *stats);
 size_t skipmask_words(const VolumeParams &vol, uint32_t *off);
 int launch_skipmask(cudaStream_t st, const VolumeParams &vol, const uint32_t *bits, const uint8_t *chain, uint32_t *nz,
-                    uint32_t *dil, uint32_t *mask);
+                    uint32_t *dil, uint32_t *mask, uint32_t *fill);
 int launch_generate_boards(cudaStream_t st, int n, const float minOff[3], const float maxOff[3], float minScale,
                            float maxScale, double radiusFactor, uint64_t seed, float *pos0, float *pos, float *scale);
 size_t export_scratch_words(size_t words);

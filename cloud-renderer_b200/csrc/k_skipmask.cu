@@ -36,6 +36,7 @@ struct MaskArgs {
     uint32_t *nz;                  // non-zero bits, levels >= 1 (level 0 slot unused)
     uint32_t *dil;                 // S_l
     uint32_t *mask;                // M_l
+    uint32_t *fill;                // fill[l] = number of set bits of M_l (the trace kernel skips tests that cannot pay off)
 };
 
 __device__ __forceinline__ bool locate(const MaskArgs &a, uint32_t w, int &l, int &z, int &y, int &wx) {
@@ -116,17 +117,23 @@ __device__ __forceinline__ uint32_t double_bits16(uint32_t h) {     // 16 bits -
 
 __global__ void __launch_bounds__(256) combine_kernel(MaskArgs a) {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    int l, z, y, wx;
-    if (!locate(a, w, l, z, y, wx)) return;
-    uint32_t m = a.dil[w];
-    if (l + 1 < a.levels) {
-        const int np = a.size[l + 1], wprp = a.wpr[l + 1];
-        const uint32_t *prow = a.dil + a.off[l + 1] + ((size_t)(z >> 1) * np + (y >> 1)) * wprp;
-        const uint32_t pw = prow[wx >> 1];
-        m |= double_bits16((wx & 1) ? (pw >> 16) : pw);
-        if (a.size[l] < 32) m &= (1u << a.size[l]) - 1u;
+    int l = -1, z, y, wx;
+    uint32_t m = 0;
+    if (locate(a, w, l, z, y, wx)) {
+        m = a.dil[w];
+        if (l + 1 < a.levels) {
+            const int np = a.size[l + 1], wprp = a.wpr[l + 1];
+            const uint32_t *prow = a.dil + a.off[l + 1] + ((size_t)(z >> 1) * np + (y >> 1)) * wprp;
+            const uint32_t pw = prow[wx >> 1];
+            m |= double_bits16((wx & 1) ? (pw >> 16) : pw);
+            if (a.size[l] < 32) m &= (1u << a.size[l]) - 1u;
+        }
+        a.mask[w] = m;
     }
-    a.mask[w] = m;
+    // per-level population of M_l: one atomic per (warp, level)
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, l);
+    const uint32_t sum = __reduce_add_sync(peers, (uint32_t)__popc(m));
+    if (l >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1 && sum) atomicAdd(&a.fill[l], sum);
 }
 
 } // namespace
@@ -142,7 +149,7 @@ size_t skipmask_words(const VolumeParams &vol, uint32_t *off) {
 }
 
 int launch_skipmask(cudaStream_t st, const VolumeParams &vol, const uint32_t *bits, const uint8_t *chain, uint32_t *nz,
-                    uint32_t *dil, uint32_t *mask) {
+                    uint32_t *dil, uint32_t *mask, uint32_t *fill) {
     MaskArgs a{};
     a.levels = vol.levels;
     for (int l = 0; l < vol.levels; l++) {
@@ -151,7 +158,8 @@ int launch_skipmask(cudaStream_t st, const VolumeParams &vol, const uint32_t *bi
         a.chainOff[l] = vol.levelOff[l];
     }
     a.totalWords = (uint32_t)skipmask_words(vol, a.off);
-    a.bits = bits; a.chain = chain; a.nz = nz; a.dil = dil; a.mask = mask;
+    a.bits = bits; a.chain = chain; a.nz = nz; a.dil = dil; a.mask = mask; a.fill = fill;
+    cudaMemsetAsync(fill, 0, kMaxLevels * sizeof(uint32_t), st);
     a.texelBytes = vol.texelBytes;
     int launches = 0;
     if (vol.levels > 1) {

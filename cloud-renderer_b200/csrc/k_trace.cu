@@ -51,6 +51,7 @@ struct TraceArgs {
     float invRange[3];            // 1 / range per axis
     float invDim;                 // 1 / voxelDim
     const uint32_t *mask;         // empty-space masks M_l (k_skipmask.cu), or nullptr
+    const uint32_t *fill;         // set bits of M_l per level
     const uint32_t *order;        // launch order of the tiles, longest list first (k_bin.cu)
 };
 
@@ -233,6 +234,12 @@ __global__ void __launch_bounds__(kTraceThreads, 2048 / kTraceThreads / 2) trace
 
     const uint32_t cnt = tp.active ? a.tileCnt[tile] : 0;
     const uint32_t off = cnt ? a.tileOff[tile] : 0;
+    // which groups are worth an empty-space test: a mask that is (nearly) full can (almost) never clear a group, and
+    // not testing is always exact (the samples are simply fetched)
+    uint32_t testBits = 0;
+    if (a.mask && cnt)
+        for (int g = 0; g < tp.nGroups; g++)
+            if ((unsigned long long)__ldg(a.fill + tp.groups[g].level) * 8ull < (unsigned long long)tp.groups[g].total * 7ull) testBits |= 1u << g;
     const float cutoff = tp.p.transmittanceCutoff;
     const int D = a.vol.dim;
     (void)D;
@@ -362,7 +369,7 @@ __global__ void __launch_bounds__(kTraceThreads, 2048 / kTraceThreads / 2) trace
                     const ConeGroup &gr = tp.groups[g];
                     bool need = shade;
                     // one conservative lookup decides the whole group: all-zero footprints contribute exactly 0
-                    if (a.mask && need)
+                    if (((testBits >> g) & 1u) && need)
                         need = group_occupied(a.mask, gr, fmaf(gr.height, ex, nx), fmaf(gr.height, ey, ny), fmaf(gr.height, ez, nz));
                     if (kStats && shade && !need) nSkip += gr.count;
                     if (!__any_sync(0xFFFFFFFFu, need)) continue;
@@ -453,7 +460,7 @@ __global__ void __launch_bounds__(kTraceThreads, 2048 / kTraceThreads / 2) trace
 
 int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol, const TraceParams &tp,
                  const BoardRec *recs, const Bins &b, const uint32_t *bits, const uint8_t *chain,
-                 const uint32_t *bitsA, const uint8_t *chainA, const int8_t *noise, const TexSet *ts, const uint32_t *skipMask, const uint32_t *tileOrder, void *image,
+                 const uint32_t *bitsA, const uint8_t *chainA, const int8_t *noise, const TexSet *ts, const uint32_t *skipMask, const uint32_t *maskFill, const uint32_t *tileOrder, void *image,
                  int format, unsigned long long *stats) {
     TraceArgs a;
     a.vol = vol;
@@ -464,6 +471,7 @@ int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol
     a.noise = reinterpret_cast<const float2 *>(noise);
     a.image = image; a.format = format; a.stats = stats;
     a.mask = (skipMask && tp.p.skipEmptySpace) ? skipMask : nullptr;
+    a.fill = maskFill;
     a.order = tileOrder;
     a.invRange[0] = 1.0f / (vol.xB[1] - vol.xB[0]);
     a.invRange[1] = 1.0f / (vol.yB[1] - vol.yB[0]);
