@@ -545,7 +545,7 @@ void build_trace_params(crn_ctx *c, const ViewParams &cam, TraceParams *tp) {
         ConeGroup &g = tp->groups[tp->nGroups++];
         g.height = 0.5f * (tp->steps[i].height + tp->steps[j].height);
         g.size = c->vparams.levelSize[l]; g.nMinus1 = g.size - 1;
-        g.sizeF = (float)g.size;
+        g.sizeF = (float)g.size; g.sizeLo = g.sizeF - 1.0f / 1024.0f;
         g.wpr = g.size >= 32 ? g.size / 32 : 1;
         g.maskOff = maskOff[l];
         g.first = i; g.count = j - i + 1;

@@ -63,6 +63,7 @@ struct ConeStep {                     // traceCone's per-step constants (identic
 struct ConeGroup {                    // consecutive cone steps decided by ONE empty-space lookup (k_skipmask.cu)
     float height;                     // lookup point along the cone, voxels
     float sizeF;                      // level size as float: normalized coordinate -> level texels
+    float sizeLo;                     // sizeF - 2^-10 (see group_occupied_sat)
     int32_t nMinus1;                  // level size - 1 (index clamp)
     int32_t size;                     // level size
     int32_t wpr;                      // mask words per row

@@ -68,6 +68,18 @@ __device__ __forceinline__ bool group_occupied(const uint32_t *__restrict__ mask
 
 __device__ __forceinline__ float saturatef(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
 
+// The same test with the index clamp folded into the arithmetic: the point is saturated to [0,1] (a free modifier on
+// the FFMA that produces it) and scaled by sizeLo = size - 2^-10 < size, so the truncated index cannot leave the
+// level.  A point within 2^-10 texel above a texel boundary may be looked up one texel low; M_l's 5x5x5 dilation
+// covers the footprints of the group from either texel, so the test stays conservative.
+__device__ __forceinline__ bool group_occupied_sat(const uint32_t *__restrict__ mask, const ConeGroup &g, float px, float py, float pz) {
+    const int ix = (int)(__saturatef(px) * g.sizeLo);
+    const int iy = (int)(__saturatef(py) * g.sizeLo);
+    const int iz = (int)(__saturatef(pz) * g.sizeLo);
+    const uint32_t word = g.maskOff + (uint32_t)((iz * g.size + iy) * g.wpr + (ix >> 5));
+    return (__ldg(mask + word) >> (ix & 31)) & 1u;
+}
+
 struct Lin {                       // one axis of a linear filter footprint
     int i0, i1;
     float a;
@@ -193,6 +205,7 @@ __device__ __forceinline__ bool sun_fragment(const TraceParams &tp, const ViewPa
 }
 
 // kTex = false: explicit filtering (CRN_SAMPLER_EXPLICIT);  kTex = true: texture units (CRN_SAMPLER_TEXTURE)
+constexpr int kFastGroups = 8;        // the unrolled (fast) variant handles up to this many empty-space groups
 constexpr int kTraceThreads = 64;     // 2 warp patches per CTA: measured best (256: 5.87 ms, 128: 5.83, 64: 5.79 at C3)
 
 // kGate: the paper variant's `if (sampleColor.a > 0)` on a second (occupancy) chain, CRN_VOLUME_RG8 only
@@ -364,15 +377,20 @@ __global__ void __launch_bounds__(kTraceThreads, 2048 / kTraceThreads / 2) trace
                 const float il = rsqrtf(ex * ex + ey * ey + ez * ez) * a.invDim;      // normalize(dir) / voxelDim
                 ex *= il; ey *= il; ez *= il;
                 float indirect = 0.0f;
-                // group and step loops are warp-uniform (constants come from uniform registers); lanes take part by predicate
-                for (int g = 0; g < tp.nGroups; g++) {
+                // group and step loops are warp-uniform (constants come from uniform registers); lanes take part by predicate.
+                // The fast variant unrolls the group loop (at most kFastGroups groups) so the group constants are immediates.
+                auto coneGroup = [&](const int g) {
                     const ConeGroup &gr = tp.groups[g];
                     bool need = shade;
                     // one conservative lookup decides the whole group: all-zero footprints contribute exactly 0
-                    if (((testBits >> g) & 1u) && need)
-                        need = group_occupied(a.mask, gr, fmaf(gr.height, ex, nx), fmaf(gr.height, ey, ny), fmaf(gr.height, ez, nz));
+                    if (((testBits >> g) & 1u) && need) {
+                        if constexpr (kOct4)
+                            need = group_occupied_sat(a.mask, gr, fmaf(gr.height, ex, nx), fmaf(gr.height, ey, ny), fmaf(gr.height, ez, nz));
+                        else
+                            need = group_occupied(a.mask, gr, fmaf(gr.height, ex, nx), fmaf(gr.height, ey, ny), fmaf(gr.height, ez, nz));
+                    }
                     if (kStats && shade && !need) nSkip += gr.count;
-                    if (!__any_sync(0xFFFFFFFFu, need)) continue;
+                    if (!__any_sync(0xFFFFFFFFu, need)) return;
 #pragma unroll 2
                     for (int i = gr.first; i < gr.first + gr.count; i++) {
                         const ConeStep &st = tp.steps[i];
@@ -402,6 +420,13 @@ __global__ void __launch_bounds__(kTraceThreads, 2048 / kTraceThreads / 2) trace
                             if (kStats) nFetch += st.frac != 0.0f ? 2 : 1;
                         }
                     }
+                };
+                if constexpr (kOct4) {
+#pragma unroll
+                    for (int g = 0; g < kFastGroups; g++)
+                        if (g < tp.nGroups) coneGroup(g);
+                } else {
+                    for (int g = 0; g < tp.nGroups; g++) coneGroup(g);
                 }
                 if (kStats && shade) nCone += tp.nSteps;
                 if (tp.p.doNoiseSample) { col[0] *= indirect; col[1] *= indirect; col[2] *= indirect; }
@@ -481,7 +506,8 @@ int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol
     const bool useTex = ts && ts->enabled && tp.p.sampler == CRN_SAMPLER_TEXTURE;
     const int grid = b.tilesX * b.tilesY * (256 / kTraceThreads);
     const bool gate = bitsA != nullptr;
-    const bool oct4 = tp.p.numOctaves == 4 && tp.noiseDim == 32;     // the reference's configuration: unrolled octave loop
+    // the reference's configuration (4 octaves, 32^3 noise) with the octave and group loops unrolled
+    const bool oct4 = tp.p.numOctaves == 4 && tp.noiseDim == 32 && tp.nGroups <= kFastGroups;
     if (gate) {                                                   // opt-in paper variant: stats variant only when asked
         if (useTex && tp.stats) trace_kernel<true, true, true, false><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, *ts);
         else if (useTex) trace_kernel<true, false, true, false><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, *ts);
