@@ -366,12 +366,13 @@ def main():
     r.set_stats(False)
     frag, cone, noise, bins = st.fragments, st.coneSamples, st.noiseSamples, st.binEntries
     cone_skipped, fetches = st.coneSamplesSkipped, st.filteredFetches
-    tex_peak = None
+    tex_peak = bil_peak = None
     if rank == 0 and args.sampler == "texture":
         try:
             tex_peak = min(pkg.microbench(0, local), pkg.microbench(1, local))     # G trilinear fetches/s, measured now
+            bil_peak = pkg.microbench(6, local)                                     # G bilinear (layered 2D) fetches/s
         except Exception:
-            tex_peak = None
+            tex_peak = bil_peak = None
 
     if rank == 0:
         job_frames = K if slab_mode else world * K          # C4 shards ONE frame per step over all ranks
@@ -411,10 +412,17 @@ def main():
                          "note": ("algorithmic texel bytes (SURVEY 8d: 16 B per fetched cone sample, 32 B per noise tap, + the image) are served "
                                   "by L1 at a 99.9% hit rate, so this fraction can exceed 1 and HBM is NOT the binding roof (traffic = DRAM bytes "
                                   "of one ncu capture, profiles/); the binding roof is the texture pipe: see roofline_tex")},
+            # texture-pipe roofline: the cone trace's volume lookups are 3D trilinear (two bilinear passes in the texture
+            # unit), the noise taps are single bilinear passes on the layered slice-pair texture; each kind is charged at
+            # its own measured ceiling and the fraction is (time at the ceilings) / (measured kernel time)
             "roofline_tex": None if not tex_peak else {
-                "bound": "tex", "achieved": fetches / (trace_ms * 1e-3) / 1e9, "peak": tex_peak, "unit": "G trilinear fetches/s",
-                "frac": fetches / (trace_ms * 1e-3) / 1e9 / tex_peak, "fetches_per_launch": fetches,
-                "peak_source": "crn_microbench tex3D trilinear (min of RGBA8 32^3 and R8 256^3), measured in this run"},
+                "bound": "tex", "unit": "G bilinear passes/s",
+                "achieved": (2 * (fetches - noise) + noise) / (trace_ms * 1e-3) / 1e9, "peak": bil_peak,
+                "frac": ((fetches - noise) / tex_peak + noise / bil_peak) / 1e9 / (trace_ms * 1e-3),
+                "cone_trilinear_lookups_per_launch": fetches - noise, "noise_bilinear_lookups_per_launch": noise,
+                "trilinear_peak": tex_peak,
+                "peak_source": "crn_microbench, measured in this run: tex2DLayered RGBA8 bilinear (peak) and tex3D trilinear "
+                               "(min of RGBA8 32^3 and R8 256^3) for the volume lookups"},
         }
         if not args.no_cpu_baseline and world == 1:
             orc = entry.import_oracle()

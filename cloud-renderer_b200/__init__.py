@@ -391,7 +391,8 @@ class Renderer:
 
 
 MICROBENCH = {0: "tex3D trilinear RGBA8_SNORM 32^3 (L1)", 1: "tex3D trilinear R8 256^3 (L2)", 2: "LDG.32 L1-hit",
-              3: "global atomicOr (RED), 2 MB set", 4: "shared atomicOr", 5: "FFMA"}
+              3: "global atomicOr (RED), 2 MB set", 4: "shared atomicOr", 5: "FFMA",
+              6: "tex2DLayered bilinear RGBA8_SNORM 32x32x32 (L1)"}
 
 
 def microbench(which, device=0):

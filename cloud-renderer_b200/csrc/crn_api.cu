@@ -559,7 +559,6 @@ void build_trace_params(crn_ctx *c, const ViewParams &cam, TraceParams *tp) {
         tp->octBias[o] = (o < 3 ? tp->octaveOffsets[o] : 0.0f) * freq;
         tp->octFreqZ[o] = tp->octFreq[o] * (float)c->noiseDim;
         tp->octBiasZ[o] = tp->octBias[o] * (float)c->noiseDim - 0.5f;
-        tp->octBiasZh[o] = tp->octBiasZ[o] - 0.5f;
         freq *= c->tp.freqStep; pers *= c->tp.persStep;
     }
 }

@@ -93,7 +93,6 @@ struct TraceParams {
     float octPers[kMaxOctaves];       // persStep^o
     float octFreqZ[kMaxOctaves];      // freq * noiseDim and bias * noiseDim - 0.5: the z texel coordinate of the layered
     float octBiasZ[kMaxOctaves];      //   noise texture (z filtered in the kernel, see TexSet::noise)
-    float octBiasZh[kMaxOctaves];     // octBiasZ - 0.5
     int32_t noiseMask;                // noiseDim - 1 if noiseDim is a power of two, else -1
     ConeStep steps[kMaxConeSteps];
     ConeGroup groups[kMaxConeSteps];

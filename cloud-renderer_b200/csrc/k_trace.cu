@@ -317,11 +317,11 @@ __global__ void __launch_bounds__(kTraceThreads, 2048 / kTraceThreads / 2) trace
                         if constexpr (kTex && kOct4) {
 #pragma unroll
                             for (int o = 0; o < 4; o++) {
-                                // layer = floor(z texel coordinate) as round-to-nearest of (z - 0.5) through the 1.5*2^23
-                                // trick (FADD pipe only); at an exact integer either neighbour gives the same blend
-                                const float zc = fmaf(tz, tp.octFreqZ[o], tp.octBiasZh[o]);
-                                const float m = __fadd_rn(zc, 12582912.0f);
-                                const float az = __fadd_rn(__fadd_rn(zc, -__fadd_rn(m, -12582912.0f)), 0.5f);
+                                // layer = floor(z texel coordinate) on the FADD pipe: adding 1.5*2^23 rounding DOWN leaves the
+                                // floor in the low mantissa bits (two's complement, so the & also wraps negative layers)
+                                const float zc = fmaf(tz, tp.octFreqZ[o], tp.octBiasZ[o]);
+                                const float m = __fadd_rd(zc, 12582912.0f);
+                                const float az = __fadd_rn(zc, -__fadd_rn(m, -12582912.0f));
                                 const int layer = __float_as_int(m) & 31;
                                 float4 t;                              // tex2DLayered without the header's 16-bit layer clamp
                                 asm("tex.a2d.v4.f32.f32 {%0, %1, %2, %3}, [%4, {%5, %6, %7, %7}];"
