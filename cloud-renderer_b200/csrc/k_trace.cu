@@ -309,25 +309,37 @@ __global__ void __launch_bounds__(kTraceThreads, 2048 / kTraceThreads / 2) trace
                 const float inv = 1.0f / (iSteps - 1.0f);
                 const float dxs = rx * len * inv, dys = ry * len * inv, dzs = rz * len * inv;              // localTexDelta
                 float opacity = 0.0f, light = 0.0f;
+                float adv = 0.0f;                                       // texture-space distance marched so far (fast variant)
+                const float sStep = len * inv;
                 const int nIter = shade ? (int)ceilf(iSteps) : 0;
                 const int nMax = __reduce_max_sync(0xFFFFFFFFu, nIter);
                 for (int i = 0; i < nMax; i++) {
                     if (i < nIter) {
                         float ng = 0.0f, na = 0.0f;
+                        // this step's texture / unit-sphere coordinates.  Fast variant: start + adv * viewRay with ONE running
+                        // scalar (the march follows the view ray, a kernel constant); generic: the shader's running sums
+                        float cx, cy, cz, vx, vy, vz;
+                        if constexpr (kTex && kOct4) {
+                            cx = fmaf(adv, rx, tx); cy = fmaf(adv, ry, tyy); cz = fmaf(adv, rz, tz);
+                            vx = fmaf(adv, rx, ux); vy = fmaf(adv, ry, uy); vz = fmaf(adv, rz, uz);
+                        } else {
+                            cx = tx; cy = tyy; cz = tz; vx = ux; vy = uy; vz = uz;
+                        }
                         if constexpr (kTex && kOct4) {
 #pragma unroll
                             for (int o = 0; o < 4; o++) {
                                 // layer = floor(z texel coordinate) on the FADD pipe: adding 1.5*2^23 rounding DOWN leaves the
                                 // floor in the low mantissa bits (two's complement, so the & also wraps negative layers)
-                                const float zc = fmaf(tz, tp.octFreqZ[o], tp.octBiasZ[o]);
+                                // octave 3's offset is 0 by decree (octaveOffsets[3]): its bias is a literal, not a constant load
+                                const float zc = o == 3 ? fmaf(cz, tp.octFreqZ[o], -0.5f) : fmaf(cz, tp.octFreqZ[o], tp.octBiasZ[o]);
                                 const float m = __fadd_rd(zc, 12582912.0f);
                                 const float az = __fadd_rn(zc, -__fadd_rn(m, -12582912.0f));
                                 const int layer = __float_as_int(m) & 31;
                                 float4 t;                              // tex2DLayered without the header's 16-bit layer clamp
                                 asm("tex.a2d.v4.f32.f32 {%0, %1, %2, %3}, [%4, {%5, %6, %7, %7}];"
                                     : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
-                                    : "l"(ts.noise), "r"(layer), "f"(fmaf(tx, tp.octFreq[o], tp.octBias[o])),
-                                      "f"(fmaf(tyy, tp.octFreq[o], tp.octBias[o])));
+                                    : "l"(ts.noise), "r"(layer), "f"(o == 3 ? cx * tp.octFreq[o] : fmaf(cx, tp.octFreq[o], tp.octBias[o])),
+                                      "f"(o == 3 ? cy * tp.octFreq[o] : fmaf(cy, tp.octFreq[o], tp.octBias[o])));
                                 ng = fmaf(tp.octPers[o], fmaf(az, t.z - t.x, t.x), ng);
                                 na = fmaf(tp.octPers[o], fmaf(az, t.w - t.y, t.y), na);
                             }
@@ -337,26 +349,29 @@ __global__ void __launch_bounds__(kTraceThreads, 2048 / kTraceThreads / 2) trace
                             float2 s;
                             if constexpr (kTex) {
                                 // one bilinear pass on layer floor(z) returns (g,a) of slices z and z+1; blend them here
-                                const float wz = fmaf(tz, tp.octFreqZ[o], tp.octBiasZ[o]);
+                                const float wz = fmaf(cz, tp.octFreqZ[o], tp.octBiasZ[o]);
                                 const float fl = floorf(wz), az = wz - fl;
                                 int layer = (int)fl;
                                 if (tp.noiseMask >= 0) layer &= tp.noiseMask;
                                 else { layer %= nzDim; if (layer < 0) layer += nzDim; }
-                                const float4 t = tex2DLayered<float4>(ts.noise, fmaf(tx, f, b), fmaf(tyy, f, b), layer);
+                                const float4 t = tex2DLayered<float4>(ts.noise, fmaf(cx, f, b), fmaf(cy, f, b), layer);
                                 s = make_float2(fmaf(az, t.z - t.x, t.x), fmaf(az, t.w - t.y, t.y));
                             } else {
-                                s = sample_noise(a.noise, nzDim, fmaf(tx, f, b), fmaf(tyy, f, b), fmaf(tz, f, b));
+                                s = sample_noise(a.noise, nzDim, fmaf(cx, f, b), fmaf(cy, f, b), fmaf(cz, f, b));
                             }
                             ng = fmaf(tp.octPers[o], s.x, ng);
                             na = fmaf(tp.octPers[o], s.y, na);
                         }
                         na = fabsf(na);
-                        const float uu = ux * ux + uy * uy + uz * uz;
-                        ng += uy * rsqrtf(uu);                          // noiseCell.xyz += normalize(unitTex)
+                        const float uu = vx * vx + vy * vy + vz * vz;
+                        ng += vy * rsqrtf(uu);                          // noiseCell.xyz += normalize(unitTex)
                         opacity = fmaf(na, 1.0f - uu, opacity);
                         light += saturatef(ng * 0.5f + 0.5f);
-                        tx += dxs; tyy += dys; tz += dzs;
-                        ux += dxs; uy += dys; uz += dzs;                // (sic) tex-space delta on the unit-sphere coord
+                        if constexpr (kTex && kOct4) adv += sStep;
+                        else {
+                            tx += dxs; tyy += dys; tz += dzs;
+                            ux += dxs; uy += dys; uz += dzs;            // (sic) tex-space delta on the unit-sphere coord
+                        }
                         if (kStats) nNoise += tp.p.numOctaves;
                     }
                 }

@@ -646,13 +646,14 @@ def test_paper_variant_occupancy_channel(name, pkg, scenes, orc):
         print(f"{name}/RG8/sampler{sampler}: PSNR {p:.1f} dB, max err {np.abs(img - ref).max():.2e}, "
               f"lit {int((l0 > 0).sum())}, occupied {int((a0 > 0).sum())}")
         assert p >= bar
-        # the gated kernel is a separate template instantiation: under --use_fast_math nvcc may contract its float
-        # expressions differently, so "unchanged" is bit-equal for the explicit sampler and 2e-4 for the texture one
+        # "unchanged" is bit-equal for the explicit sampler.  With the texture sampler the ungated frame ran the fast
+        # kernel variant (unrolled loops, start + adv * ray coordinates) and the gated one the generic variant (the
+        # shader's running sums), so the two differ by float rounding in the noise coordinates: 70 dB between them
         # (an instrumented build counted zero samples with alpha == 0 < rgb and zero with alpha < rgb)
         if sampler == pkg.SAMPLER_EXPLICIT:
             assert np.array_equal(img.view(np.uint32), base[sampler].view(np.uint32)), "the alpha gate changed the image"
         else:
-            assert np.abs(img - base[sampler]).max() < 2e-4, "the alpha gate changed the image"
+            assert psnr(img, base[sampler]) >= 70.0, "the alpha gate changed the image"
     # Z-slab sharding is not offered for this variant
     r.set_z_slab(0, s.vol.dimension // 2)
     with pytest.raises(pkg.CrnError):
@@ -736,4 +737,29 @@ def test_voxel_export(pkg, scenes, orc):
     want = expected(a0 > 0, l0 > 0, s.vol)
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
     assert 0 < got[:, 3].sum() == (l0 > 0).sum() < got.shape[0]
+    r.close()
+
+
+@pytest.mark.parametrize("dim,octaves,steps,angle", [(16, 4, 16, 0.9), (24, 4, 16, 0.9), (32, 5, 16, 0.9), (32, 4, 40, 0.25), (8, 2, 7, 1.4)])
+def test_noise_sizes_and_cone_settings_off_the_fast_path(dim, octaves, steps, angle, pkg, scenes, orc):
+    """The trace kernel has a fast variant for the reference's configuration (4 octaves, 32^3 noise, <= 8 empty-space
+    groups); every other setting takes the generic one: noise textures of other sizes (power of two or not: the layer
+    wrap of the slice-pair texture), more octaves, many cone steps (more than 8 groups)."""
+    s = steady_state(scenes.make_scene("small"), orc)
+    s.noise = scenes.make_noise(scenes.SEED, dim)
+    s.tp.numOctaves, s.tp.vctSteps, s.tp.vctConeAngle = octaves, steps, angle
+    r = pkg.Renderer(0)
+    r.set_scene(s); r.voxelize()
+    _, _, l0 = orc.voxelize(s, want_posmap=False)
+    ref, _, _ = orc.cone_trace(s, orc.mips(l0, s.vol.levels), want_u8=False)
+    for sampler, bar in ((pkg.SAMPLER_EXPLICIT, 90.0), (pkg.SAMPLER_TEXTURE, 45.0)):
+        imgs = []
+        for skip in (1, 0):
+            s.tp.sampler, s.tp.skipEmptySpace = sampler, skip
+            r.set_trace_params(s.tp)
+            imgs.append(r.cone_trace(fmt=pkg.IMAGE_RGBA32F).copy())
+        p = psnr(imgs[0], ref)
+        print(f"noise {dim}^3, {octaves} octaves, {steps} steps, sampler {sampler}: PSNR {p:.1f} dB, max err {np.abs(imgs[0] - ref).max():.2e}")
+        assert p >= bar
+        assert np.array_equal(imgs[0].view(np.uint32), imgs[1].view(np.uint32)), "empty-space skipping changed the image"
     r.close()
