@@ -206,13 +206,18 @@ __device__ __forceinline__ bool sun_fragment(const TraceParams &tp, const ViewPa
 
 // kTex = false: explicit filtering (CRN_SAMPLER_EXPLICIT);  kTex = true: texture units (CRN_SAMPLER_TEXTURE)
 constexpr int kFastGroups = 8;        // the unrolled (fast) variant handles up to this many empty-space groups
+// resident CTAs per SM the kernel is compiled for (register cap = 65536 / 64 / MINB).  Measured at C3 (trace ms):
+// 12: 4.82, 14: 4.73, 16: 4.39, 18: 4.36, 20: 4.52, 24: 4.60 -> 16 (64 registers, no spills in the fast variant)
+#ifndef CRN_TRACE_MINB
+#define CRN_TRACE_MINB 16
+#endif
 constexpr int kTraceThreads = 64;     // 2 warp patches per CTA: measured best (256: 5.87 ms, 128: 5.83, 64: 5.79 at C3)
 
 // kGate: the paper variant's `if (sampleColor.a > 0)` on a second (occupancy) chain, CRN_VOLUME_RG8 only
 // kOct4: the reference's noise configuration (numOctaves == 4, 32^3 texture) with the octave loop unrolled, so the
 //        per-octave constants become immediate operands instead of indexed constant loads
 template <bool kTex, bool kStats, bool kGate, bool kOct4>
-__global__ void __launch_bounds__(kTraceThreads, 2048 / kTraceThreads / 2) trace_kernel(const __grid_constant__ TraceArgs a, const __grid_constant__ ViewParams cam,
+__global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_kernel(const __grid_constant__ TraceArgs a, const __grid_constant__ ViewParams cam,
                                                     const __grid_constant__ TraceParams tp, const __grid_constant__ TexSet ts) {
     // a 16x16 tile is 8 warp patches; a CTA carries kTraceThreads/32 of them, so a slow patch holds up fewer warps
     constexpr int kWarps = kTraceThreads / 32, kSplit = 8 / kWarps;
