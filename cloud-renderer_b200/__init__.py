@@ -52,7 +52,8 @@ class TraceParams(C.Structure):
 
 
 class TraceStats(C.Structure):
-    _fields_ = [("fragments", u64), ("coneSamples", u64), ("noiseSamples", u64), ("binEntries", u64), ("coneSamplesSkipped", u64), ("filteredFetches", u64)]
+    _fields_ = [("fragments", u64), ("coneSamples", u64), ("noiseSamples", u64), ("binEntries", u64), ("coneSamplesSkipped", u64), ("filteredFetches", u64),
+                ("bakedFetches", u64)]
 
 
 class Timings(C.Structure):
@@ -392,7 +393,11 @@ class Renderer:
 
 MICROBENCH = {0: "tex3D trilinear RGBA8_SNORM 32^3 (L1)", 1: "tex3D trilinear R8 256^3 (L2)", 2: "LDG.32 L1-hit",
               3: "global atomicOr (RED), 2 MB set", 4: "shared atomicOr", 5: "FFMA",
-              6: "tex2DLayered bilinear RGBA8_SNORM 32x32x32 (L1)"}
+              6: "tex2DLayered bilinear RGBA8_SNORM 32x32x32 (L1)",
+              7: "tex2DLayered bilinear RG16 UNORM 129x129x128", 8: "tex2DLayered bilinear RG8 UNORM 129x129x128",
+              9: "tex2DLayered bilinear RGBA8_SNORM f16x2 return", 10: "tex3D trilinear R16 UNORM 129^3",
+              11: "tex3DLod R8 mipmapped 256^3 LOD 4.5", 12: "tex3DLod R8 mipmapped 256^3 LOD 2.5",
+              13: "tex2DLayered bilinear RG16F 129x129x128", 14: "tex3D RGBA8_SNORM 32^3, z on slice centres"}
 
 
 def microbench(which, device=0):

@@ -11,6 +11,7 @@
 // with CRN_ERR_NO_DEVICE / CRN_ERR_CUDA otherwise.
 #include "crn_internal.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -138,6 +139,7 @@ struct crn_ctx {
     int ilvIndex = 0, ilvCount = 1;
     int z0 = 0, z1 = -1;                 // -1: whole volume
     bool keepPosmap = false, statsOn = false, timingOn = false;
+    bool noBake = false;                 // CRN_NO_BAKE=1: every cone step through textureLod (A/B and tests)
     bool voxelized = false, traced = false;
 
     VolumeParams vparams{};
@@ -161,6 +163,18 @@ struct crn_ctx {
     cudaArray_t noiseArray = nullptr;
     TexSet ts{};
     bool texCurrent = false;             // the arrays hold the chain of the last voxelize
+
+    // per-frame cone acceleration data (k_conebake.cu): baked step textures + the need-code grid
+    cudaArray_t bakedArr[kMaxBakedTex] = {};
+    cudaSurfaceObject_t bakedSurf[kMaxBakedTex] = {};
+    int bakedN[kMaxBakedTex] = {};
+    BakeTex bakePlan[kMaxBakedTex] = {};
+    int nBakePlan = 0;
+    DevBuf needCode;
+    uint64_t volumeGen = 0;              // bumped whenever the chain changes (voxelize, finish_mips)
+    struct BakeKey { uint64_t gen; int nTex; int level0[kMaxBakedTex]; float frac[kMaxBakedTex]; int n[kMaxBakedTex]; } bakeKey{};
+    struct CodeKey { uint64_t gen; int G, nGroups; float height[kCodeGroups]; int level[kCodeGroups]; float light[3]; float bounds[6]; } codeKey{};
+    bool bakeValid = false, codeValid = false;
 
     // pipelined read-back (crn_cone_trace_async): second image buffer, copy stream, frame/copy events
     DevBuf image2;
@@ -289,6 +303,13 @@ void free_chain_textures(cudaMipmappedArray_t &arr, TexSet &ts) {
     arr = nullptr;
 }
 
+void free_baked(crn_ctx *c, int i) {
+    if (c->ts.baked[i]) cudaDestroyTextureObject(c->ts.baked[i]);
+    if (c->bakedSurf[i]) cudaDestroySurfaceObject(c->bakedSurf[i]);
+    if (c->bakedArr[i]) cudaFreeArray(c->bakedArr[i]);
+    c->ts.baked[i] = 0; c->bakedSurf[i] = 0; c->bakedArr[i] = nullptr; c->bakedN[i] = 0;
+}
+
 void free_vol_textures(crn_ctx *c) {
     free_chain_textures(c->volArray, c->ts);
     free_chain_textures(c->volArrayA, c->tsA);
@@ -413,6 +434,59 @@ int build_masks(crn_ctx *c) {
     return CRN_OK;
 }
 
+// layered RG16 array of one baked cone step: n x n texels, n-1 layers (layer k = node planes k and k+1)
+int ensure_baked_array(crn_ctx *c, int i, int n) {
+    if (c->bakedArr[i] && c->bakedN[i] == n) return CRN_OK;
+    CRN_CUDA(c, cudaStreamSynchronize(c->stream));
+    free_baked(c, i);
+    cudaChannelFormatDesc cd = cudaCreateChannelDesc(16, 16, 0, 0, cudaChannelFormatKindUnsigned);
+    CRN_CUDA(c, cudaMalloc3DArray(&c->bakedArr[i], &cd, make_cudaExtent(n, n, n - 1), cudaArrayLayered | cudaArraySurfaceLoadStore));
+    cudaResourceDesc rd{};
+    rd.resType = cudaResourceTypeArray; rd.res.array.array = c->bakedArr[i];
+    CRN_CUDA(c, cudaCreateSurfaceObject(&c->bakedSurf[i], &rd));
+    cudaTextureDesc td{};
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModeLinear; td.readMode = cudaReadModeNormalizedFloat; td.normalizedCoords = 1;
+    CRN_CUDA(c, cudaCreateTextureObject(&c->ts.baked[i], &rd, &td, nullptr));
+    c->bakedN[i] = n;
+    c->bakeValid = false;
+    return CRN_OK;
+}
+
+// (re)build whatever of the cone acceleration data is stale for this frame's volume / cone parameters / light
+int build_cone_accel(crn_ctx *c, TraceParams &tp) {
+    int r;
+    if (c->nBakePlan > 0) {
+        crn_ctx::BakeKey k{};
+        k.gen = c->volumeGen; k.nTex = c->nBakePlan;
+        for (int i = 0; i < c->nBakePlan; i++) {
+            if ((r = ensure_baked_array(c, i, c->bakePlan[i].n))) return r;
+            c->bakePlan[i].surf = c->bakedSurf[i];
+            k.level0[i] = c->bakePlan[i].level0; k.frac[i] = c->bakePlan[i].frac; k.n[i] = c->bakePlan[i].n;
+        }
+        if (!c->bakeValid || std::memcmp(&k, &c->bakeKey, sizeof k) != 0) {
+            c->launches += launch_bake_steps(c->stream, c->vparams, (const uint32_t *)c->bits.p, (const uint8_t *)c->chain.p, c->bakePlan, c->nBakePlan);
+            c->bakeKey = k; c->bakeValid = true;
+        }
+    }
+    for (int b = 0; b < tp.nBaked; b++) tp.baked[b].tex = (unsigned long long)c->ts.baked[tp.baked[b].tex];
+    if (tp.codeDim > 0) {
+        const size_t cells = (size_t)tp.codeDim * tp.codeDim * tp.codeDim;
+        if ((r = reserve(c, c->needCode, cells))) return r;
+        crn_ctx::CodeKey k{};
+        k.gen = c->volumeGen; k.G = tp.codeDim; k.nGroups = std::min(tp.nGroups, kCodeGroups);
+        for (int g = 0; g < k.nGroups; g++) { k.height[g] = tp.groups[g].height; k.level[g] = tp.groups[g].level; }
+        for (int i = 0; i < 3; i++) k.light[i] = tp.lightPos[i];
+        const float b[6] = {c->vparams.xB[0], c->vparams.xB[1], c->vparams.yB[0], c->vparams.yB[1], c->vparams.zB[0], c->vparams.zB[1]};
+        std::memcpy(k.bounds, b, sizeof b);
+        if (!c->codeValid || std::memcmp(&k, &c->codeKey, sizeof k) != 0) {
+            c->launches += launch_need_code(c->stream, c->vparams, tp, (const uint32_t *)c->mask.p, (uint8_t *)c->needCode.p);
+            c->codeKey = k; c->codeValid = true;
+        }
+    }
+    return CRN_OK;
+}
+
 int enqueue_voxelize(crn_ctx *c) {
     const int n = c->nBoards;
     crn_sun_derived sd;
@@ -489,6 +563,7 @@ int enqueue_voxelize(crn_ctx *c) {
     const bool whole = c->vparams.z0 == 0 && c->vparams.z1 == c->vol.dimension;
     c->texCurrent = toTex && whole;
     c->maskCurrent = false;
+    c->volumeGen++;
     if (whole && c->tp.skipEmptySpace) {
         if ((r = build_masks(c))) return r;
     }
@@ -531,26 +606,80 @@ void build_trace_params(crn_ctx *c, const ViewParams &cam, TraceParams *tp) {
         s.lod0 = (float)s.level0; s.lod1 = (float)(s.level0 + 1); s.lod = s.lod0 + s.frac;
         coneHeight += coneRadius;
     }
-    // groups for the empty-space test: consecutive steps with the same lower level whose sample points
+    // Baked steps (k_conebake.cu): the longest suffix of the step list whose (level, fraction) lattices are small enough.
+    // Only the texture sampler of the shipped formats uses them: the explicit sampler stays the full-precision path and
+    // the paper variant needs its alpha gate per sample.
+    const int D = c->vol.dimension, S = c->tp.vctSteps;
+    tp->nFine = S; tp->nBaked = 0;
+    c->nBakePlan = 0;
+    if (c->tp.sampler == CRN_SAMPLER_TEXTURE && c->vol.format != CRN_VOLUME_RG8 && c->tp.doConeTrace && !c->noBake) {
+        int first = S;
+        size_t bytes = 0;
+        int texOf[kMaxConeSteps];
+        for (int i = S - 1; i >= 0 && S - i <= kMaxBakedSteps; i--) {
+            const int l0 = tp->steps[i].level0;
+            const float fr = tp->steps[i].frac;
+            const int n = l0 == 0 ? 2 * D + 1 : (D >> (l0 - 1)) + 1;
+            if (n > 129) break;
+            int t = -1;
+            for (int j = 0; j < c->nBakePlan; j++)
+                if (c->bakePlan[j].level0 == l0 && c->bakePlan[j].frac == fr) t = j;
+            if (t < 0) {
+                const size_t need = (size_t)n * n * (n - 1) * 4;
+                if (c->nBakePlan == kMaxBakedTex || bytes + need > ((size_t)128 << 20)) break;
+                t = c->nBakePlan++;
+                c->bakePlan[t].level0 = l0; c->bakePlan[t].frac = fr; c->bakePlan[t].n = n; c->bakePlan[t].surf = 0;
+                bytes += need;
+            }
+            texOf[i] = t;
+            first = i;
+        }
+        tp->nFine = first; tp->nBaked = S - first;
+        for (int i = first; i < S; i++) {
+            BakedStep &b = tp->baked[i - first];
+            const int n = c->bakePlan[texOf[i]].n;
+            b.height = tp->steps[i].height; b.weight = tp->steps[i].weight;
+            b.A = (float)(n - 1) / (float)n; b.B = 0.5f / (float)n;
+            b.zScale = (float)(n - 1) * (1.0f - 1.0f / 1048576.0f);
+            b.hA = b.height * b.A;
+            b.tex = (unsigned long long)texOf[i];         // plan index here; build_cone_accel swaps in the texture object
+        }
+        // drop plan entries no surviving step refers to (a break above may have left the last one unused)
+        bool used[kMaxBakedTex] = {};
+        for (int i = first; i < S; i++) used[texOf[i]] = true;
+        while (c->nBakePlan > 0 && !used[c->nBakePlan - 1]) c->nBakePlan--;
+    }
+    // groups for the empty-space test: consecutive textureLod steps with the same lower level whose sample points
     // all lie within one level-l texel of the group's mid height (so M_l's 5x5x5 dilation covers them)
     tp->nGroups = 0;
     uint32_t maskOff[kMaxLevels] = {};
     skipmask_words(c->vparams, maskOff);
-    for (int i = 0; i < c->tp.vctSteps;) {
+    for (int i = 0; i < tp->nFine;) {
         const int l = tp->steps[i].level0;
         const float texel = 0.98f * (float)(1 << l);
         int j = i;
-        while (j + 1 < c->tp.vctSteps && tp->steps[j + 1].level0 == l &&
+        while (j + 1 < tp->nFine && tp->steps[j + 1].level0 == l &&
                0.5f * fabsf(tp->steps[j + 1].height - tp->steps[i].height) < texel) j++;
         ConeGroup &g = tp->groups[tp->nGroups++];
         g.height = 0.5f * (tp->steps[i].height + tp->steps[j].height);
-        g.size = c->vparams.levelSize[l]; g.nMinus1 = g.size - 1;
-        g.sizeF = (float)g.size; g.sizeLo = g.sizeF - 1.0f / 1024.0f;
+        g.size = c->vparams.levelSize[l];
         g.wpr = g.size >= 32 ? g.size / 32 : 1;
         g.maskOff = maskOff[l];
         g.first = i; g.count = j - i + 1;
-        g.level = l; g.total = (uint32_t)g.size * g.size * g.size;
+        g.level = l;
         i = j + 1;
+    }
+    // need-code grid: cells of two voxels; only worth a kernel when some step is still fetched with textureLod
+    tp->codeDim = (c->tp.skipEmptySpace && tp->nGroups > 0 && c->tp.doConeTrace) ? std::max(16, D / 2) : 0;
+    tp->codeDimF = (float)tp->codeDim;
+    {   // derived constants of the fast variant
+        FastConst &f = tp->f;
+        f.invP0 = 1.0f / cam.P[0]; f.invP5 = 1.0f / cam.P[5];
+        f.invAdjust = 1.0f / c->tp.adjustSize; f.invStep = 1.0f / c->tp.stepSize;
+        f.span = (float)(c->tp.maxNoiseSteps - c->tp.minNoiseSteps); f.minSteps = (float)c->tp.minNoiseSteps;
+        const float lo[3] = {c->vparams.xB[0], c->vparams.yB[0], c->vparams.zB[0]}, hi[3] = {c->vparams.xB[1], c->vparams.yB[1], c->vparams.zB[1]};
+        for (int k = 0; k < 3; k++) { f.nScale[k] = 1.0f / (hi[k] - lo[k]); f.nBias[k] = -lo[k] * f.nScale[k]; }
+        f.invDim = 1.0f / (float)c->vol.dimension;
     }
     // noise3D's per-octave constants (res/conetrace_frag.glsl:107-114)
     float freq = 1.0f, pers = 1.0f;
@@ -604,6 +733,8 @@ int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
     }
     unsigned long long *dStats = (unsigned long long *)((char *)c->misc.p + 64);
     if (c->statsOn) cudaMemsetAsync(dStats, 0, 8 * sizeof(unsigned long long), st);
+    if (c->timingOn) cudaEventRecord(c->evT[2], st);                // the cone acceleration data is part of the trace stage
+    if ((r = build_cone_accel(c, tp))) return r;
     // ---- camera-side set-up on the side stream: after the billboard upload and after the previous trace (which reads
     //      the same records / bins), concurrently with whatever voxelize work is still queued on the main stream
     cudaStream_t ax = c->auxStream;
@@ -627,12 +758,10 @@ int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
     if (c->timingOn) cudaEventRecord(c->evAuxT[2], ax);
     cudaEventRecord(c->evAuxDone, ax);
     cudaStreamWaitEvent(st, c->evAuxDone, 0);
-    if (c->timingOn) cudaEventRecord(c->evT[2], st);
     c->launches += launch_trace(st, cam, c->vparams, tp, (const BoardRec *)c->recC.p, c->binsC, (const uint32_t *)c->bits.p,
                                 (const uint8_t *)c->chain.p, c->vol.format == CRN_VOLUME_RG8 ? (const uint32_t *)c->bitsA.p : nullptr,
                                 (const uint8_t *)c->chainA.p, (const int8_t *)c->noise.p, useTex ? &c->ts : nullptr,
-                                c->tp.skipEmptySpace ? (const uint32_t *)c->mask.p : nullptr,
-                                (const uint32_t *)((char *)c->misc.p + 192), (const uint32_t *)c->tileOrder.p,
+                                tp.codeDim > 0 ? (const uint8_t *)c->needCode.p : nullptr, (const uint32_t *)c->tileOrder.p,
                                 img.p, format, dStats);
     cudaEventRecord(c->evTraceEnd, st);
     c->traceEndValid = true;
@@ -704,6 +833,7 @@ int crn_create(int device, void *stream, crn_ctx **out) {
     for (auto &ev : c->evV) cudaEventCreate(&ev);
     for (auto &ev : c->evT) cudaEventCreate(&ev);
     crn_default_trace_params(&c->tp);
+    if (const char *nb = getenv("CRN_NO_BAKE")) c->noBake = atoi(nb) != 0;
     if (const char *pm = getenv("CRN_BIN_POOL_MIN")) { const long v = atol(pm); if (v > 0) c->poolMin = (size_t)v; }
     if ((e = cudaGetLastError()) != cudaSuccess) {
         crn_destroy(c);
@@ -726,6 +856,8 @@ void crn_destroy(crn_ctx *c) {
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     free_bins(c->binsL); free_bins(c->binsC);
     free_vol_textures(c);
+    for (int i = 0; i < kMaxBakedTex; i++) free_baked(c, i);
+    if (c->needCode.p) cudaFree(c->needCode.p);
     if (c->ts.noise) cudaDestroyTextureObject(c->ts.noise);
     if (c->noiseArray) cudaFreeArray(c->noiseArray);
     if (c->hCursors) cudaFreeHost(c->hCursors);
@@ -1154,6 +1286,7 @@ int crn_finish_mips(crn_ctx *c, int32_t first_level) {
     c->voxelized = true;
     c->texCurrent = false;              // the texture-unit copy is refreshed from the chain at the next trace
     c->maskCurrent = false;
+    c->volumeGen++;
     return CRN_OK;
 }
 
@@ -1294,7 +1427,8 @@ int crn_get_trace_stats(crn_ctx *c, crn_trace_stats *out) {
     out->fragments = c->hStats[0]; out->coneSamples = c->hStats[1]; out->noiseSamples = c->hStats[2];
     out->binEntries = c->hCursors[3];
     out->coneSamplesSkipped = c->hStats[3];
-    out->filteredFetches = c->hStats[4] + c->hStats[2];      // cone fetches + noise taps
+    out->bakedFetches = c->hStats[5];
+    out->filteredFetches = c->hStats[4] + c->hStats[5] + c->hStats[2];      // textureLod cone fetches + baked cone fetches + noise taps
     return CRN_OK;
 }
 

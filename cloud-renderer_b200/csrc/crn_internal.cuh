@@ -19,6 +19,9 @@ constexpr int kCoarse = 4;           // coarse tile = kCoarse x kCoarse fine til
 constexpr int kMaxConeSteps = 128;   // vctSteps upper bound (reference UI slider tops out far lower)
 constexpr int kMaxLevels = 16;
 constexpr int kMaxOctaves = 8;
+constexpr int kMaxBakedTex = 16;     // baked cone-step textures per frame (k_conebake.cu)
+constexpr int kMaxBakedSteps = 32;   // cone steps that may read them (several steps can share one texture)
+constexpr int kCodeGroups = 8;       // empty-space groups with a bit in the need-code grid (later groups are always fetched)
 
 // One billboard as a pass sees it, stored in that pass's list order (32 B, two 128-bit loads).
 struct BoardRec {
@@ -60,17 +63,33 @@ struct ConeStep {                     // traceCone's per-step constants (identic
     float lod;                        // level0 + frac: the tex3DLod operand (mip-linear blend in the texture unit)
 };
 
-struct ConeGroup {                    // consecutive cone steps decided by ONE empty-space lookup (k_skipmask.cu)
+struct ConeGroup {                    // consecutive cone steps decided by ONE empty-space bit (k_skipmask.cu, k_conebake.cu)
     float height;                     // lookup point along the cone, voxels
-    float sizeF;                      // level size as float: normalized coordinate -> level texels
-    float sizeLo;                     // sizeF - 2^-10 (see group_occupied_sat)
-    int32_t nMinus1;                  // level size - 1 (index clamp)
     int32_t size;                     // level size
     int32_t wpr;                      // mask words per row
     uint32_t maskOff;                 // word offset of M_level
     int32_t first, count;             // steps [first, first+count)
     int32_t level;                    // mip level of the mask
-    uint32_t total;                   // texels of that level
+};
+
+// A cone step whose (lower level, mip fraction) pair was baked into its own texture for this frame (k_conebake.cu):
+// one bilinear fetch on a layered slice-pair texture + a z blend in the kernel replaces the two trilinear fetches of
+// textureLod.  The lattice has n nodes per axis over [0,1] (texel centres ON the nodes).
+struct BakedStep {
+    float height, weight;
+    float A, B;                       // x' = s * A + B: normalized volume coordinate -> normalized texture coordinate, A = (n-1)/n, B = 0.5/n
+    float zScale;                     // (n-1) * (1 - 2^-20): lattice z of saturate(s), always < n-1 so that floor() <= n-2
+    float hA;                         // height * A
+    unsigned long long tex;           // cudaTextureObject_t of the step's layered RG16 slice-pair texture
+};
+
+// constants of the fast trace variant, derived on the host once per frame
+struct FastConst {
+    float invP0, invP5;               // 1 / P[0], 1 / P[5]
+    float invAdjust, invStep;         // 1 / adjustSize, 1 / stepSize
+    float span, minSteps;             // maxNoiseSteps - minNoiseSteps, minNoiseSteps (as floats)
+    float nScale[3], nBias[3];        // normalized volume coordinate of a world position: w * nScale + nBias
+    float invDim;
 };
 
 struct TraceParams {
@@ -94,6 +113,12 @@ struct TraceParams {
     float octFreqZ[kMaxOctaves];      // freq * noiseDim and bias * noiseDim - 0.5: the z texel coordinate of the layered
     float octBiasZ[kMaxOctaves];      //   noise texture (z filtered in the kernel, see TexSet::noise)
     int32_t noiseMask;                // noiseDim - 1 if noiseDim is a power of two, else -1
+    int32_t nFine;                    // steps[0..nFine) are fetched with textureLod (grouped for the empty-space test)
+    int32_t nBaked;                   // baked[0..nBaked) are the remaining steps, in step order
+    int32_t codeDim;                  // cells per axis of the need-code grid (0: no empty-space skipping)
+    float codeDimF;
+    FastConst f;
+    BakedStep baked[kMaxBakedSteps];
     ConeStep steps[kMaxConeSteps];
     ConeGroup groups[kMaxConeSteps];
 };
@@ -130,7 +155,18 @@ struct TexSet {
     cudaTextureObject_t vol;                // the whole mipmapped array: LINEAR in-level and between levels (tex3DLod)
     cudaTextureObject_t volA;               // CRN_VOLUME_RG8: the occupancy channel's chain, same sampling state
     cudaTextureObject_t noise;              // layered 2D RGBA8_SNORM, LINEAR, REPEAT: layer z holds (g_z, a_z, g_z+1, a_z+1)
+    cudaTextureObject_t baked[kMaxBakedTex]; // layered 2D RG16 UNORM, LINEAR, CLAMP: layer k holds (B(x,y,k), B(x,y,k+1)) of one baked step
     int32_t enabled;
+};
+
+// one baked cone-step texture: value(node) = (1-frac) * trilinear(level0) + frac * trilinear(level0+1) at the nodes of
+// a lattice that contains the texel centres of both levels (spacing 2^(level0-1) voxels), so that linear interpolation
+// between nodes reproduces the mip-linear lookup exactly
+struct BakeTex {
+    int32_t level0;
+    float frac;
+    int32_t n;                        // nodes per axis = dim / spacing + 1
+    cudaSurfaceObject_t surf;         // layered RG16, n x n x (n-1)
 };
 
 int launch_mips(cudaStream_t st, const VolumeParams &vol, const uint32_t *bits, uint8_t *chain, uint32_t *ticket,
@@ -139,8 +175,10 @@ int launch_chain_to_surfaces(cudaStream_t st, const VolumeParams &vol, const uin
 int launch_finish_mips(cudaStream_t st, const VolumeParams &vol, uint8_t *chain, int firstLevel);
 int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol, const TraceParams &tp,
                  const BoardRec *recs, const Bins &b, const uint32_t *bits, const uint8_t *chain,
-                 const uint32_t *bitsA, const uint8_t *chainA, const int8_t *noise, const TexSet *ts, const uint32_t *skipMask, const uint32_t *maskFill, const uint32_t *tileOrder, void *image,
+                 const uint32_t *bitsA, const uint8_t *chainA, const int8_t *noise, const TexSet *ts, const uint8_t *needCode, const uint32_t *tileOrder, void *image,
                  int format, unsigned long long *stats);
+int launch_bake_steps(cudaStream_t st, const VolumeParams &vol, const uint32_t *bits, const uint8_t *chain, const BakeTex *tex, int nTex);
+int launch_need_code(cudaStream_t st, const VolumeParams &vol, const TraceParams &tp, const uint32_t *mask, uint8_t *code);
 size_t skipmask_words(const VolumeParams &vol, uint32_t *off);
 int launch_skipmask(cudaStream_t st, const VolumeParams &vol, const uint32_t *bits, const uint8_t *chain, uint32_t *nz,
                     uint32_t *dil, uint32_t *mask, uint32_t *fill);

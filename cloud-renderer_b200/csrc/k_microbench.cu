@@ -7,6 +7,15 @@
 //   3  global atomicOr (RED) rate, addresses spread over a 2 MB bitset
 //   4  shared-memory atomicOr rate, spread addresses
 //   5  FFMA issue rate (sanity: the instruction-issue ceiling)
+//   6  tex2DLayered bilinear, RGBA8_SNORM 32x32x32 layers (the noise texture's layout)
+//   7  tex2DLayered bilinear, RG16 UNORM 129x129x128 layers (baked cone-step textures, slice pairs)
+//   8  tex2DLayered bilinear, RG8 UNORM 129x129x128 layers
+//   9  tex2DLayered bilinear, RGBA8_SNORM, f16x2 return (two registers instead of four)
+//  10  tex3D trilinear, R16 UNORM 129^3
+//  11  tex3DLod on the mipmapped R8 256^3 volume at LOD 4.5 (two levels blended: "quadrilinear")
+//  12  tex3DLod on the mipmapped R8 256^3 volume at LOD 2.5
+//  13  tex2DLayered bilinear, RG16F 129x129x128 layers
+//  14  tex3D RGBA8_SNORM 32^3 sampled exactly AT slice centres in z (does the filter skip the zero-weight slice?)
 // Each returns giga-operations per second (lane-level operations), timed with CUDA events.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -32,6 +41,21 @@ __global__ void __launch_bounds__(256) tex_noise_kernel(cudaTextureObject_t tex,
     if (acc.x + acc.y + acc.z + acc.w == 12345.678f) out[0] = acc.x;
 }
 
+// 3D fetch whose z coordinate sits exactly on a slice centre: the second slice has weight 0
+__global__ void __launch_bounds__(256) tex_noise_zc_kernel(cudaTextureObject_t tex, float *out, float step) {
+    const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    float u = (lane & 7) * 0.006f + warp * 0.013f, v = (lane >> 3) * 0.006f + warp * 0.007f;
+    int layer = warp & 31;
+    float4 acc = make_float4(0, 0, 0, 0);
+#pragma unroll 8
+    for (int i = 0; i < kIters; i++) {
+        const float4 t = tex3D<float4>(tex, u, v, ((float)layer + 0.5f) * (1.0f / 32.0f));
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        u += step; v += step * 0.7f; layer = (layer + (i & 1)) & 31;
+    }
+    if (acc.x + acc.y + acc.z + acc.w == 12345.678f) out[0] = acc.x;
+}
+
 // bilinear fetch from a layered 2D RGBA8_SNORM texture (the noise texture's layout in the trace kernel)
 __global__ void __launch_bounds__(256) tex_layered_kernel(cudaTextureObject_t tex, float *out, float step) {
     const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -45,6 +69,51 @@ __global__ void __launch_bounds__(256) tex_layered_kernel(cudaTextureObject_t te
         u += step; v += step * 0.7f; layer = (layer + (i & 1)) & 31;
     }
     if (acc.x + acc.y + acc.z + acc.w == 12345.678f) out[0] = acc.x;
+}
+
+// two-channel layered texture (baked cone-step slice pairs)
+__global__ void __launch_bounds__(256) tex_layered2_kernel(cudaTextureObject_t tex, float *out, float step, int layers) {
+    const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    float u = 0.1f + (lane & 7) * 0.0008f + (warp % 97) * 0.008f, v = 0.1f + (lane >> 3) * 0.0012f + (warp % 89) * 0.009f;
+    int layer = warp % layers;
+    float2 acc = make_float2(0, 0);
+#pragma unroll 8
+    for (int i = 0; i < kIters; i++) {
+        const float2 t = tex2DLayered<float2>(tex, u, v, layer);
+        acc.x += t.x; acc.y += t.y;
+        u += step; v += step * 0.7f; layer += (i & 15) == 15; if (layer >= layers) layer = 0;
+    }
+    if (acc.x + acc.y == 12345.678f) out[0] = acc.x;
+}
+
+// RGBA8_SNORM layered, result as two f16x2 registers
+__global__ void __launch_bounds__(256) tex_layered_h2_kernel(cudaTextureObject_t tex, float *out, float step) {
+    const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    float u = (lane & 7) * 0.006f + warp * 0.013f, v = (lane >> 3) * 0.006f + warp * 0.007f;
+    int layer = warp & 31;
+    uint32_t a0 = 0, a1 = 0;
+#pragma unroll 8
+    for (int i = 0; i < kIters; i++) {
+        uint32_t lo, hi;
+        asm volatile("tex.a2d.v2.f16x2.f32 {%0, %1}, [%2, {%3, %4, %5, %5}];" : "=r"(lo), "=r"(hi) : "l"(tex), "r"(layer), "f"(u), "f"(v));
+        asm("add.f16x2 %0, %0, %1;" : "+r"(a0) : "r"(lo));
+        asm("add.f16x2 %0, %0, %1;" : "+r"(a1) : "r"(hi));
+        u += step; v += step * 0.7f; layer = (layer + (i & 1)) & 31;
+    }
+    if (a0 + a1 == 0x12345678u) out[0] = 1.0f;
+}
+
+__global__ void __launch_bounds__(256) tex_lod_kernel(cudaTextureObject_t tex, float *out, float step, float lod) {
+    const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    float u = 0.1f + (lane & 7) * 0.0008f + (warp % 97) * 0.008f, v = 0.1f + (lane >> 3) * 0.0012f + (warp % 89) * 0.009f,
+          w = 0.1f + (warp % 83) * 0.0095f;
+    float acc = 0;
+#pragma unroll 8
+    for (int i = 0; i < kIters; i++) {
+        acc += tex3DLod<float>(tex, u, v, w, lod);
+        u += step; v += step * 0.7f; w += step * 0.3f;
+    }
+    if (acc == 12345.678f) out[0] = acc;
 }
 
 __global__ void __launch_bounds__(256) tex_vol_kernel(cudaTextureObject_t tex, float *out, float step) {
@@ -150,21 +219,22 @@ extern "C" int crn_microbench(int device, int which, double *gops) {
     float *dOut = nullptr;
     cudaMalloc(&dOut, 256);
     double ms = 0, ops = lanes;
-    if (which == 0 || which == 1) {
-        const int n = which == 0 ? 32 : 256;
-        cudaChannelFormatDesc cd = which == 0 ? cudaCreateChannelDesc(8, 8, 8, 8, cudaChannelFormatKindSigned)
+    if (which == 0 || which == 1 || which == 14) {
+        const int n = which != 1 ? 32 : 256;
+        cudaChannelFormatDesc cd = which != 1 ? cudaCreateChannelDesc(8, 8, 8, 8, cudaChannelFormatKindSigned)
                                               : cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned);
         cudaArray_t arr = nullptr;
         cudaMalloc3DArray(&arr, &cd, make_cudaExtent(n, n, n));
-        const size_t texel = which == 0 ? 4 : 1;
+        const size_t texel = which != 1 ? 4 : 1;
         std::vector<uint8_t> h((size_t)n * n * n * texel);
         for (size_t i = 0; i < h.size(); i++) h[i] = (uint8_t)(i * 2654435761u >> 24);
         cudaMemcpy3DParms cp{};
         cp.srcPtr = make_cudaPitchedPtr(h.data(), n * texel, n, n);
         cp.dstArray = arr; cp.extent = make_cudaExtent(n, n, n); cp.kind = cudaMemcpyHostToDevice;
         cudaMemcpy3D(&cp);
-        cudaTextureObject_t tex = make_tex(arr, which == 0);
-        if (which == 0) ms = time_ms([&] { tex_noise_kernel<<<blocks, threads>>>(tex, dOut, 0.004f); }, 5);
+        cudaTextureObject_t tex = make_tex(arr, which != 1);
+        if (which == 14) ms = time_ms([&] { tex_noise_zc_kernel<<<blocks, threads>>>(tex, dOut, 0.004f); }, 5);
+        else if (which == 0) ms = time_ms([&] { tex_noise_kernel<<<blocks, threads>>>(tex, dOut, 0.004f); }, 5);
         else ms = time_ms([&] { tex_vol_kernel<<<blocks, threads>>>(tex, dOut, 0.0009f); }, 5);
         cudaDestroyTextureObject(tex);
         cudaFreeArray(arr);
@@ -183,6 +253,88 @@ extern "C" int crn_microbench(int device, int which, double *gops) {
         ms = time_ms([&] { tex_layered_kernel<<<blocks, threads>>>(tex, dOut, 0.004f); }, 5);
         cudaDestroyTextureObject(tex);
         cudaFreeArray(arr);
+    } else if (which == 7 || which == 8 || which == 13) {
+        const int n = 129, layers = 128;
+        const int bits = which == 8 ? 8 : 16;
+        cudaChannelFormatDesc cd = cudaCreateChannelDesc(bits, bits, 0, 0, which == 13 ? cudaChannelFormatKindFloat : cudaChannelFormatKindUnsigned);
+        cudaArray_t arr = nullptr;
+        cudaMalloc3DArray(&arr, &cd, make_cudaExtent(n, n, layers), cudaArrayLayered);
+        const size_t texel = bits / 4;
+        std::vector<uint8_t> h((size_t)n * n * layers * texel);
+        for (size_t i = 0; i < h.size(); i++) h[i] = which == 13 ? (uint8_t)((i & 1) ? 0x3c : (i * 2654435761u >> 24)) : (uint8_t)(i * 2654435761u >> 24);
+        cudaMemcpy3DParms cp{};
+        cp.srcPtr = make_cudaPitchedPtr(h.data(), n * texel, n, n);
+        cp.dstArray = arr; cp.extent = make_cudaExtent(n, n, layers); cp.kind = cudaMemcpyHostToDevice;
+        cudaMemcpy3D(&cp);
+        cudaResourceDesc rd{};
+        rd.resType = cudaResourceTypeArray; rd.res.array.array = arr;
+        cudaTextureDesc td{};
+        td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModeLinear; td.readMode = which == 13 ? cudaReadModeElementType : cudaReadModeNormalizedFloat; td.normalizedCoords = 1;
+        cudaTextureObject_t tex = 0;
+        cudaCreateTextureObject(&tex, &rd, &td, nullptr);
+        ms = time_ms([&] { tex_layered2_kernel<<<blocks, threads>>>(tex, dOut, 0.0009f, layers); }, 5);
+        cudaDestroyTextureObject(tex);
+        cudaFreeArray(arr);
+    } else if (which == 9) {
+        const int n = 32;
+        cudaChannelFormatDesc cd = cudaCreateChannelDesc(8, 8, 8, 8, cudaChannelFormatKindSigned);
+        cudaArray_t arr = nullptr;
+        cudaMalloc3DArray(&arr, &cd, make_cudaExtent(n, n, n), cudaArrayLayered);
+        std::vector<uint8_t> h((size_t)n * n * n * 4);
+        for (size_t i = 0; i < h.size(); i++) h[i] = (uint8_t)(i * 2654435761u >> 24);
+        cudaMemcpy3DParms cp{};
+        cp.srcPtr = make_cudaPitchedPtr(h.data(), n * 4, n, n);
+        cp.dstArray = arr; cp.extent = make_cudaExtent(n, n, n); cp.kind = cudaMemcpyHostToDevice;
+        cudaMemcpy3D(&cp);
+        cudaTextureObject_t tex = make_tex(arr, true);
+        ms = time_ms([&] { tex_layered_h2_kernel<<<blocks, threads>>>(tex, dOut, 0.004f); }, 5);
+        cudaDestroyTextureObject(tex);
+        cudaFreeArray(arr);
+    } else if (which == 10) {
+        const int n = 129;
+        cudaChannelFormatDesc cd = cudaCreateChannelDesc(16, 0, 0, 0, cudaChannelFormatKindUnsigned);
+        cudaArray_t arr = nullptr;
+        cudaMalloc3DArray(&arr, &cd, make_cudaExtent(n, n, n));
+        std::vector<uint8_t> h((size_t)n * n * n * 2);
+        for (size_t i = 0; i < h.size(); i++) h[i] = (uint8_t)(i * 2654435761u >> 24);
+        cudaMemcpy3DParms cp{};
+        cp.srcPtr = make_cudaPitchedPtr(h.data(), n * 2, n, n);
+        cp.dstArray = arr; cp.extent = make_cudaExtent(n, n, n); cp.kind = cudaMemcpyHostToDevice;
+        cudaMemcpy3D(&cp);
+        cudaTextureObject_t tex = make_tex(arr, false);
+        ms = time_ms([&] { tex_vol_kernel<<<blocks, threads>>>(tex, dOut, 0.0009f); }, 5);
+        cudaDestroyTextureObject(tex);
+        cudaFreeArray(arr);
+    } else if (which == 11 || which == 12) {
+        const int n = 256, L = 9;
+        cudaChannelFormatDesc cd = cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned);
+        cudaMipmappedArray_t marr = nullptr;
+        cudaMallocMipmappedArray(&marr, &cd, make_cudaExtent(n, n, n), L);
+        for (int l = 0; l < L; l++) {
+            const int s = n >> l;
+            cudaArray_t lvl = nullptr;
+            cudaGetMipmappedArrayLevel(&lvl, marr, l);
+            std::vector<uint8_t> h((size_t)s * s * s);
+            for (size_t i = 0; i < h.size(); i++) h[i] = (uint8_t)(i * 2654435761u >> 24);
+            cudaMemcpy3DParms cp{};
+            cp.srcPtr = make_cudaPitchedPtr(h.data(), s, s, s);
+            cp.dstArray = lvl; cp.extent = make_cudaExtent(s, s, s); cp.kind = cudaMemcpyHostToDevice;
+            cudaMemcpy3D(&cp);
+        }
+        cudaResourceDesc rd{};
+        rd.resType = cudaResourceTypeMipmappedArray; rd.res.mipmap.mipmap = marr;
+        cudaTextureDesc td{};
+        td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModeLinear; td.mipmapFilterMode = cudaFilterModeLinear;
+        td.readMode = cudaReadModeNormalizedFloat; td.normalizedCoords = 1;
+        td.minMipmapLevelClamp = 0.0f; td.maxMipmapLevelClamp = (float)(L - 1);
+        cudaTextureObject_t tex = 0;
+        cudaCreateTextureObject(&tex, &rd, &td, nullptr);
+        const float lod = which == 11 ? 4.5f : 2.5f;
+        ms = time_ms([&] { tex_lod_kernel<<<blocks, threads>>>(tex, dOut, 0.0009f, lod); }, 5);
+        cudaDestroyTextureObject(tex);
+        cudaFreeMipmappedArray(marr);
     } else if (which == 2) {
         uint32_t *tab = nullptr;
         cudaMalloc(&tab, 64 << 10);

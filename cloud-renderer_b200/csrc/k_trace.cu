@@ -27,9 +27,13 @@
 //                        (g,a) float2 copy; trilinear / mip-linear weights follow GL 4.4 §8.14 in full
 //                        float precision (134 dB against the oracle, 3x slower: issue-bound).
 // traceCone's per-step height, LOD split and weight are identical for every fragment and are
-// precomputed on the host (TraceParams::steps); consecutive steps are grouped and a group whose
-// conservative empty-space mask (k_skipmask.cu) is clear is skipped exactly.
+// precomputed on the host (TraceParams::steps).  With the texture sampler the coarse steps read
+// per-frame baked step textures (k_conebake.cu: one bilinear pass + a z blend instead of a mip-linear
+// 3D fetch, exact); the remaining fine steps are grouped, and a group whose bit in the need-code grid
+// (k_conebake.cu, from the conservative empty-space masks of k_skipmask.cu) is clear is skipped exactly.
 #include "crn_internal.cuh"
+
+#include <cstdlib>
 
 namespace crn {
 
@@ -50,35 +54,11 @@ struct TraceArgs {
     unsigned long long *stats;
     float invRange[3];            // 1 / range per axis
     float invDim;                 // 1 / voxelDim
-    const uint32_t *mask;         // empty-space masks M_l (k_skipmask.cu), or nullptr
-    const uint32_t *fill;         // set bits of M_l per level
+    const uint8_t *code;          // need-code grid (k_conebake.cu): bit g = group g may contribute from this cell; or nullptr
     const uint32_t *order;        // launch order of the tiles, longest list first (k_bin.cu)
 };
 
-// M_l at the level-l texel containing voxel-space point p: 0 => every filter footprint of the group is all-zero
-// (p = normalized texture coordinate of the lookup point)
-__device__ __forceinline__ bool group_occupied(const uint32_t *__restrict__ mask, const ConeGroup &g, float px, float py, float pz) {
-    const int ix = min(max(__float2int_rd(px * g.sizeF), 0), g.nMinus1);
-    const int iy = min(max(__float2int_rd(py * g.sizeF), 0), g.nMinus1);
-    const int iz = min(max(__float2int_rd(pz * g.sizeF), 0), g.nMinus1);
-    const uint32_t word = g.maskOff + (uint32_t)((iz * g.size + iy) * g.wpr + (ix >> 5));
-    const uint32_t w = __ldg(mask + word);
-    return (w >> (ix & 31)) & 1u;
-}
-
 __device__ __forceinline__ float saturatef(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
-
-// The same test with the index clamp folded into the arithmetic: the point is saturated to [0,1] (a free modifier on
-// the FFMA that produces it) and scaled by sizeLo = size - 2^-10 < size, so the truncated index cannot leave the
-// level.  A point within 2^-10 texel above a texel boundary may be looked up one texel low; M_l's 5x5x5 dilation
-// covers the footprints of the group from either texel, so the test stays conservative.
-__device__ __forceinline__ bool group_occupied_sat(const uint32_t *__restrict__ mask, const ConeGroup &g, float px, float py, float pz) {
-    const int ix = (int)(__saturatef(px) * g.sizeLo);
-    const int iy = (int)(__saturatef(py) * g.sizeLo);
-    const int iz = (int)(__saturatef(pz) * g.sizeLo);
-    const uint32_t word = g.maskOff + (uint32_t)((iz * g.size + iy) * g.wpr + (ix >> 5));
-    return (__ldg(mask + word) >> (ix & 31)) & 1u;
-}
 
 struct Lin {                       // one axis of a linear filter footprint
     int i0, i1;
@@ -205,7 +185,7 @@ __device__ __forceinline__ bool sun_fragment(const TraceParams &tp, const ViewPa
 }
 
 // kTex = false: explicit filtering (CRN_SAMPLER_EXPLICIT);  kTex = true: texture units (CRN_SAMPLER_TEXTURE)
-constexpr int kFastGroups = 8;        // the unrolled (fast) variant handles up to this many empty-space groups
+constexpr int kFastBaked = 8;         // the fast variant unrolls (and handles at most) this many baked steps
 // resident CTAs per SM the kernel is compiled for (register cap = 65536 / 64 / MINB).  Measured at C3 (trace ms):
 // 12: 4.82, 14: 4.73, 16: 4.39, 18: 4.36, 20: 4.52, 24: 4.60 -> 16 (64 registers, no spills in the fast variant)
 #ifndef CRN_TRACE_MINB
@@ -214,9 +194,7 @@ constexpr int kFastGroups = 8;        // the unrolled (fast) variant handles up 
 constexpr int kTraceThreads = 64;     // 2 warp patches per CTA: measured best (256: 5.87 ms, 128: 5.83, 64: 5.79 at C3)
 
 // kGate: the paper variant's `if (sampleColor.a > 0)` on a second (occupancy) chain, CRN_VOLUME_RG8 only
-// kOct4: the reference's noise configuration (numOctaves == 4, 32^3 texture) with the octave loop unrolled, so the
-//        per-octave constants become immediate operands instead of indexed constant loads
-template <bool kTex, bool kStats, bool kGate, bool kOct4>
+template <bool kTex, bool kStats, bool kGate>
 __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_kernel(const __grid_constant__ TraceArgs a, const __grid_constant__ ViewParams cam,
                                                     const __grid_constant__ TraceParams tp, const __grid_constant__ TexSet ts) {
     // a 16x16 tile is 8 warp patches; a CTA carries kTraceThreads/32 of them, so a slow patch holds up fewer warps
@@ -248,16 +226,10 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_kernel(co
 
     float C[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     float T = 1.0f;
-    unsigned long long nFrag = 0, nCone = 0, nNoise = 0, nSkip = 0, nFetch = 0;
+    unsigned long long nFrag = 0, nCone = 0, nNoise = 0, nSkip = 0, nFetch = 0, nBakedF = 0;
 
     const uint32_t cnt = tp.active ? a.tileCnt[tile] : 0;
     const uint32_t off = cnt ? a.tileOff[tile] : 0;
-    // which groups are worth an empty-space test: a mask that is (nearly) full can (almost) never clear a group, and
-    // not testing is always exact (the samples are simply fetched)
-    uint32_t testBits = 0;
-    if (a.mask && cnt)
-        for (int g = 0; g < tp.nGroups; g++)
-            if ((unsigned long long)__ldg(a.fill + tp.groups[g].level) * 8ull < (unsigned long long)tp.groups[g].total * 7ull) testBits |= 1u << g;
     const float cutoff = tp.p.transmittanceCutoff;
     const int D = a.vol.dim;
     (void)D;
@@ -314,41 +286,12 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_kernel(co
                 const float inv = 1.0f / (iSteps - 1.0f);
                 const float dxs = rx * len * inv, dys = ry * len * inv, dzs = rz * len * inv;              // localTexDelta
                 float opacity = 0.0f, light = 0.0f;
-                float adv = 0.0f;                                       // texture-space distance marched so far (fast variant)
-                const float sStep = len * inv;
                 const int nIter = shade ? (int)ceilf(iSteps) : 0;
                 const int nMax = __reduce_max_sync(0xFFFFFFFFu, nIter);
                 for (int i = 0; i < nMax; i++) {
                     if (i < nIter) {
                         float ng = 0.0f, na = 0.0f;
-                        // this step's texture / unit-sphere coordinates.  Fast variant: start + adv * viewRay with ONE running
-                        // scalar (the march follows the view ray, a kernel constant); generic: the shader's running sums
-                        float cx, cy, cz, vx, vy, vz;
-                        if constexpr (kTex && kOct4) {
-                            cx = fmaf(adv, rx, tx); cy = fmaf(adv, ry, tyy); cz = fmaf(adv, rz, tz);
-                            vx = fmaf(adv, rx, ux); vy = fmaf(adv, ry, uy); vz = fmaf(adv, rz, uz);
-                        } else {
-                            cx = tx; cy = tyy; cz = tz; vx = ux; vy = uy; vz = uz;
-                        }
-                        if constexpr (kTex && kOct4) {
-#pragma unroll
-                            for (int o = 0; o < 4; o++) {
-                                // layer = floor(z texel coordinate) on the FADD pipe: adding 1.5*2^23 rounding DOWN leaves the
-                                // floor in the low mantissa bits (two's complement, so the & also wraps negative layers)
-                                // octave 3's offset is 0 by decree (octaveOffsets[3]): its bias is a literal, not a constant load
-                                const float zc = o == 3 ? fmaf(cz, tp.octFreqZ[o], -0.5f) : fmaf(cz, tp.octFreqZ[o], tp.octBiasZ[o]);
-                                const float m = __fadd_rd(zc, 12582912.0f);
-                                const float az = __fadd_rn(zc, -__fadd_rn(m, -12582912.0f));
-                                const int layer = __float_as_int(m) & 31;
-                                float4 t;                              // tex2DLayered without the header's 16-bit layer clamp
-                                asm("tex.a2d.v4.f32.f32 {%0, %1, %2, %3}, [%4, {%5, %6, %7, %7}];"
-                                    : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
-                                    : "l"(ts.noise), "r"(layer), "f"(o == 3 ? cx * tp.octFreq[o] : fmaf(cx, tp.octFreq[o], tp.octBias[o])),
-                                      "f"(o == 3 ? cy * tp.octFreq[o] : fmaf(cy, tp.octFreq[o], tp.octBias[o])));
-                                ng = fmaf(tp.octPers[o], fmaf(az, t.z - t.x, t.x), ng);
-                                na = fmaf(tp.octPers[o], fmaf(az, t.w - t.y, t.y), na);
-                            }
-                        } else
+                        const float cx = tx, cy = tyy, cz = tz, vx = ux, vy = uy, vz = uz;
                         for (int o = 0; o < tp.p.numOctaves; o++) {     // noise3D, :103-120: texture(noiseMap, (uv + offset_o) * freq_o) * pers_o
                             const float f = tp.octFreq[o], b = tp.octBias[o];
                             float2 s;
@@ -372,11 +315,8 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_kernel(co
                         ng += vy * rsqrtf(uu);                          // noiseCell.xyz += normalize(unitTex)
                         opacity = fmaf(na, 1.0f - uu, opacity);
                         light += saturatef(ng * 0.5f + 0.5f);
-                        if constexpr (kTex && kOct4) adv += sStep;
-                        else {
-                            tx += dxs; tyy += dys; tz += dzs;
-                            ux += dxs; uy += dys; uz += dzs;            // (sic) tex-space delta on the unit-sphere coord
-                        }
+                        tx += dxs; tyy += dys; tz += dzs;
+                        ux += dxs; uy += dys; uz += dzs;            // (sic) tex-space delta on the unit-sphere coord
                         if (kStats) nNoise += tp.p.numOctaves;
                     }
                 }
@@ -397,18 +337,20 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_kernel(co
                 const float il = rsqrtf(ex * ex + ey * ey + ez * ez) * a.invDim;      // normalize(dir) / voxelDim
                 ex *= il; ey *= il; ez *= il;
                 float indirect = 0.0f;
-                // group and step loops are warp-uniform (constants come from uniform registers); lanes take part by predicate.
-                // The fast variant unrolls the group loop (at most kFastGroups groups) so the group constants are immediates.
+                // One byte decides every group of fine steps: bit g of the start cell's need code is clear when no start
+                // position inside that cell can reach a non-zero texel with group g (all-zero footprints contribute exactly 0).
+                // Start positions outside the volume have no cell: everything is fetched (CLAMP_TO_EDGE lookups).
+                uint32_t code = 0xFFFFFFFFu;
+                if (a.code && tp.nGroups > 0) {
+                    const int ix = __float2int_rd(nx * tp.codeDimF), iy = __float2int_rd(ny * tp.codeDimF), iz = __float2int_rd(nz * tp.codeDimF);
+                    const uint32_t G = (uint32_t)tp.codeDim;
+                    if (shade && (uint32_t)ix < G && (uint32_t)iy < G && (uint32_t)iz < G)
+                        code = __ldg(a.code + ((uint32_t)iz * G + (uint32_t)iy) * G + (uint32_t)ix) | ~((1u << kCodeGroups) - 1u);
+                }
+                // group and step loops are warp-uniform (constants come from uniform registers); lanes take part by predicate
                 auto coneGroup = [&](const int g) {
                     const ConeGroup &gr = tp.groups[g];
-                    bool need = shade;
-                    // one conservative lookup decides the whole group: all-zero footprints contribute exactly 0
-                    if (((testBits >> g) & 1u) && need) {
-                        if constexpr (kOct4)
-                            need = group_occupied_sat(a.mask, gr, fmaf(gr.height, ex, nx), fmaf(gr.height, ey, ny), fmaf(gr.height, ez, nz));
-                        else
-                            need = group_occupied(a.mask, gr, fmaf(gr.height, ex, nx), fmaf(gr.height, ey, ny), fmaf(gr.height, ez, nz));
-                    }
+                    const bool need = shade && ((code >> (g < 31 ? g : 31)) & 1u);
                     if (kStats && shade && !need) nSkip += gr.count;
                     if (!__any_sync(0xFFFFFFFFu, need)) return;
 #pragma unroll 2
@@ -441,12 +383,25 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_kernel(co
                         }
                     }
                 };
-                if constexpr (kOct4) {
-#pragma unroll
-                    for (int g = 0; g < kFastGroups; g++)
-                        if (g < tp.nGroups) coneGroup(g);
-                } else {
-                    for (int g = 0; g < tp.nGroups; g++) coneGroup(g);
+                for (int g = 0; g < tp.nGroups; g++) coneGroup(g);
+                // baked steps: the mip-linear lookup of this step, pre-blended on a lattice that holds the texel centres of
+                // both levels (exact), as slice pairs: one bilinear pass returns the node planes floor(z) and floor(z)+1
+                if constexpr (kTex && !kGate) {
+                    auto bakedStep = [&](const int b) {
+                        const BakedStep &bs = tp.baked[b];
+                        const float sx = fmaf(bs.height, ex, nx), sy = fmaf(bs.height, ey, ny);
+                        const float zl = __saturatef(fmaf(bs.height, ez, nz)) * bs.zScale;      // [0, n-1)
+                        const float m = __fadd_rd(zl, 12582912.0f);                             // floor in the low mantissa bits
+                        const float az = __fadd_rn(zl, -__fadd_rn(m, -12582912.0f));
+                        const int layer = __float_as_int(m) & 0xFF;
+                        float4 t;
+                        asm("tex.a2d.v4.f32.f32 {%0, %1, %2, %3}, [%4, {%5, %6, %7, %7}];"
+                            : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                            : "l"(bs.tex), "r"(layer), "f"(fmaf(sx, bs.A, bs.B)), "f"(fmaf(sy, bs.A, bs.B)));
+                        if (shade) indirect = fmaf(fmaf(az, t.y - t.x, t.x), bs.weight, indirect);
+                        if (kStats && shade) nBakedF++;
+                    };
+                    for (int b = 0; b < tp.nBaked; b++) bakedStep(b);
                 }
                 if (kStats && shade) nCone += tp.nSteps;
                 if (tp.p.doNoiseSample) { col[0] *= indirect; col[1] *= indirect; col[2] *= indirect; }
@@ -490,6 +445,7 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_kernel(co
             nNoise += __shfl_down_sync(0xFFFFFFFFu, nNoise, s);
             nSkip += __shfl_down_sync(0xFFFFFFFFu, nSkip, s);
             nFetch += __shfl_down_sync(0xFFFFFFFFu, nFetch, s);
+            nBakedF += __shfl_down_sync(0xFFFFFFFFu, nBakedF, s);
         }
         if (lane == 0) {
             if (nFrag) atomicAdd(&a.stats[0], nFrag);
@@ -497,6 +453,201 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_kernel(co
             if (nNoise) atomicAdd(&a.stats[2], nNoise);
             if (nSkip) atomicAdd(&a.stats[3], nSkip);
             if (nFetch) atomicAdd(&a.stats[4], nFetch);
+            if (nBakedF) atomicAdd(&a.stats[5], nBakedF);
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// The fast variant: the reference's own configuration (src/Shaders/ConeTraceShader.hpp:15-36 defaults in kind, any
+// values) — texture sampler, noise on with 4 octaves on a 32^3 texture, cone trace on, showQuad off, perspective
+// camera, R8/R32F volume — with everything that does not depend on the fragment folded into constants, the octave /
+// group / baked-step loops unrolled, and the per-fragment state arranged so that nothing is recomputed inside the
+// noise march (the generic kernel above re-materialises a dozen values per step under its 64-register cap):
+//   * colour is grey in every mode of conetrace_frag.glsl, so ONE colour accumulator + alpha;
+//   * the noise march runs along the view ray, a kernel constant perpendicular to the billboard plane:
+//     texture coordinate = QA + s1 * ray, |unitTex|^2 = |o|^2 / r^2 + s2^2 with two running scalars;
+//   * background (clear colour + sun disc) is evaluated after the list walk, not carried through it.
+// Same fragments, same lookups, same order of composition as the generic kernel.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fma_sat(float a, float b, float c) {
+    float d;
+    asm("fma.rn.sat.ftz.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// bilinear fetch of texel pair planes from a layered texture (explicit level 0: no LOD operand in SASS)
+__device__ __forceinline__ float4 tex_layer4(unsigned long long tex, int layer, float u, float v) {
+    float4 t;
+    asm("tex.level.a2d.v4.f32.f32 {%0, %1, %2, %3}, [%4, {%5, %6, %7, %7}], 0f00000000;"
+        : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "l"(tex), "r"(layer), "f"(u), "f"(v));
+    return t;
+}
+
+template <int NB>                      // number of baked cone steps (compile-time: no predication of the unused slots)
+__global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_fast_kernel(const __grid_constant__ TraceArgs a, const __grid_constant__ ViewParams cam,
+                                                    const __grid_constant__ TraceParams tp, const __grid_constant__ TexSet ts) {
+    constexpr int kWarps = kTraceThreads / 32, kSplit = 8 / kWarps;
+    const int tile = (int)a.order[blockIdx.x / kSplit];
+    const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) + (blockIdx.x % kSplit) * kWarps;
+    const int tx = tile % a.tilesX, ty = tile / a.tilesX;
+    const int px = tx * kTile + (warp & 1) * 8 + (lane & 7);
+    const int py = ty * kTile + (warp >> 1) * 4 + (lane >> 3);
+    if (tp.ilvCount > 1 && (ty % tp.ilvCount) != tp.ilvIndex) return;
+    const bool valid = px < cam.W && py < cam.H && py >= tp.row0 && py < tp.row1;
+    if (__all_sync(0xFFFFFFFFu, !valid)) return;
+
+    const float ndcx = ((float)px + 0.5f) / (float)cam.W * 2.0f - 1.0f;
+    const float ndcy = ((float)py + 0.5f) / (float)cam.H * 2.0f - 1.0f;
+    const float xs = ndcx * tp.f.invP0, ys = ndcy * tp.f.invP5;        // view-space x, y of the pixel ray at unit depth
+
+    float Cg = 0.0f, Ca = 0.0f, T = 1.0f;
+    const uint32_t cnt = a.tileCnt[tile];
+    const uint32_t *list = a.tileList + (cnt ? a.tileOff[tile] : 0);
+    const float cutoff = tp.p.transmittanceCutoff;
+    const float rx = cam.nrm[0], ry = cam.nrm[1], rz = cam.nrm[2];     // viewRay (res/conetrace_frag.glsl:138)
+
+    for (uint32_t e = 0; e < cnt; e++) {
+        const bool live = valid && T > cutoff;
+        if (__all_sync(0xFFFFFFFFu, !live)) break;                      // early ray termination, whole patch
+        const uint32_t k = __ldg(list + e);
+        const float4 r0 = __ldg(reinterpret_cast<const float4 *>(&a.recs[k].cx));
+        const float4 r1 = __ldg(reinterpret_cast<const float4 *>(&a.recs[k].xv));
+        const float radius = r0.w;
+        const float u = fmaf(xs, -r1.z, -r1.x), v = fmaf(ys, -r1.z, -r1.y);
+        const float d2 = fmaf(u, u, v * v), r2 = radius * radius;
+        const float h2 = r2 - d2;
+        // both discards (4 h^2 < 0.01 and h^2 < 1e-4 r^2) and the quad test (implied by h^2 > 0) in one compare
+        const bool shade = live && h2 >= fmaxf(1.0e-4f * r2, 0.0025f);
+        if (!__any_sync(0xFFFFFFFFu, shade)) continue;
+
+        const float h = sqrtf(fmaxf(h2, 0.0f));
+        const float invr = 1.0f / radius;
+        const float ox = fmaf(u, cam.right[0], v * cam.up[0]);
+        const float oy = fmaf(u, cam.right[1], v * cam.up[1]);
+        const float oz = fmaf(u, cam.right[2], v * cam.up[2]);
+        // point of the billboard plane under this pixel
+        const float qx = r0.x + ox, qy = r0.y + oy, qz = r0.z + oz;
+
+        // ---- noise march (res/conetrace_frag.glsl:137-174)
+        const float invAdjust = tp.f.invAdjust;
+        const float len = 2.0f * h * invAdjust;
+        const float iSteps = fminf(len * tp.f.invStep, tp.f.span) + tp.f.minSteps;
+        const float inv = 1.0f / (iSteps - 1.0f);
+        const float sStep = len * inv;
+        const int nIter = shade ? (int)ceilf(iSteps) : 0;
+        const int nMax = __reduce_max_sync(0xFFFFFFFFu, nIter);
+        const float qax = qx * invAdjust, qay = qy * invAdjust, qaz = qz * invAdjust;
+        const float uu0 = d2 * invr * invr, vy0 = oy * invr;
+        float s1 = -h * invAdjust;                                      // texture-space distance from the plane point
+        float s2 = -h * invr;                                           // unit-sphere distance from the plane (sic: advanced by the texture-space step)
+        float opacity = 0.0f, light = 0.0f;
+        for (int i = 0; i < nMax; i++) {
+            if (i < nIter) {
+                const float cx = fmaf(s1, rx, qax), cy = fmaf(s1, ry, qay), cz = fmaf(s1, rz, qaz);
+                float ng = 0.0f, na = 0.0f;
+#pragma unroll
+                for (int o = 0; o < 4; o++) {
+                    // layer = floor(z texel coordinate) on the FADD pipe: adding 1.5*2^23 rounding DOWN leaves the floor in
+                    // the low mantissa bits (two's complement, so the & also wraps negative layers); octave 3's offset is 0
+                    // by decree (octaveOffsets[3]): literal bias.  Octave 0 has frequency and persistence 1 (noise3D starts there).
+                    const float zc = o == 3 ? fmaf(cz, tp.octFreqZ[o], -0.5f) : fmaf(cz, tp.octFreqZ[o], tp.octBiasZ[o]);
+                    const float m = __fadd_rd(zc, 12582912.0f);
+                    const float az = __fadd_rn(zc, -__fadd_rn(m, -12582912.0f));
+                    const int layer = __float_as_int(m) & 31;
+                    const float tu = o == 0 ? cx + tp.octBias[0] : o == 3 ? cx * tp.octFreq[o] : fmaf(cx, tp.octFreq[o], tp.octBias[o]);
+                    const float tv = o == 0 ? cy + tp.octBias[0] : o == 3 ? cy * tp.octFreq[o] : fmaf(cy, tp.octFreq[o], tp.octBias[o]);
+                    const float4 t = tex_layer4(ts.noise, layer, tu, tv);
+                    const float sg = fmaf(az, t.z - t.x, t.x), sa = fmaf(az, t.w - t.y, t.y);
+                    if (o == 0) { ng = sg; na = sa; }
+                    else { ng = fmaf(tp.octPers[o], sg, ng); na = fmaf(tp.octPers[o], sa, na); }
+                }
+                const float uu = fmaf(s2, s2, uu0);                     // |unitTex|^2: the plane offset is perpendicular to the ray
+                ng = fmaf(fmaf(s2, ry, vy0), rsqrtf(uu), ng);           // noiseCell.xyz += normalize(unitTex)
+                opacity = fmaf(fabsf(na), 1.0f - uu, opacity);
+                light += fma_sat(ng, 0.5f, 0.5f);
+                s1 += sStep; s2 += sStep;
+            }
+        }
+        const float grey = fmaf(tp.p.noiseColorScale * light, inv, tp.p.minNoiseColor);
+        const float alpha = __saturatef(opacity * tp.p.noiseOpacity * inv) * (1.0f - sqrtf(d2) * invr);
+
+        // ---- cone trace towards the sun (res/conetrace_frag.glsl:176-200, traceCone :64-79)
+        const float wx3 = fmaf(rx, h, qx), wy3 = fmaf(ry, h, qy), wz3 = fmaf(rz, h, qz);   // camera-facing sphere surface
+        const float nx = fmaf(wx3, tp.f.nScale[0], tp.f.nBias[0]);
+        const float ny = fmaf(wy3, tp.f.nScale[1], tp.f.nBias[1]);
+        const float nz = fmaf(wz3, tp.f.nScale[2], tp.f.nBias[2]);
+        float ex = tp.lightPos[0] - wx3, ey = tp.lightPos[1] - wy3, ez = tp.lightPos[2] - wz3;
+        const float il = rsqrtf(fmaf(ex, ex, fmaf(ey, ey, ez * ez))) * tp.f.invDim;        // normalize(dir) / voxelDim
+        ex *= il; ey *= il; ez *= il;
+        float indirect = 0.0f;
+        if (tp.nGroups > 0) {
+            // bit g of the start cell's need code: can group g reach a non-zero texel from a start position in this cell?
+            // Groups beyond kCodeGroups have no bit and start positions outside the volume no cell: always fetched.
+            uint32_t code = 0xFFFFFFFFu;
+            if (a.code) {
+                const int ix = __float2int_rd(nx * tp.codeDimF), iy = __float2int_rd(ny * tp.codeDimF), iz = __float2int_rd(nz * tp.codeDimF);
+                const uint32_t G = (uint32_t)tp.codeDim;
+                if (shade && (uint32_t)ix < G && (uint32_t)iy < G && (uint32_t)iz < G)
+                    code = __ldg(a.code + ((uint32_t)iz * G + (uint32_t)iy) * G + (uint32_t)ix) | ~((1u << kCodeGroups) - 1u);
+            }
+            code = shade ? code & (tp.nGroups >= 32 ? 0xFFFFFFFFu : (1u << tp.nGroups) - 1u) : 0u;
+            if (__any_sync(0xFFFFFFFFu, code != 0)) {                   // most patches need no fine step at all
+                for (int g = 0; g < tp.nGroups; g++) {
+                    const ConeGroup &gr = tp.groups[g];
+                    const bool need = (code >> (g < 31 ? g : 31)) & 1u;
+                    if (!__any_sync(0xFFFFFFFFu, need)) continue;
+                    for (int i = gr.first; i < gr.first + gr.count; i++) {
+                        const ConeStep &st = tp.steps[i];
+                        if (need) {
+                            const float s = tex3DLod<float>(ts.vol, fmaf(st.height, ex, nx), fmaf(st.height, ey, ny), fmaf(st.height, ez, nz), st.lod);
+                            indirect = fmaf(s, st.weight, indirect);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            const BakedStep &bs = tp.baked[b];
+            const float zl = fma_sat(bs.height, ez, nz) * bs.zScale;                        // [0, n-1)
+            const float m = __fadd_rd(zl, 12582912.0f);                                     // floor in the low mantissa bits
+            const float az = __fadd_rn(zl, -__fadd_rn(m, -12582912.0f));
+            const float4 t = tex_layer4(bs.tex, __float_as_int(m) & 0xFF, fmaf(bs.hA, ex, fmaf(nx, bs.A, bs.B)), fmaf(bs.hA, ey, fmaf(ny, bs.A, bs.B)));
+            indirect = fmaf(fmaf(az, t.y - t.x, t.x), bs.weight, indirect);
+        }
+
+        if (shade) {                                                    // blend, front to back
+            const float w = T * alpha;                                  // alpha is already in [0,1]
+            Cg = fmaf(w, __saturatef(grey * indirect), Cg);
+            Ca = fmaf(w, alpha, Ca);
+            T *= (1.0f - alpha);
+        }
+    }
+
+    if (valid) {
+        // background = clear colour, then the sun pass blended over it
+        float bg[4] = {tp.bg[0], tp.bg[1], tp.bg[2], tp.bg[3]};
+        if (tp.p.drawSun) {
+            float sc[4];
+            if (sun_fragment(tp, cam, ndcx, ndcy, px, py, sc)) {
+                const float sa = saturatef(sc[3]);
+#pragma unroll
+                for (int k = 0; k < 4; k++) bg[k] = saturatef(sc[k]) * sa + bg[k] * (1.0f - sa);
+            }
+        }
+        const float o0 = fmaf(T, bg[0], Cg), o1 = fmaf(T, bg[1], Cg), o2 = fmaf(T, bg[2], Cg), o3 = fmaf(T, bg[3], Ca);
+        const size_t p = (size_t)py * cam.W + px;
+        if (a.format == CRN_IMAGE_RGBA32F) {
+            reinterpret_cast<float4 *>(a.image)[p] = make_float4(o0, o1, o2, o3);
+        } else {
+            uchar4 q;
+            q.x = (unsigned char)floorf(saturatef(o0) * 255.0f + 0.5f);
+            q.y = (unsigned char)floorf(saturatef(o1) * 255.0f + 0.5f);
+            q.z = (unsigned char)floorf(saturatef(o2) * 255.0f + 0.5f);
+            q.w = (unsigned char)floorf(saturatef(o3) * 255.0f + 0.5f);
+            reinterpret_cast<uchar4 *>(a.image)[p] = q;
         }
     }
 }
@@ -505,7 +656,7 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_kernel(co
 
 int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol, const TraceParams &tp,
                  const BoardRec *recs, const Bins &b, const uint32_t *bits, const uint8_t *chain,
-                 const uint32_t *bitsA, const uint8_t *chainA, const int8_t *noise, const TexSet *ts, const uint32_t *skipMask, const uint32_t *maskFill, const uint32_t *tileOrder, void *image,
+                 const uint32_t *bitsA, const uint8_t *chainA, const int8_t *noise, const TexSet *ts, const uint8_t *needCode, const uint32_t *tileOrder, void *image,
                  int format, unsigned long long *stats) {
     TraceArgs a;
     a.vol = vol;
@@ -515,8 +666,7 @@ int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol
     a.bits = bits; a.chain = chain; a.bitsA = bitsA; a.chainA = chainA;
     a.noise = reinterpret_cast<const float2 *>(noise);
     a.image = image; a.format = format; a.stats = stats;
-    a.mask = (skipMask && tp.p.skipEmptySpace) ? skipMask : nullptr;
-    a.fill = maskFill;
+    a.code = (needCode && tp.p.skipEmptySpace && tp.codeDim > 0) ? needCode : nullptr;
     a.order = tileOrder;
     a.invRange[0] = 1.0f / (vol.xB[1] - vol.xB[0]);
     a.invRange[1] = 1.0f / (vol.yB[1] - vol.yB[0]);
@@ -526,19 +676,26 @@ int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol
     const bool useTex = ts && ts->enabled && tp.p.sampler == CRN_SAMPLER_TEXTURE;
     const int grid = b.tilesX * b.tilesY * (256 / kTraceThreads);
     const bool gate = bitsA != nullptr;
-    // the reference's configuration (4 octaves, 32^3 noise) with the octave and group loops unrolled
-    const bool oct4 = tp.p.numOctaves == 4 && tp.noiseDim == 32 && tp.nGroups <= kFastGroups;
+    // the reference's configuration: see trace_fast_kernel
+    const bool fast = useTex && !gate && !tp.stats && tp.active && tp.p.numOctaves == 4 && tp.noiseDim == 32 && tp.p.doNoiseSample &&
+                      tp.p.doConeTrace && !tp.p.showQuad && !cam.ortho && tp.nBaked <= kFastBaked && vol.texelBytes <= 4 && !getenv("CRN_NO_FAST");
     if (gate) {                                                   // opt-in paper variant: stats variant only when asked
-        if (useTex && tp.stats) trace_kernel<true, true, true, false><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, *ts);
-        else if (useTex) trace_kernel<true, false, true, false><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, *ts);
-        else if (tp.stats) trace_kernel<false, true, true, false><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, none);
-        else trace_kernel<false, false, true, false><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, none);
+        if (useTex && tp.stats) trace_kernel<true, true, true><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, *ts);
+        else if (useTex) trace_kernel<true, false, true><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, *ts);
+        else if (tp.stats) trace_kernel<false, true, true><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, none);
+        else trace_kernel<false, false, true><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, none);
     }
-    else if (useTex && tp.stats) trace_kernel<true, true, false, false><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, *ts);
-    else if (useTex && oct4) trace_kernel<true, false, false, true><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, *ts);
-    else if (useTex) trace_kernel<true, false, false, false><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, *ts);
-    else if (tp.stats) trace_kernel<false, true, false, false><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, none);
-    else trace_kernel<false, false, false, false><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, none);
+    else if (fast) {
+        switch (tp.nBaked) {
+#define CRN_FAST(NB) case NB: trace_fast_kernel<NB><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, *ts); break;
+            CRN_FAST(0) CRN_FAST(1) CRN_FAST(2) CRN_FAST(3) CRN_FAST(4) CRN_FAST(5) CRN_FAST(6) CRN_FAST(7) CRN_FAST(8)
+#undef CRN_FAST
+        }
+    }
+    else if (useTex && tp.stats) trace_kernel<true, true, false><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, *ts);
+    else if (useTex) trace_kernel<true, false, false><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, *ts);
+    else if (tp.stats) trace_kernel<false, true, false><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, none);
+    else trace_kernel<false, false, false><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, none);
     return 1;
 }
 

@@ -145,7 +145,8 @@ typedef struct crn_trace_stats {
     uint64_t noiseSamples;     /* texture(noiseMap) taps taken by noise3D               */
     uint64_t binEntries;       /* (tile, billboard) pairs in the camera-space bins      */
     uint64_t coneSamplesSkipped; /* of coneSamples: proven zero by the empty-space masks, not fetched */
-    uint64_t filteredFetches;  /* filtered lookups actually issued: noise taps (bilinear, slice pairs) + 1 or 2 trilinear per fetched cone sample */
+    uint64_t filteredFetches;  /* filtered lookups actually issued: noise taps (bilinear, slice pairs) + 1 or 2 trilinear per fetched textureLod cone sample + bakedFetches */
+    uint64_t bakedFetches;     /* of filteredFetches: cone samples served by a baked step texture (one bilinear pass each) */
 } crn_trace_stats;
 
 /* Stage timings of the most recent frame, milliseconds, measured with CUDA events on
@@ -300,7 +301,9 @@ int crn_get_launch_count(crn_ctx *ctx, uint64_t *count);
 /* Measures one hardware ceiling with a resident synthetic kernel; result in giga lane-operations
  * per second.  which: 0 tex3D trilinear RGBA8 32^3, 1 tex3D trilinear R8 256^3, 2 LDG.32 L1-hit,
  * 3 global atomicOr (RED) on a 2 MB set, 4 shared-memory atomicOr, 5 FFMA issue,
- * 6 tex2DLayered bilinear RGBA8 32x32x32 (the noise texture's layout). */
+ * 6 tex2DLayered bilinear RGBA8 32x32x32 (the noise texture's layout), 7 tex2DLayered bilinear RG16 (baked cone
+ * steps), 8 the same RG8, 9 RGBA8 with f16x2 return, 10 tex3D trilinear R16, 11/12 tex3DLod on a mipmapped R8 256^3
+ * at LOD 4.5 / 2.5 (mip-linear: four bilinear passes), 13 tex2DLayered bilinear RG16F. */
 int crn_microbench(int device, int32_t which, double *giga_ops_per_s);
 
 /* library identification: "cloud-renderer_b200 <version> sm_100a" */

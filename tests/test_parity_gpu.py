@@ -301,11 +301,14 @@ def test_tile_row_interleave_is_result_invariant(pkg, scenes, orc, renderer):
     r2.close()
 
 
-@pytest.mark.parametrize("name", ["small", "C1"])
+@pytest.mark.parametrize("name", ["small", "C1", "C2crop"])
 def test_empty_space_skipping_is_exact(name, pkg, scenes, orc, renderer):
-    """cone samples proven all-zero by the dilated occupancy masks contribute exactly 0: the image with
-    skipping on is bit-identical to the image with every sample fetched, for both samplers"""
-    s = steady_state(scenes.make_scene(name), orc)
+    """cone samples proven all-zero by the dilated occupancy masks (through the need-code grid) contribute exactly 0: the
+    image with skipping on is bit-identical to the image with every sample fetched, for both samplers.  With the texture
+    sampler the coarse steps are baked (never skipped); at 32^3 / 64^3 that is every step, at 128^3 the level-0 steps
+    remain textureLod fetches and are skipped."""
+    s = scenes.make_scene("C2", boards=600, size=(640, 360)) if name == "C2crop" else scenes.make_scene(name)
+    s = steady_state(s, orc)
     renderer.set_scene(s)
     renderer.voxelize()
     renderer.set_stats(True)
@@ -319,7 +322,10 @@ def test_empty_space_skipping_is_exact(name, pkg, scenes, orc, renderer):
             st = renderer.trace_stats()
             skipped.append(st.coneSamplesSkipped)
             assert st.coneSamples == st.fragments * s.tp.vctSteps
-        assert skipped[0] == 0 and skipped[1] > 0
+        assert skipped[0] == 0
+        assert skipped[1] > 0 or (sampler == pkg.SAMPLER_TEXTURE and st.bakedFetches == st.coneSamples), "nothing skipped although fine steps exist"
+        if name == "C2crop" and sampler == pkg.SAMPLER_TEXTURE:
+            assert 0 < st.bakedFetches < st.coneSamples and skipped[1] > 0
         assert np.array_equal(imgs[0].view(np.uint32), imgs[1].view(np.uint32)), f"sampler {sampler}: skipping changed the image"
         print(f"{name}/sampler{sampler}: {skipped[1]} of {st.coneSamples} cone samples skipped ({100.0 * skipped[1] / st.coneSamples:.1f} %)")
     renderer.set_stats(False)
@@ -763,3 +769,43 @@ def test_noise_sizes_and_cone_settings_off_the_fast_path(dim, octaves, steps, an
         assert p >= bar
         assert np.array_equal(imgs[0].view(np.uint32), imgs[1].view(np.uint32)), "empty-space skipping changed the image"
     r.close()
+
+
+@pytest.mark.parametrize("name", ["small", "C1", "C2crop"])
+def test_fast_generic_baked_and_textureLod_paths_agree(name, pkg, scenes, orc):
+    """Three routes to the same image with the texture sampler: the fast kernel, the generic kernel (CRN_NO_FAST) and the
+    generic kernel with every cone step fetched by textureLod instead of the baked step textures (CRN_NO_BAKE).  Fast and
+    generic issue the same lookups (differences: float re-association only); baked and textureLod differ by the texture
+    unit's filter precision (the baked lattice is finer than the level it replaces).  All three >= 45 dB vs the oracle."""
+    import os
+    s = scenes.make_scene("C2", boards=600, size=(640, 360)) if name == "C2crop" else scenes.make_scene(name)
+    s = steady_state(s, orc)
+    s.tp.sampler = pkg.SAMPLER_TEXTURE
+    _, _, l0 = orc.voxelize(s, want_posmap=False)
+    ref, _, _ = orc.cone_trace(s, orc.mips(l0, s.vol.levels))
+    imgs = {}
+    try:
+        r = pkg.Renderer(0)
+        r.set_scene(s); r.voxelize()
+        imgs["fast"] = r.cone_trace(fmt=pkg.IMAGE_RGBA32F).copy()
+        os.environ["CRN_NO_FAST"] = "1"
+        imgs["generic"] = r.cone_trace(fmt=pkg.IMAGE_RGBA32F).copy()
+        r.close()
+        os.environ["CRN_NO_BAKE"] = "1"
+        r = pkg.Renderer(0)
+        r.set_scene(s); r.voxelize()
+        imgs["textureLod"] = r.cone_trace(fmt=pkg.IMAGE_RGBA32F).copy()
+        r.set_stats(True)
+        r.cone_trace(fmt=pkg.IMAGE_RGBA32F)
+        assert r.trace_stats().bakedFetches == 0
+        r.close()
+    finally:
+        os.environ.pop("CRN_NO_FAST", None)
+        os.environ.pop("CRN_NO_BAKE", None)
+    for k, im in imgs.items():
+        p = psnr(im, ref)
+        print(f"{name}/{k}: PSNR {p:.2f} dB vs oracle, max err {np.abs(im - ref).max():.3e}")
+        assert p >= 45.0
+    pf, pb = psnr(imgs["fast"], imgs["generic"]), psnr(imgs["generic"], imgs["textureLod"])
+    print(f"{name}: fast vs generic {pf:.1f} dB, baked vs textureLod {pb:.1f} dB")
+    assert pf >= 99.0 and pb >= 60.0
