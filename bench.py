@@ -1,18 +1,22 @@
 #!/usr/bin/env python
 """bench.py — frames/s of the per-frame volumetric pipeline (voxelize + mip chain + cone trace).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C3|C2|C1|C4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C3|C1|C2|C4|C5]
 
-One step = one full frame of BASELINE.json's headline configuration (C3: 256^3 animated
-volume, 20k billboards, 3840x2160, sun shadow cones): new billboard positions -> voxelize
-(pass 1 + pass 2) -> mip chain -> camera sort/bin -> cone trace -> RGBA8 image.
-With N > 1 the frames (views of the C5 orbit / time steps) are sharded round-robin over ranks,
-volume replicated, no data-path collective: weak scaling.
+One step = one full frame of BASELINE.json's headline configuration (C3: 256^3 animated volume, 20k billboards,
+3840x2160, sun shadow cones): new billboard positions -> voxelize (pass 1 + pass 2) -> mip chain -> camera sort/bin
+-> cone acceleration data -> cone trace -> RGBA8 image.  The SAME workload at every N: with N > 1 the animation's
+time steps are dealt round-robin over the ranks (rank r renders frames r, r+N, ...), volume replicated, no data-path
+collective: weak scaling.
 
-value  : whole-job frames/s with the step's inputs already in HBM and the image left in HBM.
-e2e    : the same through the C-ABI with HOST buffers (pinned billboards in, RGBA8 image out).
---impl reference : the CPU oracle (restated reference, all host threads) on a bounded sample
-                   of the same frame.  Not llvmpipe: see BASELINE.md §2.
+value  : whole-job frames/s, inputs already in HBM, image left in HBM; K frames enqueued back to back (the library
+         overlaps frame k+1's light side with frame k's trace), ONE event pair, L2 flushes included.
+e2e    : the same through the C-ABI with HOST buffers (pinned billboards in, RGBA8 image out, pipelined read-back).
+stages : per-stage CUDA-event times from a separate, serialised pass (a sync after every frame).
+extra  : the other BASELINE.json configs in the same run (C1, C2, C4, C5 orbit; at N > 1: C5 view-sharded and C4
+         with the Z-slab exchange vs. replicated voxelize), a few frames each.
+--impl reference : the CPU oracle (restated reference, all host threads) on a bounded sample of the same frame.
+                   It does not load the product library.  Not llvmpipe: see BASELINE.md §2.
 """
 import argparse
 import json
@@ -50,7 +54,9 @@ def parse():
     ap.add_argument("--radius-mode", default="auto", choices=["auto", "fill", "reference"],
                     help="billboard radii for N > 200: 'fill' keeps the cloud's fill (headline), 'reference' keeps U[1,2.5] (SURVEY 8d)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="only the headline config (no extra.C1/C2/C4/C5)")
     ap.add_argument("--no-flush", action="store_true", help="back-to-back steps (no L2 flush between them)")
+    ap.add_argument("--save", default=None, help="also write the JSON line to this file (profiles/bench_r02_*.json)")
     return ap.parse_args()
 
 
@@ -113,8 +119,9 @@ def metric_name(config):
 
 def workload_name(sc, config, radius_mode):
     D, L, N, W, H = sc.CONFIGS[config]
-    return (f"{config}: {D}^3 R8 volume ({L} levels), {N} billboards ({radius_mode} radii), {W}x{H}, "
-            f"animated (one new frame per step), sun shadow cones 16 steps, noise 4 octaves")
+    view = "64-view camera/sun orbit, one view per step" if config == "C5" else "static camera, animated billboards (one new time step per step)"
+    return (f"{config}: {D}^3 R8 volume ({L} levels), {N} billboards ({radius_mode} radii), {W}x{H}, {view}, "
+            f"sun shadow cones 16 steps, noise 4 octaves")
 
 
 def ncu_traffic(name):
@@ -130,24 +137,24 @@ def ncu_traffic(name):
         return None
 
 
-def frame_inputs(sc, config, n_frames, rank, world, radius_mode="auto"):
-    """billboard offsets for the frames this rank renders + the camera/sun of each"""
-    base = sc.make_scene(config, cutoff=0.0, radius_mode=radius_mode)
+def make_frames(sc, config, n_frames, rank, world, radius_mode="auto", host=None):
+    """the scenes this rank renders: global frame g = k * world + rank (round-robin).  C5 walks the 64-view orbit
+    (camera + sun move), every other config keeps the camera and animates the billboards."""
+    kw = dict(radius_mode=radius_mode)
+    if host is not None:
+        kw["host"] = host
     frames = []
     for k in range(n_frames):
-        g = k * world + rank                          # global frame id, round-robin over ranks
-        if world > 1:
-            s = sc.make_scene(config, frame=g, view=g % 64, radius_mode=radius_mode)
-        else:
-            s = sc.make_scene(config, frame=g, radius_mode=radius_mode)
-        frames.append(s)
-    return base, frames
+        g = k * world + rank
+        frames.append(sc.make_scene(config, frame=g, view=(g % 64) if config == "C5" else None, **kw))
+    return frames
 
 
-def cpu_baseline(config, orc, sc, budget_rows=64):
+def cpu_baseline(config, orc, sc, budget_rows=64, host=None):
     """The oracle on a bounded sample of one frame: voxelize + mips in full, the trace on every
     `stride`-th image row (an unbiased sample of the frame), extrapolated to the frame."""
-    s = sc.make_scene(config, frame=1)
+    kw = {} if host is None else {"host": host}
+    s = sc.make_scene(config, frame=1, view=1 if config == "C5" else None, **kw)
     orc.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     t0 = time.perf_counter()
     _, _, l0 = orc.voxelize(s, want_posmap=False)
@@ -183,29 +190,195 @@ def run_reference(args):
         return
     orc = entry.import_oracle()
     orc.build()
-    entry.import_package()
+    entry.import_package()                      # ctypes struct mirrors + fixtures only: the product .so is never dlopen'ed here
     from cloud_renderer_b200 import scene as sc
+    host = sc.OracleHost(orc)                   # camera matrices, noise texture and defaults from the oracle's own host math
     vals = []
     cb = None
     for i in range(args.warmup + args.steps):
-        cb = cpu_baseline(args.config, orc, sc, budget_rows=32)
+        cb = cpu_baseline(args.config, orc, sc, budget_rows=32, host=host)
         if i >= args.warmup:
             vals.append(cb["value"])
-        if i == 0 and 1.0 / cb["value"] > 60:        # keep the whole run within minutes
-            pass
     v = float(np.mean(vals))
     cb["value"] = v
-    D, L, N, W, H = sc.CONFIGS[args.config]
+    import cloud_renderer_b200 as pkg
+    assert pkg._lib is None, "the reference arm must not load the product library"
     print(json.dumps({
         "impl": "reference", "metric": metric_name(args.config), "value": v, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(sc, args.config, sc.make_scene(args.config).meta["radius_mode"]),
+        "config": {"workload": workload_name(sc, args.config, sc.make_scene(args.config, host=host).meta["radius_mode"]),
                    "implementation": "CPU oracle: the reference's algorithm restated in C++/OpenMP (oracle/oracle.cpp), all host threads; "
                                      "the reference's GL 4.4 executable cannot be built or run here (BASELINE.md 2), not llvmpipe"},
         "cpu_baseline": cb,
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+class Runner:
+    """one config on this rank: resident + pinned inputs, the three timed legs"""
+
+    def __init__(self, ctx, config, K, Wm, args, mode="frames"):
+        self.ctx, self.config, self.K, self.Wm, self.args, self.mode = ctx, config, K, Wm, args, mode
+        torch, pkg, sc = ctx["torch"], ctx["pkg"], ctx["sc"]
+        world, rank, dev = ctx["world"], ctx["rank"], ctx["dev"]
+        self.D, self.L, self.N, self.Wd, self.Ht = sc.CONFIGS[config]
+        shared = mode in ("slab", "replicate")              # C4 at N>1: every rank works on the SAME frame
+        self.frames = make_frames(sc, config, K + Wm, 0 if shared else rank, 1 if shared else world, args.radius_mode)
+        for f in self.frames:
+            f.tp.transmittanceCutoff = args.cutoff
+            f.tp.sampler = pkg.SAMPLER_TEXTURE if args.sampler == "texture" else pkg.SAMPLER_EXPLICIT
+            f.tp.skipEmptySpace = 0 if args.no_skip else 1
+            f.vol.format = {"r8": pkg.VOLUME_R8, "r32f": pkg.VOLUME_R32F, "rg8": pkg.VOLUME_RG8}[args.volume_format]
+        self.r = pkg.Renderer(ctx["local"], ctx["stream"].cuda_stream)
+        self.r.set_scene(self.frames[0])
+        base = sc.make_scene(config, frame=0, radius_mode=args.radius_mode)       # un-advected offsets: the resident input
+        self.base_pos, self.base_scale = base.board_pos, base.board_scale
+        self.h_pos = [torch.from_numpy(f.board_pos).pin_memory() for f in self.frames]
+        self.h_scale = torch.from_numpy(self.frames[0].board_scale).pin_memory()
+        self.d_img = torch.empty((self.Ht, self.Wd, 4), dtype=torch.uint8, device=dev)
+        self.h_img = [torch.empty((self.Ht, self.Wd, 4), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self.gather = None
+        self.r.voxelize()
+        self.r.cone_trace(self.d_img, pkg.IMAGE_RGBA8)      # one synchronous frame sizes the bin pools before the pipelined legs
+        if shared:
+            self.r.set_tile_row_interleave(rank, world)     # balanced: 16-row tile rows dealt round-robin
+        if mode == "slab":
+            # ONE frame per step for the whole job: every rank voxelizes + mips its Z-slab, one all-gather of the finished
+            # slab-local levels, replicated top levels, then each rank traces its tile rows (no image gather)
+            from cloud_renderer_b200 import sharding as sh
+            self.gather = sh.SlabExchange(torch, ctx["dist"], self.r, self.D, self.L, rank, world, dev)
+
+    def close(self):
+        self.r.close()
+
+    def prewarm(self, seconds=0.3):
+        """Untimed: run the pipeline until the GPU has left its idle clocks.  The first ~50 ms of work after start-up run
+        at a fraction of the boost clock (measured: the first 13 C3 frames took 5.7 ms each, every later leg 3.3 ms), which
+        the W warm-up frames of a short run do not cover."""
+        self.r.set_billboards(self.base_pos, self.base_scale)
+        t0 = time.perf_counter()
+        i = 0
+        while time.perf_counter() - t0 < seconds:
+            self.step(i % len(self.frames), False, asynchronous=True)
+            i += 1
+            if i % 8 == 0:
+                self.r.wait_images()
+        self.r.wait_images()
+        self.barrier()
+
+    def step(self, i, host, out=None, asynchronous=False):
+        """one frame.  host: pinned billboards in, RGBA8 image out to pinned host memory (asynchronous: pipelined read-back).
+        resident: the frame's billboard offsets come from the device-resident base set (crn_animate_billboards: the same
+        rotation field the host fixtures apply, bytes equal — tests/test_parity_gpu.py) and the image stays in HBM."""
+        f, r, pkg = self.frames[i], self.r, self.ctx["pkg"]
+        r.set_camera(f.cam); r.set_sun(f.sun); r.set_trace_params(f.tp)
+        if host:
+            r.set_billboards(self.h_pos[i].numpy(), self.h_scale.numpy())
+        else:
+            r.animate_billboards(0.2 * f.meta["frame"] / 60.0)
+        r.voxelize()
+        if self.gather:
+            self.gather.exchange()
+        if host and asynchronous:
+            r.cone_trace_async(out.numpy(), pkg.IMAGE_RGBA8)
+        elif host:
+            r.cone_trace(out.numpy(), pkg.IMAGE_RGBA8)
+        elif asynchronous:
+            r.cone_trace_enqueue(pkg.IMAGE_RGBA8)
+        else:
+            r.cone_trace(self.d_img, pkg.IMAGE_RGBA8)
+
+    def barrier(self):
+        if self.ctx["world"] > 1:
+            self.ctx["dist"].barrier()
+        self.ctx["torch"].cuda.synchronize()
+
+    def _max_over_ranks(self, v, dtype=None, op=None):
+        torch, dist = self.ctx["torch"], self.ctx["dist"]
+        if self.ctx["world"] == 1:
+            return v
+        t = torch.tensor([v], dtype=dtype or torch.float64, device=self.ctx["dev"])
+        dist.all_reduce(t, op=op or dist.ReduceOp.MAX)
+        return t.item()
+
+    def timed(self, host, sampler=None):
+        """K frames back to back, one event pair (max over ranks), L2 flush between frames inside the region"""
+        torch, stream, r = self.ctx["torch"], self.ctx["stream"], self.r
+        if not host:
+            r.set_billboards(self.base_pos, self.base_scale)      # resident base set; every frame advects it on the device
+            r.sync()
+        for i in range(self.Wm):
+            self.step(i, host, self.h_img[i & 1], asynchronous=True)
+        r.wait_images()
+        self.barrier()
+        if sampler:
+            sampler.start()
+        l0 = r.launch_count()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for i in range(self.K):
+            if not self.args.no_flush:
+                self.ctx["flush"].fill_(i & 0xFF)          # > L2 (126 MB), inside the timed region: conservative
+            self.step(self.Wm + i, host, self.h_img[i & 1], asynchronous=True)
+        r.wait_images()                                    # host leg: every image has landed in host memory; both: pools checked
+        b.record(stream)
+        self.barrier()
+        clocks = sampler.stop() if sampler else None
+        ms = self._max_over_ranks(a.elapsed_time(b))
+        launches = r.launch_count() - l0
+        if self.ctx["world"] > 1:
+            launches = int(self._max_over_ranks(launches, torch.int64, self.ctx["dist"].ReduceOp.SUM))
+        return ms, launches, clocks
+
+    def stages(self):
+        """serialised pass: per-stage CUDA-event times (the library's own events), a sync after every frame"""
+        r = self.r
+        keys = ("prepSortMs", "lightBinMs", "voxelizeMs", "mipMs", "camBinMs", "coneAccelMs", "traceMs")
+        acc = {k: 0.0 for k in keys}
+        torch, stream = self.ctx["torch"], self.ctx["stream"]
+        r.set_billboards(self.base_pos, self.base_scale)
+        r.set_timing(True)
+        tot = 0.0
+        for i in range(self.K):
+            if not self.args.no_flush:
+                self.ctx["flush"].fill_(i & 0xFF)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            self.step(self.Wm + i, False)
+            b.record(stream)
+            t = r.timings()                                # syncs
+            tot += a.elapsed_time(b)
+            for k in keys:
+                acc[k] += getattr(t, k)
+        r.set_timing(False)
+        self.barrier()
+        return {k: v / self.K for k, v in acc.items()}, tot / self.K
+
+    def stats(self):
+        r = self.r
+        r.set_billboards(self.base_pos, self.base_scale)
+        r.set_stats(True)
+        self.step(self.Wm, False)
+        st = r.trace_stats()
+        r.set_stats(False)
+        return st
+
+
+def tex_roofline(st, trace_ms, bil_peak):
+    """texture-pipe roofline of the trace kernel: every lookup charged in bilinear passes of the texture unit (noise tap on
+    the slice-pair texture 1, baked cone step 1, trilinear 2, mip-linear textureLod 4), against the measured ceiling"""
+    noise, baked = st.noiseSamples, st.bakedFetches
+    tri = st.filteredFetches - noise - baked               # trilinear-equivalents of the textureLod cone steps
+    passes = noise + baked + 2 * tri
+    achieved = passes / (trace_ms * 1e-3) / 1e9
+    return {"bound": "tex", "unit": "G bilinear passes/s", "achieved": achieved, "peak": bil_peak,
+            "frac": achieved / bil_peak if bil_peak else None,
+            "passes_per_launch": passes, "noise_bilinear": noise, "baked_cone_bilinear": baked, "textureLod_trilinear_equiv": tri}
+
+
+def summarize(run, ms, ms_e2e, job_frames):
+    return {"frames_per_s": job_frames / (ms * 1e-3), "ms_per_frame": ms / run.K, "e2e_frames_per_s": job_frames / (ms_e2e * 1e-3)}
 
 
 def main():
@@ -230,206 +403,127 @@ def main():
     dev = torch.device("cuda", local)
     stream = torch.cuda.Stream(dev)            # torch's default stream has handle 0, which the C-ABI reads as "create your own":
     torch.cuda.set_stream(stream)              # use one explicit stream for torch's events / flush / NCCL waits AND the library's kernels
-    r = pkg.Renderer(local, stream.cuda_stream)
+    ctx = dict(torch=torch, dist=dist, pkg=pkg, sc=sc, world=world, rank=rank, local=local, dev=dev, stream=stream,
+               flush=torch.empty(256 << 20, dtype=torch.uint8, device=dev))
 
     K, Wm = args.steps, args.warmup
-    slab = args.config == "C4" and world > 1
-    base, frames = frame_inputs(sc, args.config, K + Wm, 0 if slab else rank, 1 if slab else world, args.radius_mode)
-    D, L, N, Wd, Ht = sc.CONFIGS[args.config]
-    for f in frames:
-        f.tp.transmittanceCutoff = args.cutoff
-        f.tp.sampler = pkg.SAMPLER_TEXTURE if args.sampler == "texture" else pkg.SAMPLER_EXPLICIT
-        f.tp.skipEmptySpace = 0 if args.no_skip else 1
-        f.vol.format = {"r8": pkg.VOLUME_R8, "r32f": pkg.VOLUME_R32F, "rg8": pkg.VOLUME_RG8}[args.volume_format]
-    r.set_scene(frames[0])
-
-    # resident inputs (value leg) and pinned host inputs (e2e leg)
-    d_pos = [torch.from_numpy(f.board_pos).to(dev) for f in frames]
-    d_scale = torch.from_numpy(frames[0].board_scale).to(dev)
-    h_pos = [torch.from_numpy(f.board_pos).pin_memory() for f in frames]
-    h_scale = torch.from_numpy(frames[0].board_scale).pin_memory()
-    d_img = torch.empty((Ht, Wd, 4), dtype=torch.uint8, device=dev)
-    h_img = torch.empty((Ht, Wd, 4), dtype=torch.uint8).pin_memory()
-    h_img2 = torch.empty((Ht, Wd, 4), dtype=torch.uint8).pin_memory()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    slab_mode = args.config == "C4" and world > 1
-    gather_mode = slab_mode and args.slab_exchange == "chain"
-    if slab_mode:
-        r.set_tile_row_interleave(rank, world)              # balanced: 16-row tile rows dealt round-robin
-    if gather_mode:
-        # C4: ONE frame per step for the whole job.  Every rank voxelizes + mips its Z-slab, one
-        # all-gather of the finished slab-local levels, replicated top levels, then each rank traces
-        # its band of image rows (no image gather: the bands stay on their GPUs).
-        from cloud_renderer_b200 import sharding as sh
-        z0, z1 = sh.z_slab(D, rank, world)
-        r.set_z_slab(z0, z1)
-        r.voxelize()                                        # allocates bits + chain
-        torch.cuda.synchronize()
-        tens = sh.chain_tensors(torch, r, L, dev)
-        nloc = sh.slab_local_levels(L)
-        views = [sh.slab_view(t, rank, world) for t in tens[:1 + nloc]]     # bits + levels 0..4
-
-    def step(i, host):
-        f = frames[i]
-        r.set_camera(f.cam); r.set_sun(f.sun); r.set_trace_params(f.tp)
-        if host:
-            r.set_billboards(h_pos[i].numpy(), h_scale.numpy())
-        else:
-            r.set_billboards(d_pos[i], d_scale)
-        r.voxelize()
-        if gather_mode:
-            sh.all_gather_levels(dist, views)
-            if L > nloc:
-                r.finish_mips(nloc)
-        r.cone_trace(h_img.numpy() if host else d_img, pkg.IMAGE_RGBA8)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(host, sampler=None):
-        for i in range(Wm):
-            step(i, host)
-        barrier()
-        if sampler:
-            sampler.start()
-        l0 = r.launch_count()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-        stage = {k: 0.0 for k in ("prepSortMs", "lightBinMs", "voxelizeMs", "mipMs", "camBinMs", "traceMs")}
-        r.set_timing(True)
-        for i in range(K):
-            if not args.no_flush:
-                flush.fill_(i & 0xFF)                  # > L2 (126 MB), outside the event pair
-            ev[i][0].record(stream)
-            step(Wm + i, host)
-            ev[i][1].record(stream)
-            t = r.timings()                            # syncs; per-stage CUDA-event times of this frame
-            for k in stage:
-                stage[k] += getattr(t, k)
-        r.set_timing(False)
-        barrier()
-        clocks = sampler.stop() if sampler else None
-        ms = sum(a.elapsed_time(b) for a, b in ev)
-        launches = r.launch_count() - l0
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-            lt = torch.tensor([launches], dtype=torch.int64, device=dev)
-            dist.all_reduce(lt)
-            launches = int(lt.item())
-        return ms, {k: v / K for k, v in stage.items()}, launches, clocks
-
-    def frame_host(i, out):
-        """one frame through the public API with HOST buffers: pinned billboards in, RGBA8 image out (pipelined read-back)"""
-        f = frames[i]
-        r.set_camera(f.cam); r.set_sun(f.sun); r.set_trace_params(f.tp)
-        r.set_billboards(h_pos[i].numpy(), h_scale.numpy())
-        r.voxelize()
-        if gather_mode:
-            sh.all_gather_levels(dist, views)
-            if L > nloc:
-                r.finish_mips(nloc)
-        r.cone_trace_async(out.numpy(), pkg.IMAGE_RGBA8)
-
-    def timed_e2e():
-        for i in range(Wm):
-            frame_host(i, h_img if i & 1 else h_img2)
-        r.wait_images()
-        barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
-        for i in range(K):
-            if not args.no_flush:
-                flush.fill_(i & 0xFF)                  # inside the timed region here: conservative
-            frame_host(Wm + i, h_img if i & 1 else h_img2)
-        r.wait_images()                                # every image has landed in host memory
-        b.record(stream)
-        barrier()
-        ms = a.elapsed_time(b)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
-
-    sampler = ClockSampler(local) if rank == 0 else None
-    ms, stage, launches, clocks = timed(False, sampler)
-    ms_e2e = timed_e2e()
-
-    # fragments / samples actually shaded in one frame (stats pass, outside the timed region)
-    r.set_stats(True)
-    step(Wm, False)
-    st = r.trace_stats()
-    r.set_stats(False)
-    frag, cone, noise, bins = st.fragments, st.coneSamples, st.noiseSamples, st.binEntries
-    cone_skipped, fetches = st.coneSamplesSkipped, st.filteredFetches
-    tex_peak = bil_peak = None
+    cfg = args.config
+    shared = cfg == "C4" and world > 1
+    mode = ("slab" if args.slab_exchange == "chain" else "replicate") if shared else "frames"
+    run = Runner(ctx, cfg, K, Wm, args, mode)
+    sampler = ClockSampler(local) if rank == 0 and not os.environ.get("BENCH_NO_SMI") else None
+    run.prewarm()
+    ms, launches, clocks = run.timed(False, sampler)
+    ms_e2e, _, _ = run.timed(True)
+    stage, serial_ms = run.stages()
+    st = run.stats()
+    D, L, N, Wd, Ht = sc.CONFIGS[cfg]
+    radius_mode = run.frames[0].meta["radius_mode"]
+    bil_peak = tri_peak = None
     if rank == 0 and args.sampler == "texture":
         try:
-            tex_peak = min(pkg.microbench(0, local), pkg.microbench(1, local))     # G trilinear fetches/s, measured now
-            bil_peak = pkg.microbench(6, local)                                     # G bilinear (layered 2D) fetches/s
+            bil_peak = pkg.microbench(6, local)                                     # G bilinear (layered 2D) fetches/s, measured now
+            tri_peak = min(pkg.microbench(0, local), pkg.microbench(1, local))      # G trilinear fetches/s
         except Exception:
-            tex_peak = bil_peak = None
+            bil_peak = tri_peak = None
+    run.close()
+
+    # ---- the other BASELINE.json configs, a few frames each (recorded driver-side with the headline)
+    extra = {}
+    if not args.no_extras:
+        Ke, We = min(K, 8), 3
+        def one(config, mode="frames", label=None):
+            try:
+                rr = Runner(ctx, config, Ke, We, args, mode)
+                rr.prewarm(0.1)
+                m, _, _ = rr.timed(False)
+                me, _, _ = rr.timed(True)
+                sg, ser = rr.stages()
+                s2 = rr.stats()
+                jf = Ke if mode != "frames" else world * Ke
+                out = summarize(rr, m, me, jf)
+                out.update({"n_gpus": world, "steps": Ke, "warmup": We, "mode": mode, "trace_kernel_ms": sg["traceMs"], "cone_accel_ms": sg["coneAccelMs"],
+                            "voxelize_mip_ms": sg["lightBinMs"] + sg["voxelizeMs"] + sg["mipMs"], "serialized_ms_per_frame": ser,
+                            "fragments_shaded": s2.fragments,
+                            "workload": workload_name(sc, config, rr.frames[0].meta["radius_mode"])})
+                if bil_peak or world > 1:
+                    bp = bil_peak
+                    if bp:
+                        out["tex_roofline_frac"] = tex_roofline(s2, sg["traceMs"], bp)["frac"]
+                if rr.gather:
+                    out["exchange"] = rr.gather.describe()
+                rr.close()
+                extra[label or config] = out
+            except Exception as e:                      # an extra must never take the headline down
+                extra[label or config] = {"error": repr(e)}
+        if world == 1:
+            for c in ("C1", "C2", "C5", "C4"):
+                if c != cfg:
+                    one(c)
+        else:
+            if cfg != "C5":
+                one("C5")
+            if cfg != "C4":
+                if D and (512 % (world * 16) == 0):
+                    one("C4", "slab", "C4_slab_exchange")
+                one("C4", "replicate", "C4_replicated")
 
     if rank == 0:
-        job_frames = K if slab_mode else world * K          # C4 shards ONE frame per step over all ranks
+        job_frames = K if shared else world * K          # C4 at N>1 shards ONE frame per step over all ranks
         fps = job_frames / (ms * 1e-3)
         fps_e2e = job_frames / (ms_e2e * 1e-3)
         peak, peak_src = load_peaks()
-        # dominant kernel = cone trace.  ALGORITHMIC bytes per launch (SURVEY.md §8d): every cone tap
-        # reads 8 texels per level (16 when two levels blend), every noise tap 8 RGBA8 texels, plus the image.
+        frag, cone, noise, bins = st.fragments, st.coneSamples, st.noiseSamples, st.binEntries
         trace_ms = stage["traceMs"]
-        alg_bytes = (cone - cone_skipped) * 16 * 1 + noise * 8 * 4 + Wd * Ht * 4
-        achieved = alg_bytes / (trace_ms * 1e-3) / 1e9
-        traffic = ncu_traffic("r01_trace_texture_final.txt" if args.sampler == "texture" else "r01_trace_explicit.txt")
+        roof = None
+        if bil_peak:
+            roof = tex_roofline(st, trace_ms, bil_peak)
+            roof.update({
+                "kernel": "trace_fast_kernel" if args.sampler == "texture" else "trace_kernel",
+                "traffic": ncu_traffic("r02_trace_final.txt"),
+                "trilinear_peak": tri_peak,
+                "peak_source": "crn_microbench, measured in this run: tex2DLayered RGBA8 bilinear, warp-coherent coordinates (148 SMs x 4 lanes/clk)",
+                "hbm_note": {"algorithmic_texel_GBps": ((st.filteredFetches - noise - st.bakedFetches) * 8 + st.bakedFetches * 16 + noise * 16 + Wd * Ht * 4) / (trace_ms * 1e-3) / 1e9,
+                             "hbm_peak_GBps": peak, "hbm_peak_source": peak_src,
+                             "note": "texel bytes are served by L1 (hit rate > 99 %): HBM is idle (traffic = DRAM bytes of one ncu capture), the binding roof is the texture pipe"},
+            })
         out = {
-            "metric": metric_name(args.config),
+            "metric": metric_name(cfg),
             "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
-            "higher_is_better": True, "scaling": "strong" if slab_mode else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if shared else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": workload_name(sc, args.config, frames[0].meta['radius_mode']),
-                "sharding": ("Z-slab voxelize+mips, one all-gather of the finished chain (NCCL), tile-row-interleaved trace" if gather_mode else
-                             "voxelize+mips replicated on every rank (no collective), tile-row-interleaved trace" if slab_mode else
-                             "frames round-robin over ranks, volume replicated, no collective" if world > 1 else "single GPU"),
+                "workload": workload_name(sc, cfg, radius_mode),
+                "sharding": ("Z-slab voxelize+mips, one all-gather of the finished chain (NCCL), tile-row-interleaved trace" if mode == "slab" else
+                             "voxelize+mips replicated on every rank (no collective), tile-row-interleaved trace" if mode == "replicate" else
+                             "time steps (C5: views) round-robin over ranks, volume replicated, no collective" if world > 1 else "single GPU"),
                 "transmittance_cutoff": args.cutoff, "sampler": args.sampler, "skip_empty_space": not args.no_skip,
                 "volume_format": args.volume_format,
-                "l2": "none (back to back)" if args.no_flush else "256 MiB fill between steps, outside the per-step event pairs",
+                "l2": "none (back to back)" if args.no_flush else "256 MiB fill between steps, inside the timed region",
+                "timing": "K frames enqueued back to back, one CUDA-event pair on the launching stream, max over ranks; the library overlaps the "
+                          "light side of frame k+1 with the trace of frame k (see stages_ms for the serialised per-stage times)",
             },
             "clocks": clocks,
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": N * 16, "d2h_bytes_per_step": Wd * Ht * 4,
                     "how": "crn_set_billboards(pinned host) + crn_voxelize + crn_cone_trace_async(pinned host RGBA8) per frame, "
                            "crn_wait_images at the end; the read-back of frame k overlaps the kernels of frame k+1"},
             "gpu_launches": launches,
-            "stages_ms": stage, "voxelize_mip_ms": stage["lightBinMs"] + stage["voxelizeMs"] + stage["mipMs"],
-            "per_frame": {"fragments_shaded": frag, "cone_samples": cone, "cone_samples_skipped_as_empty": cone_skipped,
-                          "noise_samples": noise, "bin_entries": bins,
+            "stages_ms": stage, "serialized_ms_per_step": serial_ms,
+            "voxelize_mip_ms": stage["lightBinMs"] + stage["voxelizeMs"] + stage["mipMs"],
+            "per_frame": {"fragments_shaded": frag, "cone_samples": cone, "cone_samples_skipped_as_empty": st.coneSamplesSkipped,
+                          "cone_samples_baked": st.bakedFetches, "noise_samples": noise, "bin_entries": bins,
                           "cone_samples_per_s": cone / (trace_ms * 1e-3), "filtered_samples_per_s": (cone + noise) / (trace_ms * 1e-3)},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "trace_kernel", "peak_source": peak_src,
-                         "note": ("algorithmic texel bytes (SURVEY 8d: 16 B per fetched cone sample, 32 B per noise tap, + the image) are served "
-                                  "by L1 at a 99.9% hit rate, so this fraction can exceed 1 and HBM is NOT the binding roof (traffic = DRAM bytes "
-                                  "of one ncu capture, profiles/); the binding roof is the texture pipe: see roofline_tex")},
-            # texture-pipe roofline: the cone trace's volume lookups are 3D trilinear (two bilinear passes in the texture
-            # unit), the noise taps are single bilinear passes on the layered slice-pair texture; each kind is charged at
-            # its own measured ceiling and the fraction is (time at the ceilings) / (measured kernel time)
-            "roofline_tex": None if not tex_peak else {
-                "bound": "tex", "unit": "G bilinear passes/s",
-                "achieved": (2 * (fetches - noise) + noise) / (trace_ms * 1e-3) / 1e9, "peak": bil_peak,
-                "frac": ((fetches - noise) / tex_peak + noise / bil_peak) / 1e9 / (trace_ms * 1e-3),
-                "cone_trilinear_lookups_per_launch": fetches - noise, "noise_bilinear_lookups_per_launch": noise,
-                "trilinear_peak": tex_peak,
-                "peak_source": "crn_microbench, measured in this run: tex2DLayered RGBA8 bilinear (peak) and tex3D trilinear "
-                               "(min of RGBA8 32^3 and R8 256^3) for the volume lookups"},
+            "roofline": roof,
+            "extra": extra,
         }
         if not args.no_cpu_baseline and world == 1:
             orc = entry.import_oracle()
             orc.build()
-            out["cpu_baseline"] = cpu_baseline(args.config, orc, sc)
-        os.write(real_stdout, (json.dumps(out) + "\n").encode())
-    r.close()
+            out["cpu_baseline"] = cpu_baseline(cfg, orc, sc)
+        line = json.dumps(out)
+        os.write(real_stdout, (line + "\n").encode())
+        if args.save:
+            with open(args.save, "w") as f:
+                f.write(line + "\n")
     if world > 1:
         dist.destroy_process_group()
 

@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcloud_renderer_b200.so")
+LIB_PATH = os.environ.get("CRN_LIB") or os.path.join(_HERE, "libcloud_renderer_b200.so")      # CRN_LIB: experiment builds (build.py build_variant)
 
 CRN_OK, CRN_ERR_INVALID_ARG, CRN_ERR_CUDA, CRN_ERR_STATE, CRN_ERR_UNSUPPORTED, CRN_ERR_NO_DEVICE = range(6)
 MEM_HOST, MEM_DEVICE = 0, 1
@@ -57,7 +57,8 @@ class TraceStats(C.Structure):
 
 
 class Timings(C.Structure):
-    _fields_ = [("prepSortMs", f32), ("lightBinMs", f32), ("voxelizeMs", f32), ("mipMs", f32), ("camBinMs", f32), ("traceMs", f32)]
+    _fields_ = [("prepSortMs", f32), ("lightBinMs", f32), ("voxelizeMs", f32), ("mipMs", f32), ("camBinMs", f32), ("traceMs", f32),
+                ("coneAccelMs", f32)]
 
 
 # every symbol include/cloud_renderer_b200.h declares (tests check the library exports all of them)
@@ -66,7 +67,7 @@ EXPORTS = [
     "crn_regenerate_billboards", "crn_animate_billboards", "crn_read_billboards", "crn_read_volume_alpha", "crn_export_voxels",
     "crn_sun_update", "crn_set_camera", "crn_camera_update", "crn_set_window", "crn_set_trace_params",
     "crn_default_trace_params", "crn_set_noise", "crn_build_noise", "crn_voxelize", "crn_cone_trace", "crn_cone_trace_async",
-    "crn_wait_images", "crn_set_row_range",
+    "crn_wait_images", "crn_cone_trace_enqueue", "crn_image_ptr", "crn_set_row_range",
     "crn_set_tile_row_interleave",
     "crn_set_z_slab", "crn_volume_level_ptr", "crn_volume_bits_ptr", "crn_finish_mips", "crn_read_volume",
     "crn_count_active_voxels", "crn_keep_position_map", "crn_read_position_map", "crn_read_sorted_order", "crn_read_bins",
@@ -113,6 +114,8 @@ def load_library():
     lib.crn_cone_trace.argtypes = [vp, vp, i32, i32]
     lib.crn_cone_trace_async.argtypes = [vp, vp, i32]
     lib.crn_wait_images.argtypes = [vp]
+    lib.crn_cone_trace_enqueue.argtypes = [vp, i32]
+    lib.crn_image_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     lib.crn_set_row_range.argtypes = [vp, i32, i32]
     lib.crn_set_z_slab.argtypes = [vp, i32, i32]
     lib.crn_set_tile_row_interleave.argtypes = [vp, i32, i32]
@@ -283,6 +286,15 @@ class Renderer:
         p, m = _ptr(out)
         assert m == MEM_HOST
         self._ck(self.lib.crn_cone_trace_async(self.h, p, fmt))
+
+    def cone_trace_enqueue(self, fmt=IMAGE_RGBA8):
+        """enqueue only; the image stays in the context's device buffer (image_ptr)"""
+        self._ck(self.lib.crn_cone_trace_enqueue(self.h, fmt))
+
+    def image_ptr(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._ck(self.lib.crn_image_ptr(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
 
     def wait_images(self):
         self._ck(self.lib.crn_wait_images(self.h))

@@ -139,6 +139,10 @@ struct crn_ctx {
     int ilvIndex = 0, ilvCount = 1;
     int z0 = 0, z1 = -1;                 // -1: whole volume
     bool keepPosmap = false, statsOn = false, timingOn = false;
+    int imageFormat = CRN_IMAGE_RGBA8;   // format of the frame in `image`
+    size_t slabPoolCap = 0;              // light-pass pool capacity that has been validated for slab voxelizes
+    bool wantLinear0 = false;            // the caller took crn_volume_level_ptr(0): keep the linear level 0 current
+    bool linear0Valid = false, linear0ValidA = false;   // chain level 0 holds the expansion of the current bits (it is produced on demand)
     bool noBake = false;                 // CRN_NO_BAKE=1: every cone step through textureLod (A/B and tests)
     bool voxelized = false, traced = false;
 
@@ -555,12 +559,16 @@ int enqueue_voxelize(crn_ctx *c) {
     st = c->stream;
     cudaStreamWaitEvent(st, c->evLightDone, 0);
     if (c->timingOn) cudaEventRecord(c->evV[5], st);
-    c->launches += launch_mips(st, c->vparams, (const uint32_t *)c->bits.p, (uint8_t *)c->chain.p, (uint32_t *)c->misc.p, true,
-                               toTex ? &c->ts : nullptr);
+    // the linear copy of level 0 (8x the bits) is not read by anything in the pipeline: it is written only for a caller
+    // that holds crn_volume_level_ptr(0), and expanded on demand for crn_read_volume
+    const bool whole = c->vparams.z0 == 0 && c->vparams.z1 == c->vol.dimension;
+    // (a slab's texture copy would be overwritten after the exchange anyway: the textures are filled then)
+    c->launches += launch_mips(st, c->vparams, (const uint32_t *)c->bits.p, (uint8_t *)c->chain.p, (uint32_t *)c->misc.p, c->wantLinear0,
+                               (toTex && whole) ? &c->ts : nullptr);
+    c->linear0Valid = c->wantLinear0; c->linear0ValidA = false;
     if (paper)
         c->launches += launch_mips(st, c->vparams, (const uint32_t *)c->bitsA.p, (uint8_t *)c->chainA.p, (uint32_t *)c->misc.p + 8,
-                                   true, toTex ? &c->tsA : nullptr);
-    const bool whole = c->vparams.z0 == 0 && c->vparams.z1 == c->vol.dimension;
+                                   false, toTex ? &c->tsA : nullptr);
     c->texCurrent = toTex && whole;
     c->maskCurrent = false;
     c->volumeGen++;
@@ -717,6 +725,7 @@ int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
     build_trace_params(c, cam, &tp);
     cudaStream_t st = c->stream;
     bool readsBits = c->tp.sampler != CRN_SAMPLER_TEXTURE;          // the explicit sampler reads level 0 from the bits
+    for (int i = 0; i < c->nBakePlan; i++) readsBits |= c->bakePlan[i].level0 == 0;    // ... and so does a level-0 bake
     if (c->tp.skipEmptySpace && !c->maskCurrent) {     // chain came from an exchange, or the option was just switched on
         if ((r = build_masks(c))) return r;
         readsBits = true;
@@ -725,9 +734,14 @@ int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
     if (useTex) {
         if ((r = ensure_vol_textures(c))) return r;
         if (!c->texCurrent) {           // sampler switched after voxelize, or the chain came from an exchange
-            c->launches += launch_chain_to_surfaces(st, c->vparams, (const uint8_t *)c->chain.p, c->ts, 0);
-            if (c->vol.format == CRN_VOLUME_RG8)
-                c->launches += launch_chain_to_surfaces(st, c->vparams, (const uint8_t *)c->chainA.p, c->tsA, 0);
+            // level 0 from the bits (they are what a slab exchange ships), the coarser levels from the linear chain
+            c->launches += launch_expand_level0(st, c->vparams, (const uint32_t *)c->bits.p, nullptr, &c->ts);
+            c->launches += launch_chain_to_surfaces(st, c->vparams, (const uint8_t *)c->chain.p, c->ts, 1);
+            if (c->vol.format == CRN_VOLUME_RG8) {
+                c->launches += launch_expand_level0(st, c->vparams, (const uint32_t *)c->bitsA.p, nullptr, &c->tsA);
+                c->launches += launch_chain_to_surfaces(st, c->vparams, (const uint8_t *)c->chainA.p, c->tsA, 1);
+            }
+            readsBits = true;
             c->texCurrent = true;
         }
     }
@@ -735,6 +749,7 @@ int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
     if (c->statsOn) cudaMemsetAsync(dStats, 0, 8 * sizeof(unsigned long long), st);
     if (c->timingOn) cudaEventRecord(c->evT[2], st);                // the cone acceleration data is part of the trace stage
     if ((r = build_cone_accel(c, tp))) return r;
+    if (c->timingOn) cudaEventRecord(c->evT[1], st);
     // ---- camera-side set-up on the side stream: after the billboard upload and after the previous trace (which reads
     //      the same records / bins), concurrently with whatever voxelize work is still queued on the main stream
     cudaStream_t ax = c->auxStream;
@@ -758,6 +773,7 @@ int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
     if (c->timingOn) cudaEventRecord(c->evAuxT[2], ax);
     cudaEventRecord(c->evAuxDone, ax);
     cudaStreamWaitEvent(st, c->evAuxDone, 0);
+    if (c->timingOn) cudaEventRecord(c->evT[0], st);
     c->launches += launch_trace(st, cam, c->vparams, tp, (const BoardRec *)c->recC.p, c->binsC, (const uint32_t *)c->bits.p,
                                 (const uint8_t *)c->chain.p, c->vol.format == CRN_VOLUME_RG8 ? (const uint32_t *)c->bitsA.p : nullptr,
                                 (const uint8_t *)c->chainA.p, (const int8_t *)c->noise.p, useTex ? &c->ts : nullptr,
@@ -887,7 +903,7 @@ void crn_destroy(crn_ctx *c) {
     delete c;
 }
 
-static int settle(crn_ctx *c, bool haveTrace, int format);
+static int settle(crn_ctx *c, bool haveTrace, int format, bool slabNotShippedYet = false);
 
 int crn_sync(crn_ctx *c) {
     if (!c) return CRN_ERR_INVALID_ARG;
@@ -1112,9 +1128,14 @@ int crn_voxelize(crn_ctx *c) {
     if ((r = require(c, c->haveVol, "volume")) || (r = require(c, c->haveSun, "sun")) || (r = require(c, c->haveWindow, "window"))) return r;
     CRN_CUDA(c, cudaSetDevice(c->device));
     if ((r = enqueue_voxelize(c))) return r;
-    // A slab is about to be handed to an exchange this library does not see (crn_volume_level_ptr + an external
-    // all-gather): it must be final when the call returns, so the bin-pool check cannot be deferred here.
-    if (c->z1 >= 0 && !(c->z0 == 0 && c->z1 == c->vol.dimension)) return settle(c, false, 0);
+    // A Z-slab is about to be handed to an exchange this library does not see.  The first slab after the bin pools were
+    // (re)allocated is checked here, once, with a host round trip (grow + re-run if the first guess was too small); every
+    // later frame stays asynchronous: a pool that turns out too small then is reported by the next synchronising call
+    // (crn_cone_trace, crn_sync, crn_wait_images return CRN_ERR_STATE after growing it; re-submit the frame, exchange included).
+    if (c->z1 >= 0 && !(c->z0 == 0 && c->z1 == c->vol.dimension) && c->slabPoolCap != c->binsL.tileCap + c->binsL.coarseCap) {
+        if ((r = settle(c, false, 0, true))) return r;
+        c->slabPoolCap = c->binsL.tileCap + c->binsL.coarseCap;
+    }
     return CRN_OK;
 }
 
@@ -1146,7 +1167,7 @@ static int copy_image(crn_ctx *c, void *out, cudaMemcpyKind kind, int format, co
 }
 
 // make sure neither pass ran with a truncated bin pool; re-run what did
-static int settle(crn_ctx *c, bool haveTrace, int format) {
+static int settle(crn_ctx *c, bool haveTrace, int format, bool slabNotShippedYet) {
     for (int attempt = 0; attempt < 4; attempt++) {
         CRN_CUDA(c, cudaStreamSynchronize(c->lightStream));
         CRN_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -1156,6 +1177,11 @@ static int settle(crn_ctx *c, bool haveTrace, int format) {
         if (c->voxelized && (r = grow_if_overflowed(c, c->binsL, c->hCursors, &grewL))) return r;
         if (haveTrace && (r = grow_if_overflowed(c, c->binsC, c->hCursors + 2, &grewC))) return r;
         if (!grewL && !grewC) return CRN_OK;
+        if (grewL && !slabNotShippedYet && c->z1 >= 0 && !(c->z0 == 0 && c->z1 == c->vol.dimension)) {
+            // the truncated slab has already been shipped to the other ranks: this library cannot redo the exchange
+            CRN_CUDA(c, cudaMemsetAsync(c->binsL.cursors + 2, 0, sizeof(uint32_t), c->lightStream));
+            return fail(c, CRN_ERR_STATE, "the light-space bin pool overflowed while voxelizing a Z-slab; the pool has been grown, re-submit the frame (exchange included)");
+        }
         // the truncated attempt left the sticky overflow flag behind; this frame is being redone, so clear it
         if (grewL) CRN_CUDA(c, cudaMemsetAsync(c->binsL.cursors + 2, 0, sizeof(uint32_t), c->lightStream));
         if (grewC) CRN_CUDA(c, cudaMemsetAsync(c->binsC.cursors + 2, 0, sizeof(uint32_t), c->stream));
@@ -1179,6 +1205,7 @@ int crn_cone_trace(crn_ctx *c, void *out, int32_t mem, int32_t format) {
     if ((r = enqueue_trace(c, format))) return r;
     if ((r = settle(c, true, format))) return r;
     c->traced = true;
+    c->imageFormat = format;
     if ((r = copy_image(c, out, mem == CRN_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, format, c->image, c->stream))) return r;
     if (mem == CRN_MEM_HOST) CRN_CUDA(c, cudaStreamSynchronize(c->stream));
     return CRN_OK;
@@ -1205,6 +1232,30 @@ int crn_cone_trace_async(crn_ctx *c, void *out, int32_t format) {
     CRN_CUDA(c, cudaEventRecord(c->evCopy[k], c->copyStream));
     c->copyPending[k] = true;
     c->imgSel ^= 1;
+    return CRN_OK;
+}
+
+int crn_cone_trace_enqueue(crn_ctx *c, int32_t format) {
+    if (!c) return CRN_ERR_INVALID_ARG;
+    if (format != CRN_IMAGE_RGBA8 && format != CRN_IMAGE_RGBA32F) return fail(c, CRN_ERR_INVALID_ARG, "unknown image format %d", format);
+    int r;
+    if ((r = require(c, c->haveVol, "volume")) || (r = require(c, c->haveSun, "sun")) || (r = require(c, c->haveCam, "camera")) ||
+        (r = require(c, c->haveWindow, "window")) || (r = require(c, c->haveNoise, "noise texture")))
+        return r;
+    if (!c->voxelized) return fail(c, CRN_ERR_STATE, "crn_voxelize has not produced a volume yet");
+    CRN_CUDA(c, cudaSetDevice(c->device));
+    if (c->copyPending[0]) { CRN_CUDA(c, cudaStreamWaitEvent(c->stream, c->evCopy[0], 0)); c->copyPending[0] = false; }
+    if ((r = enqueue_trace(c, format))) return r;
+    c->traced = true;
+    c->imageFormat = format;
+    return CRN_OK;
+}
+
+int crn_image_ptr(crn_ctx *c, void **dev_ptr, size_t *bytes) {
+    if (!c || !dev_ptr || !bytes) return CRN_ERR_INVALID_ARG;
+    if (!c->traced || !c->image.p) return fail(c, CRN_ERR_STATE, "no frame has been traced into the context's image yet");
+    *dev_ptr = c->image.p;
+    *bytes = (size_t)c->W * c->H * (c->imageFormat == CRN_IMAGE_RGBA32F ? 16 : 4);
     return CRN_OK;
 }
 
@@ -1262,6 +1313,14 @@ int crn_volume_level_ptr(crn_ctx *c, int32_t level, void **dev_ptr, size_t *byte
     const size_t s = c->vparams.levelSize[level];
     *dev_ptr = (char *)c->chain.p + c->vparams.levelOff[level];
     *bytes = s * s * s * c->vparams.texelBytes;
+    if (level == 0) {                   // from now on every voxelize keeps the linear level 0 current
+        c->wantLinear0 = true;
+        if (c->voxelized && !c->linear0Valid) {
+            CRN_CUDA(c, cudaSetDevice(c->device));
+            c->launches += launch_expand_level0(c->stream, c->vparams, (const uint32_t *)c->bits.p, (uint8_t *)c->chain.p, nullptr);
+            c->linear0Valid = true;
+        }
+    }
     return CRN_OK;
 }
 
@@ -1296,6 +1355,10 @@ int crn_read_volume(crn_ctx *c, int32_t level, void *dst) {
     if (level < 0 || level >= c->vol.levels) return fail(c, CRN_ERR_INVALID_ARG, "level %d out of range", level);
     CRN_CUDA(c, cudaSetDevice(c->device));
     int r = settle(c, false, 0); if (r) return r;
+    if (level == 0 && !c->linear0Valid) {
+        c->launches += launch_expand_level0(c->stream, c->vparams, (const uint32_t *)c->bits.p, (uint8_t *)c->chain.p, nullptr);
+        c->linear0Valid = true;
+    }
     const size_t s = c->vparams.levelSize[level];
     CRN_CUDA(c, cudaMemcpyAsync(dst, (char *)c->chain.p + c->vparams.levelOff[level], s * s * s * c->vparams.texelBytes, cudaMemcpyDeviceToHost,
                                 c->stream));
@@ -1310,6 +1373,10 @@ int crn_read_volume_alpha(crn_ctx *c, int32_t level, void *dst) {
     if (level < 0 || level >= c->vol.levels) return fail(c, CRN_ERR_INVALID_ARG, "level %d out of range", level);
     CRN_CUDA(c, cudaSetDevice(c->device));
     int r = settle(c, false, 0); if (r) return r;
+    if (level == 0 && !c->linear0ValidA) {
+        c->launches += launch_expand_level0(c->stream, c->vparams, (const uint32_t *)c->bitsA.p, (uint8_t *)c->chainA.p, nullptr);
+        c->linear0ValidA = true;
+    }
     const size_t s = c->vparams.levelSize[level];
     CRN_CUDA(c, cudaMemcpyAsync(dst, (char *)c->chainA.p + c->vparams.levelOff[level], s * s * s, cudaMemcpyDeviceToHost, c->stream));
     CRN_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -1462,7 +1529,8 @@ int crn_get_timings(crn_ctx *c, crn_timings *out) {
         CRN_CUDA(c, cudaEventElapsedTime(&t, c->evAuxT[0], c->evAuxT[1]));        // side stream: overlaps the voxelize stage
         out->prepSortMs += t;
         CRN_CUDA(c, cudaEventElapsedTime(&out->camBinMs, c->evAuxT[1], c->evAuxT[2]));
-        CRN_CUDA(c, cudaEventElapsedTime(&out->traceMs, c->evT[2], c->evT[3]));
+        CRN_CUDA(c, cudaEventElapsedTime(&out->coneAccelMs, c->evT[2], c->evT[1]));
+        CRN_CUDA(c, cudaEventElapsedTime(&out->traceMs, c->evT[0], c->evT[3]));
     }
     return CRN_OK;
 }

@@ -171,6 +171,7 @@ struct BakeTex {
 
 int launch_mips(cudaStream_t st, const VolumeParams &vol, const uint32_t *bits, uint8_t *chain, uint32_t *ticket,
                 bool writeLevel0, const TexSet *ts);
+int launch_expand_level0(cudaStream_t st, const VolumeParams &vol, const uint32_t *bits, uint8_t *chain, const TexSet *ts);   // chain / ts may be null
 int launch_chain_to_surfaces(cudaStream_t st, const VolumeParams &vol, const uint8_t *chain, const TexSet &ts, int firstLevel);
 int launch_finish_mips(cudaStream_t st, const VolumeParams &vol, uint8_t *chain, int firstLevel);
 int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol, const TraceParams &tp,

@@ -27,88 +27,109 @@ namespace crn {
 
 namespace {
 
-struct BakeArgs {
-    VolumeParams vol;
-    const uint32_t *bits;
-    const uint8_t *chain;
-    int nTex;
-    BakeTex tex[kMaxBakedTex];
+// textures that share one lattice (same lower level) are evaluated together: the two trilinear samples are the same,
+// only the blend fraction differs
+struct BakeGroup {
+    int level0, n, count;
+    int NL, NU;                              // texels per axis of the lower / upper level (NU = 0: no upper level needed)
+    uint32_t offL, offU;                     // byte offsets of the two levels in the chain
+    float frac[kMaxBakedTex];
+    cudaSurfaceObject_t surf[kMaxBakedTex];
 };
 
-// trilinear sample of level l at the lattice node (kx,ky,kz); `scale` = lattice spacing / texel size of level l
-// (1/2 for the lower level, 1/4 for the upper one; 1/2 and 1 when the lattice is the half-voxel one of level 0)
-__device__ __forceinline__ float node_sample(const BakeArgs &a, int l, float scale, int kx, int ky, int kz) {
-    const int N = a.vol.levelSize[l];
-    int i0[3], i1[3];
-    float w[3];
-    const int k[3] = {kx, ky, kz};
-#pragma unroll
-    for (int d = 0; d < 3; d++) {
-        const float t = (float)k[d] * scale - 0.5f;              // exact: multiples of 1/4
-        const float fl = floorf(t);
-        w[d] = t - fl;
-        const int i = (int)fl;
-        i0[d] = min(max(i, 0), N - 1);                           // CLAMP_TO_EDGE
-        i1[d] = min(max(i + 1, 0), N - 1);
-    }
+struct BakeArgs {
+    const uint32_t *bits;
+    const uint8_t *chain;
+    int nGroups;
+    BakeGroup g[kMaxBakedTex];
+};
+
+// one axis of the trilinear footprint of a lattice node: the lattice spacing is half a texel of the lower level
+// (shift 1) and a quarter of the upper one (shift 2), so the weights are exact multiples of 1/4
+struct NodeAxis {
+    int i0, i1;
+    float w;
+};
+
+__device__ __forceinline__ NodeAxis node_axis(int k, int shift, int N) {
+    NodeAxis a;
+    const int i = (k - shift) >> shift;                              // floor(k / 2^shift - 1/2)
+    a.w = shift == 1 ? ((k & 1) ? 0.0f : 0.5f) : (float)((k + 2) & 3) * 0.25f;
+    a.i0 = min(max(i, 0), N - 1);                                    // CLAMP_TO_EDGE
+    a.i1 = min(max(i + 1, 0), N - 1);
+    return a;
+}
+
+// kFmt: 0 = R8 chain level (>= 1), 1 = R32F chain level (>= 1), 2 = the 1-bit level 0
+template <int kFmt>
+__device__ __forceinline__ float node_sample(const uint32_t *__restrict__ bits, const uint8_t *__restrict__ lvl, int N, int shift, int kx, int ky, int kz) {
+    const NodeAxis X = node_axis(kx, shift, N), Y = node_axis(ky, shift, N), Z = node_axis(kz, shift, N);
     float c[8];
 #pragma unroll
-    for (int q = 0; q < 8; q++) {
-        const int x = (q & 1) ? i1[0] : i0[0], y = (q & 2) ? i1[1] : i0[1], z = (q & 4) ? i1[2] : i0[2];
-        if (l == 0) {
-            const uint32_t word = __ldg(a.bits + ((size_t)z * N + y) * (N >> 5) + (x >> 5));
-            c[q] = (float)((word >> (x & 31)) & 1u);
-        } else if (a.vol.texelBytes == 4) {
-            c[q] = __ldg(reinterpret_cast<const float *>(a.chain + a.vol.levelOff[l]) + ((size_t)z * N + y) * N + x);
+    for (int q = 0; q < 4; q++) {
+        const uint32_t row = (uint32_t)(((q & 2) ? Z.i1 : Z.i0) * N + ((q & 1) ? Y.i1 : Y.i0));
+        if (kFmt == 2) {
+            const uint32_t *r = bits + row * (uint32_t)(N >> 5);
+            c[2 * q] = (float)((__ldg(r + (X.i0 >> 5)) >> (X.i0 & 31)) & 1u);
+            c[2 * q + 1] = (float)((__ldg(r + (X.i1 >> 5)) >> (X.i1 & 31)) & 1u);
+        } else if (kFmt == 1) {
+            const float *r = reinterpret_cast<const float *>(lvl) + row * (uint32_t)N;
+            c[2 * q] = __ldg(r + X.i0); c[2 * q + 1] = __ldg(r + X.i1);
         } else {
-            c[q] = (float)__ldg(a.chain + a.vol.levelOff[l] + ((size_t)z * N + y) * N + x) * (1.0f / 255.0f);
+            const uint8_t *r = lvl + row * (uint32_t)N;
+            c[2 * q] = (float)__ldg(r + X.i0); c[2 * q + 1] = (float)__ldg(r + X.i1);
         }
     }
-    const float x00 = fmaf(w[0], c[1] - c[0], c[0]), x10 = fmaf(w[0], c[3] - c[2], c[2]);
-    const float x01 = fmaf(w[0], c[5] - c[4], c[4]), x11 = fmaf(w[0], c[7] - c[6], c[6]);
-    const float y0 = fmaf(w[1], x10 - x00, x00), y1 = fmaf(w[1], x11 - x01, x01);
-    return fmaf(w[2], y1 - y0, y0);
+    const float x00 = fmaf(X.w, c[1] - c[0], c[0]), x10 = fmaf(X.w, c[3] - c[2], c[2]);
+    const float x01 = fmaf(X.w, c[5] - c[4], c[4]), x11 = fmaf(X.w, c[7] - c[6], c[6]);
+    const float y0 = fmaf(Y.w, x10 - x00, x00), y1 = fmaf(Y.w, x11 - x01, x01);
+    const float v = fmaf(Z.w, y1 - y0, y0);
+    return kFmt == 0 ? v * (1.0f / 255.0f) : v;
 }
 
-__device__ __forceinline__ float node_value(const BakeArgs &a, const BakeTex &t, int kx, int ky, int kz) {
-    // lattice spacing is 2^(L-1) voxels (half a voxel for L = 0): half a texel of level L, a quarter of level L+1
-    const float lo = node_sample(a, t.level0, 0.5f, kx, ky, kz);
-    if (!(t.frac > 0.0f)) return lo;
-    const float hi = node_sample(a, t.level0 + 1, 0.25f, kx, ky, kz);
-    return fmaf(t.frac, hi - lo, lo);
-}
-
+// one thread per lattice NODE: its value goes into the .x half of layer k and the .y half of layer k-1 (16-bit surface
+// stores at byte offsets 4x and 4x+2), so every node is evaluated once, for every texture of its group
+template <bool kF32>
 __global__ void __launch_bounds__(256) bake_steps_kernel(const __grid_constant__ BakeArgs a) {
-    const BakeTex &t = a.tex[blockIdx.y];
-    const int n = t.n;
-    const size_t total = (size_t)n * n * (n - 1);
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-        const int x = (int)(e % n), y = (int)((e / n) % n), k = (int)(e / ((size_t)n * n));
-        const float v0 = node_value(a, t, x, y, k), v1 = node_value(a, t, x, y, k + 1);
-        ushort2 o;
-        o.x = (unsigned short)__float2uint_rn(__saturatef(v0) * 65535.0f);
-        o.y = (unsigned short)__float2uint_rn(__saturatef(v1) * 65535.0f);
-        surf2DLayeredwrite(o, t.surf, x * 4, y, k);
+    const BakeGroup &g = a.g[blockIdx.z];
+    const int n = g.n;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int yk = blockIdx.y * 8 + (threadIdx.x >> 5);              // y + n * k
+    if (x >= n || yk >= n * n) return;
+    const int y = yk % n, k = yk / n;
+    float lo, hi = 0.0f;
+    if (g.level0 == 0) lo = node_sample<2>(a.bits, nullptr, g.NL, 1, x, y, k);
+    else lo = node_sample<kF32 ? 1 : 0>(nullptr, a.chain + g.offL, g.NL, 1, x, y, k);
+    if (g.NU) hi = node_sample<kF32 ? 1 : 0>(nullptr, a.chain + g.offU, g.NU, 2, x, y, k);
+    for (int t = 0; t < g.count; t++) {
+        const float v = g.frac[t] > 0.0f ? fmaf(g.frac[t], hi - lo, lo) : lo;
+        const unsigned short q = (unsigned short)__float2uint_rn(__saturatef(v) * 65535.0f);
+        if (k < n - 1) surf2DLayeredwrite(q, g.surf[t], x * 4, y, k);
+        if (k > 0) surf2DLayeredwrite(q, g.surf[t], x * 4 + 2, y, k - 1);
     }
 }
+
+struct CodeGroup {
+    float reach;                              // group height / dim: |P - pos| in normalized coordinates
+    float sizeF;
+    int size, wpr;
+    uint32_t maskOff;
+};
 
 struct CodeArgs {
     int G;
     int nGroups;
-    float height[kCodeGroups];
-    int size[kCodeGroups], wpr[kCodeGroups];
-    uint32_t maskOff[kCodeGroups];
+    CodeGroup g[kCodeGroups];
     const uint32_t *mask;
     float lightPos[3], b0[3], range[3];
-    float invDim;
     uint8_t *code;
 };
 
 __global__ void __launch_bounds__(256) need_code_kernel(const __grid_constant__ CodeArgs a) {
     const int G = a.G;
-    const size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= (size_t)G * G * G) return;
-    const int ix = (int)(cell % G), iy = (int)((cell / G) % G), iz = (int)(cell / ((size_t)G * G));
+    const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = blockIdx.y * 8 + (threadIdx.x >> 5), iz = blockIdx.z;
+    if (ix >= G || iy >= G) return;
+    const uint32_t cell = ((uint32_t)iz * G + iy) * G + ix;
     const float invG = 1.0f / (float)G;
     const float half = 0.5f * invG * 1.001f + 1.0e-6f;           // half a cell, in normalized coordinates, with slack
     const float nc[3] = {((float)ix + 0.5f) * invG, ((float)iy + 0.5f) * invG, ((float)iz + 0.5f) * invG};
@@ -122,7 +143,6 @@ __global__ void __launch_bounds__(256) need_code_kernel(const __grid_constant__ 
         hw2 += hw * hw;
     }
     const float dist = sqrtf(d2), hw = sqrtf(hw2);               // |light - centre|, half diagonal of the cell in world units
-    uint32_t bitsOut = 0;
     // the unit vector towards the light turns by at most |dw| / (distance to the light) over the cell; a light inside
     // or next to the cell gives no useful bound: every group stays needed there
     const float dmin = dist - hw;
@@ -130,32 +150,51 @@ __global__ void __launch_bounds__(256) need_code_kernel(const __grid_constant__ 
         a.code[cell] = 0xFF;
         return;
     }
-    const float invDist = 1.0f / dist;
+    const float invDist = 1.0f / dist, turn = (hw / dmin) * 1.01f;
+    uint32_t bitsOut = 0;
     for (int g = 0; g < a.nGroups; g++) {
-        const float reach = a.height[g] * a.invDim;              // |P - pos| in normalized coordinates
-        const float ext = half + reach * (hw / dmin) * 1.01f + 2.0e-5f;
-        const int n = a.size[g];
+        const CodeGroup &cg = a.g[g];
+        const float ext = half + cg.reach * turn + 2.0e-5f;
+        const int n = cg.size;
         int lo[3], hi[3];
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            const float p = nc[k] + reach * toL[k] * invDist;
+            const float p = nc[k] + cg.reach * toL[k] * invDist;
             // the trace kernel looks the point up with CLAMP_TO_EDGE semantics: clamp the texel range the same way
-            lo[k] = min(max((int)floorf((p - ext) * (float)n), 0), n - 1);
-            hi[k] = min(max((int)floorf((p + ext) * (float)n), 0), n - 1);
+            lo[k] = min(max(__float2int_rd((p - ext) * cg.sizeF), 0), n - 1);
+            hi[k] = min(max(__float2int_rd((p + ext) * cg.sizeF), 0), n - 1);
         }
-        const uint32_t *m = a.mask + a.maskOff[g];
-        uint32_t any = 0;
+        const uint32_t *m = a.mask + cg.maskOff;
         const int w0 = lo[0] >> 5, w1 = hi[0] >> 5;
-        for (int z = lo[2]; z <= hi[2] && !any; z++)
-            for (int y = lo[1]; y <= hi[1] && !any; y++) {
-                const uint32_t *row = m + ((size_t)z * n + y) * a.wpr[g];
-                for (int w = w0; w <= w1; w++) {
-                    uint32_t sel = 0xFFFFFFFFu;
-                    if (w == w0) sel &= 0xFFFFFFFFu << (lo[0] & 31);
-                    if (w == w1) sel &= 0xFFFFFFFFu >> (31 - (hi[0] & 31));
-                    any |= __ldg(row + w) & sel;
+        const uint32_t sel0 = (0xFFFFFFFFu << (lo[0] & 31)) & (w1 == w0 ? 0xFFFFFFFFu >> (31 - (hi[0] & 31)) : 0xFFFFFFFFu);
+        uint32_t any = 0;
+        // The range is at most 4 texels per axis unless the light is very close: 16 independent loads, no loop
+        // (rows past hi are clamped onto hi: duplicates do not change an OR)
+        const bool small = hi[1] - lo[1] < 4 && hi[2] - lo[2] < 4 && w1 - w0 < 2;
+        if (__all_sync(__activemask(), small)) {
+            uint32_t a0 = 0, a1 = 0;
+            const bool two = __any_sync(__activemask(), w1 != w0);
+#pragma unroll
+            for (int dz = 0; dz < 4; dz++)
+#pragma unroll
+                for (int dy = 0; dy < 4; dy++) {
+                    const uint32_t *row = m + (uint32_t)(min(lo[2] + dz, hi[2]) * n + min(lo[1] + dy, hi[1])) * (uint32_t)cg.wpr;
+                    a0 |= __ldg(row + w0);
+                    if (two) a1 |= __ldg(row + w1);
                 }
-            }
+            any = (a0 & sel0) | (w1 != w0 ? a1 & (0xFFFFFFFFu >> (31 - (hi[0] & 31))) : 0u);
+        } else {
+            for (int z = lo[2]; z <= hi[2]; z++)
+                for (int y = lo[1]; y <= hi[1]; y++) {
+                    const uint32_t *row = m + (uint32_t)(z * n + y) * (uint32_t)cg.wpr;
+                    for (int w = w0; w <= w1; w++) {
+                        uint32_t sel = 0xFFFFFFFFu;
+                        if (w == w0) sel &= 0xFFFFFFFFu << (lo[0] & 31);
+                        if (w == w1) sel &= 0xFFFFFFFFu >> (31 - (hi[0] & 31));
+                        any |= __ldg(row + w) & sel;
+                    }
+                }
+        }
         if (any) bitsOut |= 1u << g;
     }
     a.code[cell] = (uint8_t)bitsOut;
@@ -165,15 +204,28 @@ __global__ void __launch_bounds__(256) need_code_kernel(const __grid_constant__ 
 
 int launch_bake_steps(cudaStream_t st, const VolumeParams &vol, const uint32_t *bits, const uint8_t *chain, const BakeTex *tex, int nTex) {
     if (nTex <= 0) return 0;
-    BakeArgs a;
-    a.vol = vol; a.bits = bits; a.chain = chain; a.nTex = nTex;
-    size_t most = 0;
+    BakeArgs a{};
+    a.bits = bits; a.chain = chain;
+    int most = 0;
     for (int i = 0; i < nTex; i++) {
-        a.tex[i] = tex[i];
-        most = std::max(most, (size_t)tex[i].n * tex[i].n * (tex[i].n - 1));
+        int g = -1;
+        for (int j = 0; j < a.nGroups; j++)
+            if (a.g[j].level0 == tex[i].level0) g = j;
+        if (g < 0) {
+            g = a.nGroups++;
+            BakeGroup &bg = a.g[g];
+            bg.level0 = tex[i].level0; bg.n = tex[i].n; bg.count = 0;
+            bg.NL = vol.levelSize[bg.level0]; bg.offL = vol.levelOff[bg.level0];
+            bg.NU = 0; bg.offU = 0;
+            most = std::max(most, bg.n);
+        }
+        BakeGroup &bg = a.g[g];
+        if (tex[i].frac > 0.0f) { bg.NU = vol.levelSize[bg.level0 + 1]; bg.offU = vol.levelOff[bg.level0 + 1]; }
+        bg.frac[bg.count] = tex[i].frac; bg.surf[bg.count] = tex[i].surf; bg.count++;
     }
-    const unsigned blocks = (unsigned)std::min<size_t>((most + 255) / 256, 148 * 16);
-    bake_steps_kernel<<<dim3(blocks, nTex), 256, 0, st>>>(a);
+    const dim3 grid((most + 31) / 32, (most * most + 7) / 8, a.nGroups);
+    if (vol.texelBytes == 4) bake_steps_kernel<true><<<grid, 256, 0, st>>>(a);
+    else bake_steps_kernel<false><<<grid, 256, 0, st>>>(a);
     return 1;
 }
 
@@ -182,15 +234,14 @@ int launch_need_code(cudaStream_t st, const VolumeParams &vol, const TraceParams
     a.G = tp.codeDim;
     a.nGroups = std::min(tp.nGroups, kCodeGroups);
     for (int g = 0; g < a.nGroups; g++) {
-        a.height[g] = tp.groups[g].height; a.size[g] = tp.groups[g].size; a.wpr[g] = tp.groups[g].wpr; a.maskOff[g] = tp.groups[g].maskOff;
+        a.g[g].reach = tp.groups[g].height / (float)vol.dim; a.g[g].size = tp.groups[g].size; a.g[g].sizeF = (float)tp.groups[g].size;
+        a.g[g].wpr = tp.groups[g].wpr; a.g[g].maskOff = tp.groups[g].maskOff;
     }
     a.mask = mask; a.code = code;
     a.b0[0] = vol.xB[0]; a.b0[1] = vol.yB[0]; a.b0[2] = vol.zB[0];
     a.range[0] = vol.xB[1] - vol.xB[0]; a.range[1] = vol.yB[1] - vol.yB[0]; a.range[2] = vol.zB[1] - vol.zB[0];
     for (int k = 0; k < 3; k++) a.lightPos[k] = tp.lightPos[k];
-    a.invDim = 1.0f / (float)vol.dim;
-    const size_t cells = (size_t)a.G * a.G * a.G;
-    need_code_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(a);
+    need_code_kernel<<<dim3((a.G + 31) / 32, (a.G + 7) / 8, a.G), 256, 0, st>>>(a);
     return 1;
 }
 

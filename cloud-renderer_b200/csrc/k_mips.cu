@@ -18,6 +18,8 @@
 // Integer arithmetic throughout: results are bit-exact against the oracle.
 #include "crn_internal.cuh"
 
+#include <algorithm>
+
 namespace crn {
 
 namespace {
@@ -73,7 +75,7 @@ __global__ void __launch_bounds__(256) mip_chain_kernel(MipArgs a) {
     }
     __syncthreads();
 
-    if (a.writeLevel0) {
+    if (a.writeLevel0 || a.useSurf) {                    // linear level 0 only on request (nothing in the pipeline reads it)
         uint8_t *l0 = a.chain + a.vol.levelOff[0];
         constexpr int SEG = BX / 16;                     // 16-byte segments per row
 #pragma unroll
@@ -85,7 +87,7 @@ __global__ void __launch_bounds__(256) mip_chain_kernel(MipArgs a) {
             uint4 o;
             o.x = spread4(h & 15u); o.y = spread4((h >> 4) & 15u); o.z = spread4((h >> 8) & 15u); o.w = spread4(h >> 12);
             const int y = row & 15, z = row >> 4;
-            *reinterpret_cast<uint4 *>(l0 + ((size_t)(z0 + z) * D + (y0 + y)) * D + x0 + seg * 16) = o;
+            if (a.writeLevel0) *reinterpret_cast<uint4 *>(l0 + ((size_t)(z0 + z) * D + (y0 + y)) * D + x0 + seg * 16) = o;
             if (a.useSurf) surf3Dwrite(o, a.surf[0], x0 + seg * 16, y0 + y, z0 + z);
         }
     }
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(256) mip_chain_f32_kernel(MipArgs a) {
         for (int w = 0; w < WX; w++) sBits[tid * WX + w] = __ldg(src + w);
     }
     __syncthreads();
-    if (a.writeLevel0) {            // 4 voxels -> one 128-bit store; a warp writes 512 contiguous bytes
+    if (a.writeLevel0 || a.useSurf) {            // 4 voxels -> one 128-bit store; a warp writes 512 contiguous bytes
         float *l0 = level(0);
         constexpr int QUADS = BX / 4;                       // float4 per row
         for (int s = tid; s < 256 * QUADS; s += 256) {
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(256) mip_chain_f32_kernel(MipArgs a) {
             const uint32_t nib = (sBits[row * WX + (q >> 3)] >> ((q & 7) * 4)) & 15u;
             const float4 o = make_float4((nib & 1u) ? 1.0f : 0.0f, (nib & 2u) ? 1.0f : 0.0f, (nib & 4u) ? 1.0f : 0.0f, (nib & 8u) ? 1.0f : 0.0f);
             const int y = row & 15, z = row >> 4;
-            *reinterpret_cast<float4 *>(l0 + ((size_t)(z0 + z) * D + (y0 + y)) * D + x0 + q * 4) = o;
+            if (a.writeLevel0) *reinterpret_cast<float4 *>(l0 + ((size_t)(z0 + z) * D + (y0 + y)) * D + x0 + q * 4) = o;
             if (a.useSurf) surf3Dwrite(o, a.surf[0], (x0 + q * 4) * 4, y0 + y, z0 + z);
         }
     }
@@ -328,6 +330,39 @@ __global__ void __launch_bounds__(256) level_to_surface_kernel(const uint8_t *__
     }
 }
 
+// level 0 from the occupancy bits, on demand: the linear copy (crn_read_volume / crn_volume_level_ptr) and / or the
+// texture-unit copy (after a slab exchange, which ships the bits, not 8x as many bytes)
+template <bool kF32>
+__global__ void __launch_bounds__(256) expand_level0_kernel(const uint32_t *__restrict__ bits, uint8_t *__restrict__ linear, cudaSurfaceObject_t surf,
+                                                            int D, int useSurf) {
+    const size_t words = (size_t)D * D * (D >> 5);
+    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t b = __ldg(bits + w);
+        const int wpr = D >> 5;
+        const int x0 = (int)(w % wpr) * 32, y = (int)((w / wpr) % D), z = (int)(w / ((size_t)wpr * D));
+        if (kF32) {
+            float *dst = linear ? reinterpret_cast<float *>(linear) + ((size_t)z * D + y) * D + x0 : nullptr;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const uint32_t nib = (b >> (4 * q)) & 15u;
+                const float4 o = make_float4((nib & 1u) ? 1.0f : 0.0f, (nib & 2u) ? 1.0f : 0.0f, (nib & 4u) ? 1.0f : 0.0f, (nib & 8u) ? 1.0f : 0.0f);
+                if (dst) reinterpret_cast<float4 *>(dst)[q] = o;
+                if (useSurf) surf3Dwrite(o, surf, (x0 + 4 * q) * 4, y, z);
+            }
+        } else {
+            uint8_t *dst = linear ? linear + ((size_t)z * D + y) * D + x0 : nullptr;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint32_t hw = (b >> (16 * h)) & 0xFFFFu;
+                uint4 o;
+                o.x = spread4(hw & 15u); o.y = spread4((hw >> 4) & 15u); o.z = spread4((hw >> 8) & 15u); o.w = spread4(hw >> 12);
+                if (dst) reinterpret_cast<uint4 *>(dst)[h] = o;
+                if (useSurf) surf3Dwrite(o, surf, x0 + 16 * h, y, z);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) count_bits_kernel(const uint32_t *__restrict__ bits, size_t words, unsigned long long *out) {
     unsigned long long c = 0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x)
@@ -359,6 +394,16 @@ int launch_mips(cudaStream_t st, const VolumeParams &vol, const uint32_t *bits, 
     if (a.bx == 128) mip_chain_kernel<4><<<grid, 256, 0, st>>>(a);
     else if (a.bx == 64) mip_chain_kernel<2><<<grid, 256, 0, st>>>(a);
     else mip_chain_kernel<1><<<grid, 256, 0, st>>>(a);
+    return 1;
+}
+
+int launch_expand_level0(cudaStream_t st, const VolumeParams &vol, const uint32_t *bits, uint8_t *chain, const TexSet *ts) {
+    const size_t words = (size_t)vol.dim * vol.dim * (vol.dim >> 5);
+    const int blocks = (int)std::min<size_t>((words + 255) / 256, 148 * 16);
+    uint8_t *linear = chain ? chain + vol.levelOff[0] : nullptr;
+    const cudaSurfaceObject_t surf = ts ? ts->surf[0] : 0;
+    if (vol.texelBytes == 4) expand_level0_kernel<true><<<blocks, 256, 0, st>>>(bits, linear, surf, vol.dim, ts ? 1 : 0);
+    else expand_level0_kernel<false><<<blocks, 256, 0, st>>>(bits, linear, surf, vol.dim, ts ? 1 : 0);
     return 1;
 }
 

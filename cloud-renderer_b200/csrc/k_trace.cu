@@ -492,8 +492,11 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_fast_kern
     const int tile = (int)a.order[blockIdx.x / kSplit];
     const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) + (blockIdx.x % kSplit) * kWarps;
     const int tx = tile % a.tilesX, ty = tile / a.tilesX;
-    const int px = tx * kTile + (warp & 1) * 8 + (lane & 7);
-    const int py = ty * kTile + (warp >> 1) * 4 + (lane >> 3);
+    // 2x2-pixel quads: the texture unit works on groups of four consecutive lanes, and a disc edge leaves fewer
+    // partially filled 2x2 blocks than 4x1 strips (measured at C3: trace 3.35 -> 3.30 ms)
+    const int lx = (lane & 1) | ((lane >> 1) & 6), ly = ((lane >> 1) & 1) | ((lane >> 3) & 2);
+    const int px = tx * kTile + (warp & 1) * 8 + lx;
+    const int py = ty * kTile + (warp >> 1) * 4 + ly;
     if (tp.ilvCount > 1 && (ty % tp.ilvCount) != tp.ilvIndex) return;
     const bool valid = px < cam.W && py < cam.H && py >= tp.row0 && py < tp.row1;
     if (__all_sync(0xFFFFFFFFu, !valid)) return;

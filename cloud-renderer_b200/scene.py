@@ -13,7 +13,8 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from . import Camera, Sun, TraceParams, VolumeDesc, build_noise, camera_update, default_trace_params
+from . import Camera, Sun, TraceParams, VolumeDesc
+from . import build_noise as _lib_build_noise, camera_update as _lib_camera_update, default_trace_params as _lib_default_trace_params
 
 SEED = 0xC10D5EED
 _M64 = (1 << 64) - 1
@@ -68,10 +69,46 @@ CONFIGS = {
 }
 
 
-def make_noise(seed=SEED, dim=32):
+class LibraryHost:
+    """host math of the fixtures from the product library (crn_camera_update, crn_build_noise, crn_default_trace_params)"""
+    camera_update = staticmethod(_lib_camera_update)
+    build_noise = staticmethod(_lib_build_noise)
+    default_trace_params = staticmethod(_lib_default_trace_params)
+
+
+def reference_default_trace_params():
+    """src/Shaders/ConeTraceShader.hpp:15-36 + src/main.cpp:112, without touching the library (bench.py --impl reference)"""
+    p = TraceParams()
+    p.stepSize, p.noiseOpacity, p.numOctaves, p.freqStep, p.persStep = 0.01, 4.0, 4, 3.0, 0.5
+    p.adjustSize, p.minNoiseSteps, p.maxNoiseSteps, p.minNoiseColor, p.noiseColorScale = 40.0, 2, 8, 0.2, 0.45
+    p.windVel[:] = (0.01, 0.0, 0.0)
+    p.vctSteps, p.vctConeAngle, p.vctConeInitialHeight, p.vctLodOffset, p.vctDownScaling = 16, 0.9, 0.1, 0.0, 1.0
+    p.showQuad, p.doConeTrace, p.doNoiseSample = 0, 1, 1
+    p.runTime = 0.0
+    p.clearColor[:] = (0.2, 0.3, 0.5, 1.0)
+    p.drawSun, p.transmittanceCutoff, p.sampler, p.skipEmptySpace = 1, 0.0, 0, 1
+    return p
+
+
+class OracleHost:
+    """the same fixtures from the oracle's host math: the reference arm of bench.py must not load the product library"""
+
+    def __init__(self, orc):
+        self.orc = orc
+
+    def camera_update(self, width, height, eye, look_at):
+        return self.orc.camera_update(width, height, eye, look_at, Camera)
+
+    def build_noise(self, alpha):
+        return self.orc.build_noise(alpha)
+
+    default_trace_params = staticmethod(reference_default_trace_params)
+
+
+def make_noise(seed=SEED, dim=32, host=LibraryHost):
     a = np.floor(uniform01(seed ^ 0x5EED0001, dim ** 3) * 256.0 - 128.0)     # trunc of U[-128,128)
     alpha = np.clip(a, -128, 127).astype(np.int8)
-    return build_noise(alpha)
+    return host.build_noise(alpha)
 
 
 def make_boards(n, seed=SEED, radius_mode="auto"):
@@ -99,7 +136,7 @@ def animate(pos0, frame, rate=0.2, fps=60.0):
 
 
 def make_scene(name="C1", seed=SEED, frame=0, view=None, n_views=64, radius_mode="auto", size=None, boards=None,
-               cutoff=0.0):
+               cutoff=0.0, host=LibraryHost):
     D, L, N, W, H = CONFIGS[name]
     if size is not None:
         W, H = size
@@ -126,11 +163,11 @@ def make_scene(name="C1", seed=SEED, frame=0, view=None, n_views=64, radius_mode
         c, s = math.cos(ang), math.sin(ang)
         sun_pos = centre + np.array([c * rel[0] + s * rel[2], rel[1], -s * rel[0] + c * rel[2]])
     sun.position[:] = tuple(float(np.float32(v)) for v in sun_pos)
-    cam = camera_update(W, H, eye, look)
-    tp = default_trace_params()
+    cam = host.camera_update(W, H, eye, look)
+    tp = host.default_trace_params()
     tp.runTime = frame / 60.0
     tp.transmittanceCutoff = cutoff
     pos0, scale, mode = make_boards(N, seed, radius_mode)
     pos = animate(pos0, frame) if frame else pos0
-    return Scene(name, vol, sun, cam, tp, W, H, pos, scale, make_noise(seed), eye, look,
+    return Scene(name, vol, sun, cam, tp, W, H, pos, scale, make_noise(seed, host=host), eye, look,
                  dict(radius_mode=mode, frame=frame, view=view, seed=seed))

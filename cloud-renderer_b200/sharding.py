@@ -73,6 +73,72 @@ def all_gather_levels(dist, views, group=None):
         w.wait()
 
 
+class PackedSlabs:
+    """ONE collective for several slab-partitioned buffers.  Every buffer in `parts` (flat uint8 tensors: the occupancy
+    bits, chain levels 1..4) is split into `world` equal contiguous Z-slabs; rank r packs its slab of each into one chunk,
+    a single in-place all_gather_into_tensor moves all chunks, and one strided copy per buffer puts the slabs back."""
+
+    def __init__(self, torch, parts, rank, world):
+        self.parts, self.rank, self.world = parts, rank, world
+        self.sizes = [t.numel() // world for t in parts]
+        for t, sz in zip(parts, self.sizes):
+            assert sz * world == t.numel()
+        self.chunk = sum(self.sizes)
+        self.packed = torch.empty(world * self.chunk, dtype=torch.uint8, device=parts[0].device)
+        self.mine = self.packed[rank * self.chunk:(rank + 1) * self.chunk]
+
+    def pack(self):
+        off = 0
+        for t, sz in zip(self.parts, self.sizes):
+            self.mine[off:off + sz].copy_(t[self.rank * sz:(self.rank + 1) * sz])
+            off += sz
+
+    def unpack(self):
+        pv = self.packed.view(self.world, self.chunk)
+        off = 0
+        for t, sz in zip(self.parts, self.sizes):
+            t.view(self.world, sz).copy_(pv[:, off:off + sz])
+            off += sz
+
+    def exchange(self, dist, group=None):
+        self.pack()
+        dist.all_gather_into_tensor(self.packed, self.mine, group=group)      # the ONE collective
+        self.unpack()
+
+    def bytes_received(self):
+        return (self.world - 1) * self.chunk
+
+
+class SlabExchange:
+    """C4 (D >= 512): Z-slab voxelize + slab-local mips per rank, then ONE all-gather of the occupancy bits and chain
+    levels 1..4 (level 0 is NOT shipped: 8x the bits, every rank re-expands it from them), replicated top levels."""
+
+    def __init__(self, torch, dist, renderer, D, L, rank, world, device):
+        self.dist, self.r, self.L = dist, renderer, L
+        z0, z1 = z_slab(D, rank, world)
+        renderer.set_z_slab(z0, z1)
+        renderer.voxelize()                                   # allocates bits + chain
+        renderer.sync()
+        self.nloc = slab_local_levels(L)
+        p, n = renderer.volume_bits_ptr()
+        parts = [torch.as_tensor(DeviceBytes(p, n), device=device)]
+        for l in range(1, self.nloc):
+            p, n = renderer.volume_level_ptr(l)
+            parts.append(torch.as_tensor(DeviceBytes(p, n), device=device))
+        self.packed = PackedSlabs(torch, parts, rank, world)
+
+    def exchange(self):
+        self.packed.exchange(self.dist)
+        if self.L > self.nloc:
+            self.r.finish_mips(self.nloc)
+        else:
+            self.r.finish_mips(self.L)                        # nothing to reduce: marks the chain as changed
+
+    def describe(self):
+        return {"collectives_per_frame": 1, "bytes_received_per_rank": self.packed.bytes_received(),
+                "shipped": "occupancy bits + chain levels 1..%d" % (self.nloc - 1)}
+
+
 class DeviceBytes:
     """zero-copy torch view of a device buffer the C-ABI owns (crn_volume_level_ptr)"""
 

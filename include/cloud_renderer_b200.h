@@ -158,6 +158,7 @@ typedef struct crn_timings {
     float mipMs;           /* level-0 expand + all mip levels                          */
     float camBinMs;        /* camera-space binning                                     */
     float traceMs;         /* cone-trace kernel                                        */
+    float coneAccelMs;     /* per-frame cone acceleration data (baked step textures, need codes), part of the trace stage */
 } crn_timings;
 
 /* ---- lifetime --------------------------------------------------------------------- */
@@ -245,6 +246,13 @@ int crn_cone_trace(crn_ctx *ctx, void *out, int32_t mem, int32_t format);
  * of any frame since the last wait (CRN_ERR_STATE: the pools have been grown, re-submit those frames). */
 int crn_cone_trace_async(crn_ctx *ctx, void *out_host, int32_t format);
 int crn_wait_images(crn_ctx *ctx);
+/* Device-resident counterpart of crn_cone_trace_async: enqueue the frame and leave the image in the context's own
+ * device buffer (the reference leaves it in the window framebuffer, src/main.cpp:123).  Nothing is copied and the host
+ * is not synchronised; consume the image in stream order through crn_image_ptr, and call crn_sync / crn_wait_images
+ * before trusting it (they report a bin pool that overflowed, as for the asynchronous path). */
+int crn_cone_trace_enqueue(crn_ctx *ctx, int32_t format);
+/* device address + size of the image written by the most recent crn_cone_trace / crn_cone_trace_enqueue (row 0 = bottom) */
+int crn_image_ptr(crn_ctx *ctx, void **dev_ptr, size_t *bytes);
 
 /* ---- sharding hooks (multi-GPU; results are invariant to them) --------------------- */
 /* restrict crn_cone_trace to image rows [row0,row1); other rows of `out` are untouched */
@@ -254,11 +262,16 @@ int crn_set_row_range(crn_ctx *ctx, int32_t row0, int32_t row1);
 int crn_set_tile_row_interleave(crn_ctx *ctx, int32_t index, int32_t count);
 /* restrict crn_voxelize to voxel slices z in [z0,z1): only those slices of every
  * slab-local level are produced (levels whose texel spans more than the slab are left
- * for crn_finish_mips after the exchange).  With a slab set, crn_voxelize returns only
- * once the slab is final (it synchronises), so the caller may exchange it right away. */
+ * for crn_finish_mips after the exchange).  crn_voxelize stays asynchronous: the exchange is
+ * ordered after it on the context's stream (NCCL / peer copies enqueued on that stream), and
+ * what has to travel is the occupancy bits (crn_volume_bits_ptr) plus chain levels 1.. of the
+ * slab-local range — level 0 is re-expanded from the bits on every rank.  A bin pool that was
+ * too small for the slab is reported by the next synchronising call (CRN_ERR_STATE; the pool has
+ * been grown, re-submit the frame including the exchange). */
 int crn_set_z_slab(crn_ctx *ctx, int32_t z0, int32_t z1);
-/* device address + byte size of one level of the chain (for an external all-gather); the contents are final after
- * crn_sync (or after crn_voxelize itself when a Z-slab is set) */
+/* device address + byte size of one level of the chain (for an external all-gather); written in stream order by
+ * crn_voxelize.  The linear copy of level 0 (8x the bits) is produced only for a caller that has asked for it:
+ * taking its address here switches that on for every later crn_voxelize (crn_read_volume expands it on demand). */
 int crn_volume_level_ptr(crn_ctx *ctx, int32_t level, void **dev_ptr, size_t *bytes);
 /* device address + size of the level-0 occupancy bitset (1 bit per voxel, x-fastest) */
 int crn_volume_bits_ptr(crn_ctx *ctx, void **dev_ptr, size_t *bytes);

@@ -45,6 +45,26 @@ def main():
     off = sum((D >> l) ** 3 for l in range(nloc - 1))
     assert np.array_equal(top, full[off:]), "replicated top levels differ"
 
+    # --- the same exchange as ONE collective (PackedSlabs): bits + levels 1..nloc-1 packed into one chunk per rank
+    bits_full = np.packbits((l0 > 0).ravel(), bitorder="little")
+    bits_mine = np.zeros_like(bits_full)
+    per = bits_full.size // world
+    bits_mine[rank * per:(rank + 1) * per] = bits_full[rank * per:(rank + 1) * per]
+    parts = [torch.from_numpy(bits_mine.copy())]
+    for l in range(1, nloc):
+        size = D >> l
+        t = torch.zeros(size ** 3, dtype=torch.uint8)
+        lo, hi = z0 >> l, z1 >> l
+        src = orc.chain_level(orc.mips(mine0, L), D, l)
+        t.view(size, size, size)[lo:hi] = torch.from_numpy(src[lo:hi].copy())
+        parts.append(t)
+    ps = sh.PackedSlabs(torch, parts, rank, world)
+    ps.exchange(dist)
+    assert np.array_equal(parts[0].numpy(), bits_full), "bits differ after the packed gather"
+    for l in range(1, nloc):
+        assert np.array_equal(parts[l].numpy(), orc.chain_level(full, D, l).ravel()), f"packed gather: level {l} differs"
+    assert ps.bytes_received() == (world - 1) * sum(p.numel() // world for p in parts)
+
     # --- row bands of the trace: disjoint cover, and the assembled image equals the unsharded one
     H = s.height
     r0, r1 = sh.row_range(H, rank, world)
