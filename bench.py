@@ -71,14 +71,37 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons while the timed region runs"""
+    """SM clock + throttle reasons WHILE the timed region runs: NVML polled every 2 ms from a thread (the legs last tens of
+    milliseconds, too short for `nvidia-smi -lms`); nvidia-smi is the fallback when the NVML binding is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.nvml, self.stop_flag = [], None, index, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber: resolve through the PCI bus id of the CUDA device
+            import torch
+            bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(torch.cuda.get_device_properties(index), "pci_bus_id") else None
+            self.handle = None
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(h).bus == bus:
+                        self.handle = h
+            if self.handle is None:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
     def start(self):
+        if self.nvml:
+            self.samples, self.reasons = [], 0
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -87,11 +110,33 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                self.samples.append(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                self.reasons |= n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml:
+            self.stop_flag = True
+            self.thread.join(timeout=1)
+            n = self.nvml
+            names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            try:
+                mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+            except Exception:
+                mx = None
+            return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": mx,
+                    "reasons": sorted(k for k, bit in names.items() if self.reasons & bit), "samples": len(self.samples), "source": "nvml, 2 ms poll"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -110,7 +155,7 @@ class ClockSampler:
                 if len(r) > col and r[col].lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def metric_name(config):
@@ -309,6 +354,8 @@ class Runner:
             r.set_billboards(self.base_pos, self.base_scale)      # resident base set; every frame advects it on the device
             r.sync()
         for i in range(self.Wm):
+            if not self.args.no_flush:
+                self.ctx["flush"].fill_(i & 0xFF)          # warm-up steps are the timed steps, flush included
             self.step(i, host, self.h_img[i & 1], asynchronous=True)
         r.wait_images()
         self.barrier()
