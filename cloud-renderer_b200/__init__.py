@@ -202,6 +202,7 @@ class Renderer:
         self.h = h
         self.width = self.height = 0
         self.vol = None
+        self.n_boards = 0
 
     def close(self):
         if getattr(self, "h", None):
@@ -220,23 +221,34 @@ class Renderer:
         self._ck(self.lib.crn_set_volume(self.h, C.byref(vol)))
 
     def set_billboards(self, positions, scales):
+        if isinstance(positions, np.ndarray):           # host arrays: the C side reads raw float32 memory
+            positions = np.ascontiguousarray(positions, dtype=np.float32)
+            scales = np.ascontiguousarray(scales, dtype=np.float32)
+        else:
+            assert positions.is_contiguous() and scales.is_contiguous() and str(positions.dtype).endswith("float32") and str(scales.dtype).endswith("float32")
+        n = int(scales.shape[0])
+        assert tuple(positions.shape) == (n, 3) and tuple(scales.shape) == (n,), "positions must be (n,3), scales (n,)"
         p, mp = _ptr(positions)
         s, ms = _ptr(scales)
         assert mp == ms
-        n = int(scales.shape[0])
+        self._keep = (positions, scales)                # the upload is asynchronous: keep the source alive
         self._ck(self.lib.crn_set_billboards(self.h, p, s, n, mp))
+        self.n_boards = n
 
     def regenerate_billboards(self, count, min_offset, max_offset, min_scale, max_scale, radius_factor=1.0, seed=0):
         """device-side CloudVolume::regenerateBillboards (src/CloudVolume.cpp:120-137); no host->device copy"""
         lo, hi = (f32 * 3)(*min_offset), (f32 * 3)(*max_offset)
         self._ck(self.lib.crn_regenerate_billboards(self.h, count, C.byref(lo), C.byref(hi), min_scale, max_scale,
                                                     radius_factor, seed & ((1 << 64) - 1)))
+        self.n_boards = count
 
     def animate_billboards(self, angle):
         """offsets = R_y(angle) * base offsets, on the device"""
         self._ck(self.lib.crn_animate_billboards(self.h, float(angle)))
 
-    def read_billboards(self, count):
+    def read_billboards(self, count=None):
+        assert count is None or count == self.n_boards, "the C side copies every billboard of the context"
+        count = self.n_boards
         pos = np.empty((count, 3), np.float32)
         scale = np.empty(count, np.float32)
         self._ck(self.lib.crn_read_billboards(self.h, pos.ctypes.data, scale.ctypes.data))
@@ -367,8 +379,9 @@ class Renderer:
         self._ck(self.lib.crn_read_position_map(self.h, out.ctypes.data))
         return out
 
-    def read_sorted_order(self, n):
-        out = np.empty(n, dtype=np.int32)
+    def read_sorted_order(self, n=None):
+        assert n is None or n == self.n_boards, "the C side copies one entry per billboard of the context"
+        out = np.empty(self.n_boards, dtype=np.int32)
         self._ck(self.lib.crn_read_sorted_order(self.h, out.ctypes.data))
         return out
 

@@ -157,7 +157,7 @@ struct crn_ctx {
     bool maskCurrent = false;
     size_t poolMin = (size_t)1 << 20;    // initial bin-pool entries (CRN_BIN_POOL_MIN overrides: tests force the growth path)
     Bins binsL, binsC;
-    uint32_t *hCursors = nullptr;        // pinned: [0..1] light cursors, [2..3] camera cursors
+    uint32_t *hCursors = nullptr;        // pinned: [0..2] light cursors + flags, [4..6] camera cursors + flags
     unsigned long long *hStats = nullptr;
 
     // texture-unit copies (CRN_SAMPLER_TEXTURE)
@@ -547,7 +547,7 @@ int enqueue_voxelize(crn_ctx *c) {
     // flight on the same copy engine and stall the kernels of this frame
     cudaEventRecord(c->evBin[0], st);
     cudaStreamWaitEvent(c->copyStream, c->evBin[0], 0);
-    cudaMemcpyAsync(c->hCursors, c->binsL.cursors, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->copyStream);
+    cudaMemcpyAsync(c->hCursors, c->binsL.cursors, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->copyStream);
     cudaEventRecord(c->evCur[0], c->copyStream); c->curValid[0] = true;
     if (c->timingOn) cudaEventRecord(c->evV[2], st);
     c->launches += launch_voxelize(st, light, c->vparams, sd.nearPlane, sd.clipDistance, (const BoardRec *)c->recL.p,
@@ -767,7 +767,7 @@ int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
     c->launches += launch_bin(ax, (const BoardRect *)c->rectC.p, sort_tmp_bounds(c->sortTmpC.p, (int)nn, 1), n, c->W, c->H, c->binsC);
     cudaEventRecord(c->evBin[1], ax);
     cudaStreamWaitEvent(c->copyStream, c->evBin[1], 0);
-    cudaMemcpyAsync(c->hCursors + 2, c->binsC.cursors, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->copyStream);
+    cudaMemcpyAsync(c->hCursors + 4, c->binsC.cursors, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->copyStream);
     cudaEventRecord(c->evCur[1], c->copyStream); c->curValid[1] = true;
     c->launches += launch_tile_order(ax, c->binsC, (uint32_t *)c->tileOrder.p);
     if (c->timingOn) cudaEventRecord(c->evAuxT[2], ax);
@@ -826,9 +826,9 @@ int crn_create(int device, void *stream, crn_ctx **out) {
         }
         c->ownStream = true;
     }
-    cudaMallocHost(&c->hCursors, 4 * sizeof(uint32_t));
+    cudaMallocHost(&c->hCursors, 8 * sizeof(uint32_t));
     cudaMallocHost(&c->hStats, 8 * sizeof(unsigned long long));
-    std::memset(c->hCursors, 0, 4 * sizeof(uint32_t));
+    std::memset(c->hCursors, 0, 8 * sizeof(uint32_t));
     std::memset(c->hStats, 0, 8 * sizeof(unsigned long long));
     cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&c->auxStream, cudaStreamNonBlocking);
@@ -953,6 +953,9 @@ int crn_set_billboards(crn_ctx *c, const float *positions3, const float *scales,
         CRN_CUDA(c, cudaMemcpyAsync(c->scale.p, scales, (size_t)count * 4, kind, up));
     }
     CRN_CUDA(c, cudaEventRecord(c->evBoards, up));
+    // a device-resident source is read on the light stream: make the caller's stream wait for that read, so that the
+    // caller may overwrite or free the source in stream order right after this call
+    if (mem == CRN_MEM_DEVICE && count) CRN_CUDA(c, cudaStreamWaitEvent(c->stream, c->evBoards, 0));
     c->nBoards = count;
     c->havePos0 = false;
     return CRN_OK;
@@ -1144,7 +1147,14 @@ static int copy_image(crn_ctx *c, void *out, cudaMemcpyKind kind, int format, co
     const size_t texel = format == CRN_IMAGE_RGBA32F ? 16 : 4;
     const int r0 = std::max(0, c->row0), r1 = std::min(c->H, c->row1);
     const size_t rowB = (size_t)c->W * texel;
-    if (c->ilvCount > 1) {
+    if (c->ilvCount > 1 && (r0 > 0 || r1 < c->H)) {
+        // interleave AND a row range: the owned tile rows, each clipped to [row0,row1)
+        const int tilesY = (c->H + kTile - 1) / kTile;
+        for (int ty = c->ilvIndex; ty < tilesY; ty += c->ilvCount) {
+            const int a = std::max(r0, ty * kTile), b = std::min(r1, std::min(c->H, (ty + 1) * kTile));
+            if (b > a) CRN_CUDA(c, cudaMemcpyAsync((char *)out + (size_t)a * rowB, (char *)src.p + (size_t)a * rowB, (size_t)(b - a) * rowB, kind, st));
+        }
+    } else if (c->ilvCount > 1) {
         // only the tile rows this context owns: one strided 2-D copy (+ the partial last tile row)
         const int tilesY = (c->H + kTile - 1) / kTile;
         for (int ty = c->ilvIndex; ty < tilesY;) {
@@ -1175,7 +1185,16 @@ static int settle(crn_ctx *c, bool haveTrace, int format, bool slabNotShippedYet
         bool grewL = false, grewC = false;
         int r;
         if (c->voxelized && (r = grow_if_overflowed(c, c->binsL, c->hCursors, &grewL))) return r;
-        if (haveTrace && (r = grow_if_overflowed(c, c->binsC, c->hCursors + 2, &grewC))) return r;
+        if (haveTrace && (r = grow_if_overflowed(c, c->binsC, c->hCursors + 4, &grewC))) return r;
+        // bit 1 of the flags word: a coarse tile ran out of flush segments (k_bin.cu kMaxSegs: > ~147k rectangles over one
+        // 64-pixel tile).  Growing the pools cannot fix that: report it instead of returning an incomplete frame.
+        const bool segL = c->voxelized && (c->hCursors[2] & 2u), segC = haveTrace && (c->hCursors[6] & 2u);
+        if (segL || segC) {
+            if (segL) { CRN_CUDA(c, cudaMemsetAsync(c->binsL.cursors + 2, 0, sizeof(uint32_t), c->lightStream)); c->hCursors[2] = 0; }
+            if (segC) { CRN_CUDA(c, cudaMemsetAsync(c->binsC.cursors + 2, 0, sizeof(uint32_t), c->stream)); c->hCursors[6] = 0; }
+            return fail(c, CRN_ERR_UNSUPPORTED, "more billboards overlap one 64-pixel tile than the binning pass can stage (%s pass); the frame is incomplete",
+                        segL ? "light" : "camera");
+        }
         if (!grewL && !grewC) return CRN_OK;
         if (grewL && !slabNotShippedYet && c->z1 >= 0 && !(c->z0 == 0 && c->z1 == c->vol.dimension)) {
             // the truncated slab has already been shipped to the other ranks: this library cannot redo the exchange
@@ -1272,6 +1291,10 @@ int crn_wait_images(crn_ctx *c) {
         if (!bins[p]->cursors) continue;
         uint32_t cur[4] = {0, 0, 0, 0};
         CRN_CUDA(c, cudaMemcpy(cur, bins[p]->cursors, sizeof cur, cudaMemcpyDeviceToHost));
+        if (cur[2] & 2u) {
+            CRN_CUDA(c, cudaMemset(bins[p]->cursors + 2, 0, sizeof(uint32_t)));
+            return fail(c, CRN_ERR_UNSUPPORTED, "more billboards overlap one 64-pixel tile than the binning pass can stage; the asynchronous frames are incomplete");
+        }
         if (cur[2]) {
             overflow = true;
             CRN_CUDA(c, cudaMemset(bins[p]->cursors + 2, 0, sizeof(uint32_t)));
@@ -1473,7 +1496,7 @@ int crn_read_bins(crn_ctx *c, int32_t which, int32_t *tiles_x, int32_t *tiles_y,
     if (total) *total = tot;
     if (counts) for (size_t t = 0; t < tiles; t++) counts[t] = (int32_t)cnt[t];
     if (entries && tot) {
-        const uint32_t cur = c->hCursors[which == 0 ? 1 : 3];
+        const uint32_t cur = c->hCursors[which == 0 ? 1 : 5];
         std::vector<uint32_t> list(cur);
         CRN_CUDA(c, cudaMemcpy(list.data(), b.tileList, (size_t)cur * 4, cudaMemcpyDeviceToHost));
         std::vector<BoardRec> rec(std::max(c->nBoards, 1));
@@ -1492,7 +1515,7 @@ int crn_get_trace_stats(crn_ctx *c, crn_trace_stats *out) {
     CRN_CUDA(c, cudaStreamSynchronize(c->stream));
     CRN_CUDA(c, cudaStreamSynchronize(c->copyStream));
     out->fragments = c->hStats[0]; out->coneSamples = c->hStats[1]; out->noiseSamples = c->hStats[2];
-    out->binEntries = c->hCursors[3];
+    out->binEntries = c->hCursors[5];
     out->coneSamplesSkipped = c->hStats[3];
     out->bakedFetches = c->hStats[5];
     out->filteredFetches = c->hStats[4] + c->hStats[5] + c->hStats[2];      // textureLod cone fetches + baked cone fetches + noise taps

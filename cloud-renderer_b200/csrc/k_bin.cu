@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(kBinThreads) bin_kernel(BinArgs a) {
                     const uint32_t sb = atomicAdd(&a.cursors[0], buf);
                     const uint32_t k2 = sSegs;
                     if (k2 < kMaxSegs && (uint64_t)sb + buf <= a.coarseCap) { sSegBase[k2] = sb; sSegCnt[k2] = buf; sSegs = k2 + 1; }
-                    else { sBad = 1; atomicOr(&a.cursors[2], 1u); }           // sticky: survives until the host clears it
+                    else { sBad = 1; atomicOr(&a.cursors[2], k2 >= kMaxSegs ? 2u : 1u); }   // sticky until the host clears it; bit 1: segment table full (not fixable by growing the pool)
                 }
                 __syncthreads();                                   // buffer + segment visible
                 const uint32_t segBase = sBad ? 0u : sSegBase[sSegs - 1];

@@ -680,7 +680,16 @@ int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol
     const int grid = b.tilesX * b.tilesY * (256 / kTraceThreads);
     const bool gate = bitsA != nullptr;
     // the reference's configuration: see trace_fast_kernel
-    const bool fast = useTex && !gate && !tp.stats && tp.active && tp.p.numOctaves == 4 && tp.noiseDim == 32 && tp.p.doNoiseSample &&
+    // The fast variant takes floor() of the noise z coordinate by adding 1.5 * 2^23, valid for |z| < 2^22 texels.  z is
+    // (world / adjustSize * freq + offset) * 32; the host does not know the billboard positions, so it bounds |world| by
+    // 4x the volume's extent from the origin (+64): billboards further out than that need the generic variant
+    // (CRN_NO_FAST=1), which uses floorf.
+    float extent = 0.0f;
+    for (int k = 0; k < 2; k++) extent = fmaxf(extent, fmaxf(fabsf(vol.xB[k]), fmaxf(fabsf(vol.yB[k]), fabsf(vol.zB[k]))));
+    float zmax = 0.0f;
+    for (int o = 0; o < 4; o++) zmax = fmaxf(zmax, (4.0f * extent + 64.0f) / fmaxf(fabsf(tp.p.adjustSize), 1e-20f) * fabsf(tp.octFreqZ[o]) + fabsf(tp.octBiasZ[o]));
+    const bool zOk = zmax < 2097152.0f;
+    const bool fast = zOk && useTex && !gate && !tp.stats && tp.active && tp.p.numOctaves == 4 && tp.noiseDim == 32 && tp.p.doNoiseSample &&
                       tp.p.doConeTrace && !tp.p.showQuad && !cam.ortho && tp.nBaked <= kFastBaked && vol.texelBytes <= 4 && !getenv("CRN_NO_FAST");
     if (gate) {                                                   // opt-in paper variant: stats variant only when asked
         if (useTex && tp.stats) trace_kernel<true, true, true><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, *ts);

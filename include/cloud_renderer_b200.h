@@ -164,7 +164,7 @@ typedef struct crn_timings {
 /* ---- lifetime --------------------------------------------------------------------- */
 /* `stream` is a cudaStream_t (or NULL for a private non-blocking stream). One ctx per
  * (device, stream); calls on a ctx are serialised by the caller. */
-int  crn_create(int device, void *stream, crn_ctx **out);
+int  crn_create(int device, void *stream, crn_ctx **out);   /* note: every crn_* call leaves `device` current (cudaSetDevice) on the calling thread */
 void crn_destroy(crn_ctx *ctx);
 /* message for the last non-OK status on this ctx (ctx may be NULL: last create error) */
 const char *crn_last_error(const crn_ctx *ctx);

@@ -222,7 +222,7 @@ public:
     void coneTrace(CloudVolume *volume) {                // src/Shaders/ConeTraceShader.cpp:15-82
         if (!doConeTrace && !doNoiseSample && !showQuad) return;
         crn_ctx *c = volume->ctx;
-        if (!noiseUploaded) { check(c, crn_set_noise(c, noise.data(), noiseDim)); noiseUploaded = true; }
+        if (noiseUploadedTo != c) { check(c, crn_set_noise(c, noise.data(), noiseDim)); noiseUploadedTo = c; }   // per context: a second CloudVolume gets its own copy
         crn_camera cam;
         for (int i = 0; i < 16; i++) { cam.P[i] = Camera::getP().m[i]; cam.V[i] = Camera::getV().m[i]; }
         const vec3 p = Camera::getPosition();
@@ -276,7 +276,7 @@ private:
     }
     std::vector<int8_t> noise;
     int noiseDim = 0;
-    bool noiseUploaded = false;
+    const crn_ctx *noiseUploadedTo = nullptr;
 };
 
 } // namespace crn

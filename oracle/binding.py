@@ -309,3 +309,69 @@ def ref_billboard_vertex(P, V, volume_position, vert, board_position, board_scal
                                    _f(*board_position), C.c_float(board_scale), glpos, fpos, fnor, ftex, cen, C.byref(sc))
     return dict(gl_Position=np.array(glpos[:], np.float32), fragPos=np.array(fpos[:], np.float32), fragNor=np.array(fnor[:], np.float32),
                 fragTex=np.array(ftex[:], np.float32), center=np.array(cen[:], np.float32), scale=sc.value)
+
+
+# ---- the paper variant's interior march (oracle) and the reference shader with the march switched back on -------------
+def first_voxelize_march(scene, frag_pos, center, radius, cap=1024):
+    """-> (n, idx[n,3]) in-range image stores of the march for one fragment, n = -1 on discard"""
+    s = _scene_struct(scene)
+    idx = (C.c_int32 * (3 * cap))()
+    n = lib().orc_first_voxelize_march(C.byref(s), _f(*frag_pos), _f(*center), C.c_float(radius), idx, cap)
+    return n, np.array(idx[:3 * max(0, min(n, cap))], dtype=np.int32).reshape(-1, 3)
+
+
+def ref_first_voxelize_paper_fragment(vol, frag_pos, frag_nor, center, radius, near_plane, clip, cap=1024):
+    f = np.float32
+    xb = [f(vol.position[0]) + f(vol.xBounds[k]) for k in range(2)]
+    yb = [f(vol.position[1]) + f(vol.yBounds[k]) for k in range(2)]
+    zb = [f(vol.position[2]) + f(vol.zBounds[k]) for k in range(2)]
+    d = f(vol.dimension)
+    step = min(f(f(vol.xBounds[1]) - f(vol.xBounds[0])) / d, f(f(vol.yBounds[1]) - f(vol.yBounds[0])) / d, f(f(vol.zBounds[1]) - f(vol.zBounds[0])) / d)
+    idx, col, dep = (C.c_int * (3 * cap))(), (C.c_float * 4)(), C.c_float()
+    n = ref_lib().ref_first_voxelize_paper_fragment(_f(*frag_pos), _f(*frag_nor), _f(*center), C.c_float(radius), _f(*near_plane), C.c_float(clip),
+                                                    vol.dimension, _f(*xb), _f(*yb), _f(*zb), C.c_float(step), idx, cap, col, C.byref(dep))
+    return n, np.array(idx[:3 * max(0, min(n, cap))], dtype=np.int32).reshape(-1, 3), np.array(col[:], dtype=np.float32), dep.value
+
+
+# ---- the reference's HOST code compiled from /root/reference/src (oracle/ref_glsl/ref_host.cpp) -----------------------
+def ref_host_sun_update(volpos, xb, yb, zb, sunpos):
+    V, P, n, fa, clip = (C.c_float * 16)(), (C.c_float * 16)(), (C.c_float * 3)(), (C.c_float * 3)(), C.c_float()
+    ref_lib().ref_host_sun_update(_f(*volpos), _f(*xb), _f(*yb), _f(*zb), _f(*sunpos), V, P, n, fa, C.byref(clip))
+    return dict(V=np.array(V[:], np.float32), P=np.array(P[:], np.float32), nearPlane=np.array(n[:], np.float32),
+                farPlane=np.array(fa[:], np.float32), clipDistance=np.float32(clip.value))
+
+
+def ref_host_sun_defaults():
+    p, i, o, ir, orr = (C.c_float * 3)(), (C.c_float * 3)(), (C.c_float * 3)(), C.c_float(), C.c_float()
+    ref_lib().ref_host_sun_defaults(p, i, o, C.byref(ir), C.byref(orr))
+    return dict(position=np.array(p[:], np.float32), innerColor=np.array(i[:], np.float32), outerColor=np.array(o[:], np.float32),
+                innerRadius=ir.value, outerRadius=orr.value)
+
+
+def ref_host_camera_update(width, height, position, phi, theta):
+    P, V, l = (C.c_float * 16)(), (C.c_float * 16)(), (C.c_float * 3)()
+    ref_lib().ref_host_camera_update(int(width), int(height), _f(*position), C.c_double(phi), C.c_double(theta), P, V, l)
+    return dict(P=np.array(P[:], np.float32), V=np.array(V[:], np.float32), lookAt=np.array(l[:], np.float32))
+
+
+def ref_host_sort_boards(pos, scale, volpos, point):
+    p = np.array(pos, dtype=np.float32, order="C", copy=True)
+    s = np.array(scale, dtype=np.float32, order="C", copy=True)
+    ref_lib().ref_host_sort_boards(C.c_void_p(p.ctypes.data), C.c_void_p(s.ctypes.data), len(s), _f(*volpos), _f(*point))
+    return p, s
+
+
+def ref_host_voxel_index(dim, volpos, xb, yb, zb, index):
+    ijk, w, vs = (C.c_int * 3)(), (C.c_float * 3)(), (C.c_float * 3)()
+    ref_lib().ref_host_voxel_index(int(dim), _f(*volpos), _f(*xb), _f(*yb), _f(*zb), int(index), ijk, w, vs)
+    return np.array(ijk[:], np.int32), np.array(w[:], np.float32), np.array(vs[:], np.float32)
+
+
+def ref_host_noise_normals(alpha):
+    """ConeTraceShader::initNoiseMap's normal loop on a texture with the given alpha channel -> rgba[dim^3,4] int8"""
+    alpha = np.ascontiguousarray(alpha, dtype=np.int8)
+    dim = round(alpha.size ** (1.0 / 3.0))
+    rgba = np.zeros((alpha.size, 4), dtype=np.int8)
+    rgba[:, 3] = alpha
+    ref_lib().ref_host_noise_normals(C.c_void_p(rgba.ctypes.data), dim)
+    return rgba

@@ -486,6 +486,19 @@ inline void blend(float dst[4], const float src_in[4], bool quantize8) {
 // C entry points (ctypes-friendly).  Struct types come from include/cloud_renderer_b200.h
 // so that the oracle and the library are driven with byte-identical inputs.
 // =================================================================================
+/* res/first_voxelize.glsl:53-58 (commented out as shipped, live in paper/tex/voxelization.tex:13-27): walk the chord of
+ * the sphere under this fragment from the far side towards the light in steps of stepSize, one image store per step.
+ * Pinned against the shader itself compiled with those lines switched back on (oracle/ref_glsl: first_voxelize_paper). */
+template <class Store>
+static inline void paper_march(const VolumeUniforms &vu, int D, vec3 fragPos, vec3 dir, float dist, Store &&store) {
+    vec3 start = fragPos - dir * dist;
+    for (float s = 0.0f; s < 2.0f * dist; s += vu.stepSize) {
+        vec3 f = voxel_lerp(vu, start + dir * s);
+        if (!(f.x > -1.0f && f.x < (float)D && f.y > -1.0f && f.y < (float)D && f.z > -1.0f && f.z < (float)D)) continue;   // GL drops the store
+        store((int)f.x, (int)f.y, (int)f.z);
+    }
+}
+
 extern "C" {
 
 typedef struct orc_scene {
@@ -618,6 +631,7 @@ void orc_build_noise(const int8_t *alpha, int32_t dim, int8_t *rgba) {
  * instance and a clamped depth of 1 never lands; ivec3() truncates toward zero;
  * imageStore outside [0,D)^3 is dropped (GL 4.4 §8.26). */
 static void voxelize_impl(const orc_scene *sc, float *posmap_out, float *depth_out, uint8_t *level0, uint8_t *alpha0);
+
 void orc_voxelize(const orc_scene *sc, float *posmap_out, float *depth_out, uint8_t *level0) {
     voxelize_impl(sc, posmap_out, depth_out, level0, nullptr);
 }
@@ -662,15 +676,8 @@ static void voxelize_impl(const orc_scene *sc, float *posmap_out, float *depth_o
                 if (sphereContrib < 0.01f) continue;            // discard
                 vec3 dir = lb.nrm;
                 float dist = radius * sphereContrib;
-                if (alpha0) {                                   // res/first_voxelize.glsl:53-58 (commented out as shipped)
-                    vec3 start = fragPos - dir * dist;
-                    for (float s = 0.0f; s < 2.0f * dist; s += vu.stepSize) {
-                        vec3 f = voxel_lerp(vu, start + dir * s);
-                        if (!(f.x > -1.0f && f.x < (float)D && f.y > -1.0f && f.y < (float)D && f.z > -1.0f && f.z < (float)D)) continue;
-                        // every thread stores the same constant: the race is benign (and is the shader's own)
-                        alpha0[((size_t)(int)f.z * D + (int)f.y) * D + (int)f.x] = 255;
-                    }
-                }
+                if (alpha0)                                     // every thread stores the same constant: the race is benign (and is the shader's own)
+                    paper_march(vu, D, fragPos, dir, dist, [&](int x, int y, int z) { alpha0[((size_t)z * D + y) * D + x] = 255; });
                 vec3 worldPos = fragPos + dir * dist;
                 float d = distance(nearP, worldPos) / clip;
                 d = saturate(d);
@@ -880,6 +887,24 @@ int32_t orc_first_voxelize_fragment(const orc_scene *sc, const float fragPos[3],
     worldPos[0] = wp.x; worldPos[1] = wp.y; worldPos[2] = wp.z;
     *depth = distance(v3(sd.nearPlane), wp) / sd.clipDistance;
     return 1;
+}
+
+/* The image stores of the paper variant's interior march for one fragment of first_voxelize.glsl at an explicit fragPos
+ * (in-range stores only, in march order); returns their number, at most `cap` are written to idx_out (3 ints each). */
+int32_t orc_first_voxelize_march(const orc_scene *sc, const float fragPos[3], const float center[3], float radius, int32_t *idx_out, int32_t cap) {
+    crn_sun_derived sd;
+    orc_sun_update(&sc->vol, &sc->sun, &sd);
+    ViewBasis lb = make_basis(sd.P, sd.V);
+    VolumeUniforms vu = volume_uniforms(sc->vol);
+    float s = distance(v3(center), v3(fragPos)) / radius;
+    s = sqrtf(fmaxf(0.0f, 1.0f - s * s));
+    if (s < 0.01f) return -1;
+    int32_t n = 0;
+    paper_march(vu, sc->vol.dimension, v3(fragPos), lb.nrm, radius * s, [&](int x, int y, int z) {
+        if (n < cap) { idx_out[3 * n] = x; idx_out[3 * n + 1] = y; idx_out[3 * n + 2] = z; }
+        n++;
+    });
+    return n;
 }
 
 /* The 9 voxel indices second_voxelize.glsl stores for one position-map texel; -1 marks a

@@ -166,12 +166,12 @@ inline vec4 texture(const sampler3D &s, vec3 uvw) { float o[4]; s.fetch(s.user, 
 inline vec4 textureLod(const sampler3D &s, vec3 uvw, float lod) { float o[4]; s.fetch(s.user, uvw.x, uvw.y, uvw.z, lod, 1, o); return vec4(o[0], o[1], o[2], o[3]); }
 struct image3D {
     int n;                      // stores recorded so far
-    int idx[64][3];
-    float val[64][4];
+    int idx[1024][3];           // (the paper variant's first-pass march stores one voxel per step of the chord)
+    float val[1024][4];
 };
 struct image2D { const float *texels; int width, height; };
 inline void imageStore(image3D &img, ivec3 p, vec4 v) {
-    if (img.n < 64) { img.idx[img.n][0] = p.x; img.idx[img.n][1] = p.y; img.idx[img.n][2] = p.z;
+    if (img.n < 1024) { img.idx[img.n][0] = p.x; img.idx[img.n][1] = p.y; img.idx[img.n][2] = p.z;
                       img.val[img.n][0] = v.x; img.val[img.n][1] = v.y; img.val[img.n][2] = v.z; img.val[img.n][3] = v.w; img.n++; }
 }
 inline void imageStore(image3D &img, ivec3 p, ivec4 v) { imageStore(img, p, vec4((float)v.x, (float)v.y, (float)v.z, (float)v.w)); }

@@ -29,6 +29,11 @@ COMMON_BUILTINS
 extern vec3 fragPos, fragNor, center; extern float scale; extern vec3 lightNearPlane; extern float clipDistance;
 extern int voxelDim; extern vec2 xBounds, yBounds, zBounds; extern float stepSize; extern vec4 color;
 }
+namespace first_voxelize_paper {   // res/first_voxelize.glsl with lines 54-58 un-commented (build_ref.sh)
+COMMON_BUILTINS
+extern vec3 fragPos, fragNor, center; extern float scale; extern vec3 lightNearPlane; extern float clipDistance;
+extern image3D volume; extern int voxelDim; extern vec2 xBounds, yBounds, zBounds; extern float stepSize; extern vec4 color;
+}
 namespace second_voxelize {     // res/second_voxelize.glsl
 COMMON_BUILTINS
 extern image3D volume; extern int voxelDim; extern vec2 xBounds, yBounds, zBounds; extern float stepSize; extern image2D positionMap;
@@ -102,6 +107,27 @@ int ref_first_voxelize_fragment(const float fragPos[3], const float fragNor[3], 
     color[0] = S::color.x; color[1] = S::color.y; color[2] = S::color.z; color[3] = S::color.w;
     *depth = S::gl_FragDepth;
     return S::gl_Discarded ? 0 : 1;
+}
+
+// first_voxelize.glsl main() with its interior march switched back on: the image stores it issues, in order (count
+// returned, -1 on discard; at most `cap` written), plus the colour / depth outputs
+int ref_first_voxelize_paper_fragment(const float fragPos[3], const float fragNor[3], const float center[3], float scale,
+                                      const float lightNearPlane[3], float clipDistance, int voxelDim, const float xB[2], const float yB[2],
+                                      const float zB[2], float stepSize, int *idx_out, int cap, float color[4], float *depth) {
+    namespace S = first_voxelize_paper;
+    S::fragPos = v3(fragPos); S::fragNor = v3(fragNor); S::center = v3(center); S::scale = scale;
+    S::lightNearPlane = v3(lightNearPlane); S::clipDistance = clipDistance;
+    S::volume.n = 0;
+    S::voxelDim = voxelDim; S::xBounds = vec2(xB[0], xB[1]); S::yBounds = vec2(yB[0], yB[1]); S::zBounds = vec2(zB[0], zB[1]); S::stepSize = stepSize;
+    S::color = vec4(0.0f); S::gl_FragDepth = 0.0f; S::gl_Discarded = false;
+    S::shader_main();
+    if (S::gl_Discarded) return -1;
+    for (int i = 0; i < S::volume.n && i < cap; i++) {
+        idx_out[3 * i] = S::volume.idx[i][0]; idx_out[3 * i + 1] = S::volume.idx[i][1]; idx_out[3 * i + 2] = S::volume.idx[i][2];
+    }
+    color[0] = S::color.x; color[1] = S::color.y; color[2] = S::color.z; color[3] = S::color.w;
+    *depth = S::gl_FragDepth;
+    return S::volume.n;
 }
 
 // second_voxelize.glsl main() on one position-map texel: the image stores it issues (count returned)

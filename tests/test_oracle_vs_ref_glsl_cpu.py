@@ -90,3 +90,22 @@ def test_golden_vectors_are_current(pkg, scenes, ref):
     for r in G["conetrace_1"][:40]:
         ok, col = orc.ref_conetrace_fragment(s, u, chain, r[0:3], back / r[8], r[3:5], r[5:8], r[8])
         assert ok == bool(r[9]) and np.array_equal(col, r[10:14])
+
+
+def test_host_golden_vectors_are_current(pkg, scenes, ref):
+    """tests/golden/ref_host_vectors.npz is what the reference's compiled HOST code produces today (src/Sun.hpp,
+    src/Camera.cpp, src/CloudVolume.cpp, src/Shaders/ConeTraceShader.cpp through oracle/ref_glsl/host_shim)"""
+    import os
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_host_vectors.npz"))
+    orc = ref
+    for r in G["sun_update"][:10]:
+        o = orc.ref_host_sun_update(r[0:3], r[3:5], r[5:7], r[7:9], r[9:12])
+        got = np.concatenate([o["V"], o["P"], o["nearPlane"], o["farPlane"], [o["clipDistance"]]])
+        assert np.array_equal(got, r[12:])
+    for r, (phi, theta) in list(zip(G["camera_update"], G["camera_angles"]))[:10]:
+        o = orc.ref_host_camera_update(int(r[0]), int(r[1]), r[2:5], phi, theta)
+        assert np.array_equal(o["P"], r[5:21]) and np.array_equal(o["V"], r[21:37]) and np.array_equal(o["lookAt"], r[37:40])
+    a, b, pts = G["sort_1_in"], G["sort_1_out"], G["sort_1_pts"]
+    p, s = orc.ref_host_sort_boards(a[:, :3], a[:, 3], pts[:3], pts[3:])
+    assert np.array_equal(p, b[:, :3]) and np.array_equal(s, b[:, 3])
+    assert np.array_equal(orc.ref_host_noise_normals(G["noise_16_alpha"]), G["noise_16_rgba"])
