@@ -179,6 +179,7 @@ struct crn_ctx {
     struct BakeKey { uint64_t gen; int nTex; int level0[kMaxBakedTex]; float frac[kMaxBakedTex]; int n[kMaxBakedTex]; } bakeKey{};
     struct CodeKey { uint64_t gen; int G, nGroups; float height[kCodeGroups]; int level[kCodeGroups]; float light[3]; float bounds[6]; } codeKey{};
     bool bakeValid = false, codeValid = false;
+    uint64_t boardsGen = 0, codeBoardsGen = ~0ull;   // bumped whenever the billboard arrays change
 
     // pipelined read-back (crn_cone_trace_async): second image buffer, copy stream, frame/copy events
     DevBuf image2;
@@ -474,6 +475,13 @@ int build_cone_accel(crn_ctx *c, TraceParams &tp) {
         }
     }
     for (int b = 0; b < tp.nBaked; b++) tp.baked[b].tex = (unsigned long long)c->ts.baked[tp.baked[b].tex];
+    return CRN_OK;
+}
+
+// the need codes are only computed inside the world bounding box of this frame's billboards, which the camera-side
+// prep kernel produces: this runs after that kernel (the caller's stream has waited for the side stream)
+int build_need_codes(crn_ctx *c, TraceParams &tp, const uint32_t *worldBox) {
+    int r;
     if (tp.codeDim > 0) {
         const size_t cells = (size_t)tp.codeDim * tp.codeDim * tp.codeDim;
         if ((r = reserve(c, c->needCode, cells))) return r;
@@ -483,9 +491,11 @@ int build_cone_accel(crn_ctx *c, TraceParams &tp) {
         for (int i = 0; i < 3; i++) k.light[i] = tp.lightPos[i];
         const float b[6] = {c->vparams.xB[0], c->vparams.xB[1], c->vparams.yB[0], c->vparams.yB[1], c->vparams.zB[0], c->vparams.zB[1]};
         std::memcpy(k.bounds, b, sizeof b);
-        if (!c->codeValid || std::memcmp(&k, &c->codeKey, sizeof k) != 0) {
-            c->launches += launch_need_code(c->stream, c->vparams, tp, (const uint32_t *)c->mask.p, (uint8_t *)c->needCode.p);
-            c->codeKey = k; c->codeValid = true;
+        // (the box changes with the billboards, which the key cannot see: rebuilt every frame unless the billboards are the
+        //  ones of the last build)
+        if (!c->codeValid || c->codeBoardsGen != c->boardsGen || std::memcmp(&k, &c->codeKey, sizeof k) != 0) {
+            c->launches += launch_need_code(c->stream, c->vparams, tp, (const uint32_t *)c->mask.p, worldBox, (uint8_t *)c->needCode.p);
+            c->codeKey = k; c->codeValid = true; c->codeBoardsGen = c->boardsGen;
         }
     }
     return CRN_OK;
@@ -749,7 +759,6 @@ int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
     if (c->statsOn) cudaMemsetAsync(dStats, 0, 8 * sizeof(unsigned long long), st);
     if (c->timingOn) cudaEventRecord(c->evT[2], st);                // the cone acceleration data is part of the trace stage
     if ((r = build_cone_accel(c, tp))) return r;
-    if (c->timingOn) cudaEventRecord(c->evT[1], st);
     // ---- camera-side set-up on the side stream: after the billboard upload and after the previous trace (which reads
     //      the same records / bins), concurrently with whatever voxelize work is still queued on the main stream
     cudaStream_t ax = c->auxStream;
@@ -773,7 +782,8 @@ int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
     if (c->timingOn) cudaEventRecord(c->evAuxT[2], ax);
     cudaEventRecord(c->evAuxDone, ax);
     cudaStreamWaitEvent(st, c->evAuxDone, 0);
-    if (c->timingOn) cudaEventRecord(c->evT[0], st);
+    if ((r = build_need_codes(c, tp, n > 0 ? sort_tmp_world_box(c->sortTmpC.p, (int)nn) : nullptr))) return r;
+    if (c->timingOn) { cudaEventRecord(c->evT[1], st); cudaEventRecord(c->evT[0], st); }
     c->launches += launch_trace(st, cam, c->vparams, tp, (const BoardRec *)c->recC.p, c->binsC, (const uint32_t *)c->bits.p,
                                 (const uint8_t *)c->chain.p, c->vol.format == CRN_VOLUME_RG8 ? (const uint32_t *)c->bitsA.p : nullptr,
                                 (const uint8_t *)c->chainA.p, (const int8_t *)c->noise.p, useTex ? &c->ts : nullptr,
@@ -936,6 +946,7 @@ int crn_set_volume(crn_ctx *c, const crn_volume_desc *d) {
     int r = check_volume(c, d); if (r) return r;
     if (c->haveVol && (c->vol.dimension != d->dimension || c->vol.levels != d->levels || c->vol.format != d->format)) { c->voxelized = false; c->z1 = -1; c->z0 = 0; }
     c->vol = *d; c->haveVol = true;
+    c->boardsGen++;                      // position / fluffiness move the spheres
     return CRN_OK;
 }
 
@@ -958,6 +969,7 @@ int crn_set_billboards(crn_ctx *c, const float *positions3, const float *scales,
     if (mem == CRN_MEM_DEVICE && count) CRN_CUDA(c, cudaStreamWaitEvent(c->stream, c->evBoards, 0));
     c->nBoards = count;
     c->havePos0 = false;
+    c->boardsGen++;
     return CRN_OK;
 }
 
@@ -976,6 +988,7 @@ int crn_regenerate_billboards(crn_ctx *c, int32_t count, const float minOffset[3
     CRN_CUDA(c, cudaEventRecord(c->evBoards, up));
     c->nBoards = count;
     c->havePos0 = true;
+    c->boardsGen++;
     return CRN_OK;
 }
 
@@ -994,6 +1007,7 @@ int crn_animate_billboards(crn_ctx *c, double angle) {
                                         (float)std::sin(angle));
     CRN_CUDA(c, cudaGetLastError());
     CRN_CUDA(c, cudaEventRecord(c->evBoards, up));
+    c->boardsGen++;
     return CRN_OK;
 }
 

@@ -144,7 +144,8 @@ int launch_prep_sort(cudaStream_t st, const float *pos, const float *scale, int 
 size_t sort_tmp_bytes(int n);      // sortTmp must hold sort_tmp_bytes(n) + 16 bytes
 int launch_bin(cudaStream_t st, const BoardRect *rects, const int32_t *bounds, int n, int W, int H, Bins &b);
 int launch_tile_order(cudaStream_t st, const Bins &b, uint32_t *order);     // order[tilesX*tilesY]: longest lists first
-const int32_t *sort_tmp_bounds(const void *sortTmp, int n, int pass);   // rect bounds written by prep_kernel (pass 0 light, 1 camera)
+const int32_t *sort_tmp_bounds(const void *sortTmp, int n, int pass);
+const uint32_t *sort_tmp_world_box(const void *sortTmp, int n);         // camera pass: sortable bits of the spheres' world bounding box   // rect bounds written by prep_kernel (pass 0 light, 1 camera)
 int launch_voxelize(cudaStream_t st, const ViewParams &light, const VolumeParams &vol, const float nearPlane[3],
                     float clip, const BoardRec *recs, const float *lbSorted, const Bins &b, uint32_t *bits,
                     float4 *posmap, uint32_t *bitsA);
@@ -179,7 +180,7 @@ int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol
                  const uint32_t *bitsA, const uint8_t *chainA, const int8_t *noise, const TexSet *ts, const uint8_t *needCode, const uint32_t *tileOrder, void *image,
                  int format, unsigned long long *stats);
 int launch_bake_steps(cudaStream_t st, const VolumeParams &vol, const uint32_t *bits, const uint8_t *chain, const BakeTex *tex, int nTex);
-int launch_need_code(cudaStream_t st, const VolumeParams &vol, const TraceParams &tp, const uint32_t *mask, uint8_t *code);
+int launch_need_code(cudaStream_t st, const VolumeParams &vol, const TraceParams &tp, const uint32_t *mask, const uint32_t *worldBox, uint8_t *code);
 size_t skipmask_words(const VolumeParams &vol, uint32_t *off);
 int launch_skipmask(cudaStream_t st, const VolumeParams &vol, const uint32_t *bits, const uint8_t *chain, uint32_t *nz,
                     uint32_t *dil, uint32_t *mask, uint32_t *fill);

@@ -121,9 +121,12 @@ struct CodeArgs {
     int nGroups;
     CodeGroup g[kCodeGroups];
     const uint32_t *mask;
+    const uint32_t *worldBox;                 // sortable bits of the billboards' world bounding box (k_prep_sort.cu), or nullptr
     float lightPos[3], b0[3], range[3];
     uint8_t *code;
 };
+
+__device__ __forceinline__ float unsortable(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u); }
 
 __global__ void __launch_bounds__(256) need_code_kernel(const __grid_constant__ CodeArgs a) {
     const int G = a.G;
@@ -131,6 +134,16 @@ __global__ void __launch_bounds__(256) need_code_kernel(const __grid_constant__ 
     if (ix >= G || iy >= G) return;
     const uint32_t cell = ((uint32_t)iz * G + iy) * G + ix;
     const float invG = 1.0f / (float)G;
+    if (a.worldBox) {
+        // fragments start on the billboards' spheres: a cell that does not meet their bounding box is never looked up
+        const int ic[3] = {ix, iy, iz};
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float lo = unsortable(__ldg(a.worldBox + k)), hi = unsortable(__ldg(a.worldBox + 3 + k));
+            const float c0 = a.b0[k] + ((float)ic[k] - 0.01f) * invG * a.range[k], c1 = a.b0[k] + ((float)ic[k] + 1.01f) * invG * a.range[k];
+            if (fmaxf(c0, c1) < lo || fminf(c0, c1) > hi) return;
+        }
+    }
     const float half = 0.5f * invG * 1.001f + 1.0e-6f;           // half a cell, in normalized coordinates, with slack
     const float nc[3] = {((float)ix + 0.5f) * invG, ((float)iy + 0.5f) * invG, ((float)iz + 0.5f) * invG};
     float toL[3], hw2 = 0.0f, d2 = 0.0f;
@@ -229,7 +242,7 @@ int launch_bake_steps(cudaStream_t st, const VolumeParams &vol, const uint32_t *
     return 1;
 }
 
-int launch_need_code(cudaStream_t st, const VolumeParams &vol, const TraceParams &tp, const uint32_t *mask, uint8_t *code) {
+int launch_need_code(cudaStream_t st, const VolumeParams &vol, const TraceParams &tp, const uint32_t *mask, const uint32_t *worldBox, uint8_t *code) {
     CodeArgs a{};
     a.G = tp.codeDim;
     a.nGroups = std::min(tp.nGroups, kCodeGroups);
@@ -237,7 +250,7 @@ int launch_need_code(cudaStream_t st, const VolumeParams &vol, const TraceParams
         a.g[g].reach = tp.groups[g].height / (float)vol.dim; a.g[g].size = tp.groups[g].size; a.g[g].sizeF = (float)tp.groups[g].size;
         a.g[g].wpr = tp.groups[g].wpr; a.g[g].maskOff = tp.groups[g].maskOff;
     }
-    a.mask = mask; a.code = code;
+    a.mask = mask; a.code = code; a.worldBox = worldBox;
     a.b0[0] = vol.xB[0]; a.b0[1] = vol.yB[0]; a.b0[2] = vol.zB[0];
     a.range[0] = vol.xB[1] - vol.xB[0]; a.range[1] = vol.yB[1] - vol.yB[0]; a.range[2] = vol.zB[1] - vol.zB[0];
     for (int k = 0; k < 3; k++) a.lightPos[k] = tp.lightPos[k];

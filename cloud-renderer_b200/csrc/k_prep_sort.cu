@@ -68,6 +68,7 @@ struct PrepArgs {
     float *lb;
     uint32_t *range;          // [minL, maxL, minC, maxC] of the sortable key bits
     int32_t *bounds;          // [minI, maxI, minJ, maxJ] light, then camera: union of the unclipped rectangles
+    uint32_t *wbox;           // sortable bits of [min x, y, z of (centre - r) | max x, y, z of (centre + r)] over all billboards (camera pass)
 };
 
 __device__ __forceinline__ void warp_bounds(BoardRect q, bool valid, int32_t *b) {
@@ -82,6 +83,17 @@ __device__ __forceinline__ void warp_minmax(uint32_t u, bool valid, uint32_t *ra
     lo = __reduce_min_sync(0xFFFFFFFFu, lo);
     hi = __reduce_max_sync(0xFFFFFFFFu, hi);
     if ((threadIdx.x & 31) == 0) { atomicMin(&range[0], lo); atomicMax(&range[1], hi); }
+}
+
+// world-space bounding box of all spheres: every fragment's start position lies inside it (k_conebake.cu skips the rest)
+__device__ __forceinline__ void warp_box(float cx, float cy, float cz, float r, bool valid, uint32_t *wbox) {
+    const float c[3] = {cx, cy, cz};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const uint32_t lo = __reduce_min_sync(0xFFFFFFFFu, valid ? sortable(c[k] - r) : 0xFFFFFFFFu);
+        const uint32_t hi = __reduce_max_sync(0xFFFFFFFFu, valid ? sortable(c[k] + r) : 0u);
+        if ((threadIdx.x & 31) == 0) { atomicMin(&wbox[k], lo); atomicMax(&wbox[3 + k], hi); }
+    }
 }
 
 __global__ void __launch_bounds__(256) prep_kernel(PrepArgs a, ViewParams light, ViewParams cam) {
@@ -120,6 +132,7 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepArgs a, ViewParams light,
         // exact reverse of the draw order (far first, earlier instance first among equals)
         if (live) a.keyC[i] = ((uint64_t)sortable(d) << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)i);
         warp_minmax(sortable(d), live, a.range + 2);
+        warp_box(cx, cy, cz, r, live, a.wbox);
     }
 }
 
@@ -230,6 +243,10 @@ size_t sort_tmp_bytes(int n) {
     return 2 * (half > other ? half : other);
 }
 
+const uint32_t *sort_tmp_world_box(const void *sortTmp, int n) {
+    return reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(sortTmp) + sort_tmp_bytes(n)) + 12;
+}
+
 const int32_t *sort_tmp_bounds(const void *sortTmp, int n, int pass) {
     return reinterpret_cast<const int32_t *>(reinterpret_cast<const char *>(sortTmp) + sort_tmp_bytes(n)) + 4 + 4 * pass;
 }
@@ -251,8 +268,10 @@ int launch_prep_sort(cudaStream_t st, const float *pos, const float *scale, int 
     uint32_t *range = reinterpret_cast<uint32_t *>(sortTmp) + sort_tmp_bytes(n) / 4;      // 4 words after the scratch
     pa.range = range;
     pa.bounds = reinterpret_cast<int32_t *>(range + 4);
-    static const uint32_t kRangeInit[12] = {0xFFFFFFFFu, 0u, 0xFFFFFFFFu, 0u, 0x7FFFFFFFu, 0xFFFFFFFFu, 0x7FFFFFFFu, 0xFFFFFFFFu,
-                                            0x7FFFFFFFu, 0xFFFFFFFFu, 0x7FFFFFFFu, 0xFFFFFFFFu};
+    pa.wbox = range + 12;
+    static const uint32_t kRangeInit[18] = {0xFFFFFFFFu, 0u, 0xFFFFFFFFu, 0u, 0x7FFFFFFFu, 0xFFFFFFFFu, 0x7FFFFFFFu, 0xFFFFFFFFu,
+                                            0x7FFFFFFFu, 0xFFFFFFFFu, 0x7FFFFFFFu, 0xFFFFFFFFu,
+                                            0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
     cudaMemcpyAsync(range, kRangeInit, sizeof kRangeInit, cudaMemcpyHostToDevice, st);
     const int blocks = (n + 255) / 256;
     prep_kernel<<<blocks, 256, 0, st>>>(pa, light, cam);
