@@ -175,6 +175,8 @@ struct crn_ctx {
     BakeTex bakePlan[kMaxBakedTex] = {};
     int nBakePlan = 0;
     DevBuf needCode;
+    DevBuf segPartial, segArrived;       // small frames: per-segment partial composites of the cut tile lists (k_trace.cu)
+    int segOverride = -1;                // CRN_TRACE_SEGMENTS=n: force the segment count (experiments)
     uint64_t volumeGen = 0;              // bumped whenever the chain changes (voxelize, finish_mips)
     struct BakeKey { uint64_t gen; int nTex; int level0[kMaxBakedTex]; float frac[kMaxBakedTex]; int n[kMaxBakedTex]; } bakeKey{};
     struct CodeKey { uint64_t gen; int G, nGroups; float height[kCodeGroups]; int level[kCodeGroups]; float light[3]; float bounds[6]; } codeKey{};
@@ -733,6 +735,19 @@ int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
 
     TraceParams tp;
     build_trace_params(c, cam, &tp);
+    {   // small frames leave SMs idle behind the longest tile list: cut the lists (see trace_fast_kernel)
+        const size_t tiles = (size_t)c->binsC.tilesX * c->binsC.tilesY;
+        // measured trace ms at 1 / 2 / 4 segments: C1 (3600 tiles) 0.244 / 0.188 / 0.165, C2 (8160) 0.807 / 0.715 / 0.632,
+        // C3 (32400) 3.015 / 2.955 / 3.086, C4 (129600) 9.46 / 10.12 / 10.65; a rank of an interleaved trace owns 1/count of the tiles
+        const size_t active = tiles / (size_t)std::max(1, c->ilvCount);
+        tp.segCount = active <= 16384 ? 4 : active <= 65536 ? 2 : 1;
+        if (c->segOverride >= 1) tp.segCount = std::min(c->segOverride, 16);
+        tp.segMin = 6;
+        if (tp.segCount > 1) {
+            if ((r = reserve(c, c->segPartial, tiles * tp.segCount * 256 * sizeof(float4)))) return r;
+            if ((r = reserve(c, c->segArrived, tiles * 4 * sizeof(uint32_t)))) return r;      // zeroed by reserve, re-armed by the kernel
+        }
+    }
     cudaStream_t st = c->stream;
     bool readsBits = c->tp.sampler != CRN_SAMPLER_TEXTURE;          // the explicit sampler reads level 0 from the bits
     for (int i = 0; i < c->nBakePlan; i++) readsBits |= c->bakePlan[i].level0 == 0;    // ... and so does a level-0 bake
@@ -788,7 +803,8 @@ int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
                                 (const uint8_t *)c->chain.p, c->vol.format == CRN_VOLUME_RG8 ? (const uint32_t *)c->bitsA.p : nullptr,
                                 (const uint8_t *)c->chainA.p, (const int8_t *)c->noise.p, useTex ? &c->ts : nullptr,
                                 tp.codeDim > 0 ? (const uint8_t *)c->needCode.p : nullptr, (const uint32_t *)c->tileOrder.p,
-                                img.p, format, dStats);
+                                img.p, format, dStats, tp.segCount > 1 ? (float4 *)c->segPartial.p : nullptr,
+                                tp.segCount > 1 ? (uint32_t *)c->segArrived.p : nullptr);
     cudaEventRecord(c->evTraceEnd, st);
     c->traceEndValid = true;
     c->auxDoneValid = true;
@@ -860,6 +876,7 @@ int crn_create(int device, void *stream, crn_ctx **out) {
     for (auto &ev : c->evT) cudaEventCreate(&ev);
     crn_default_trace_params(&c->tp);
     if (const char *nb = getenv("CRN_NO_BAKE")) c->noBake = atoi(nb) != 0;
+    if (const char *sg = getenv("CRN_TRACE_SEGMENTS")) c->segOverride = atoi(sg);
     if (const char *pm = getenv("CRN_BIN_POOL_MIN")) { const long v = atol(pm); if (v > 0) c->poolMin = (size_t)v; }
     if ((e = cudaGetLastError()) != cudaSuccess) {
         crn_destroy(c);
@@ -877,7 +894,7 @@ void crn_destroy(crn_ctx *c) {
     if (c->auxStream) cudaStreamSynchronize(c->auxStream);
     if (c->lightStream) cudaStreamSynchronize(c->lightStream);
     DevBuf *bufs[] = {&c->exportTmp, &c->exportOut, &c->pos0, &c->bitsA, &c->chainA, &c->pos, &c->scale, &c->keyL, &c->keyC, &c->rankL, &c->rankC, &c->recTmpL, &c->recTmpC, &c->rectTmpL,
-                      &c->rectTmpC, &c->lbTmp, &c->recL, &c->recC, &c->rectL, &c->rectC, &c->lbSorted, &c->drawOrder, &c->bits,
+                      &c->rectTmpC, &c->lbTmp, &c->recL, &c->recC, &c->rectL, &c->rectC, &c->lbSorted, &c->drawOrder, &c->bits, &c->segPartial, &c->segArrived,
                       &c->chain, &c->noise, &c->posmap, &c->image, &c->image2, &c->misc, &c->maskNz, &c->maskDil, &c->mask, &c->sortTmp, &c->sortTmpC, &c->tileOrder};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     free_bins(c->binsL); free_bins(c->binsC);

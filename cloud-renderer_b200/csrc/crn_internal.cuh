@@ -115,6 +115,7 @@ struct TraceParams {
     int32_t noiseMask;                // noiseDim - 1 if noiseDim is a power of two, else -1
     int32_t nFine;                    // steps[0..nFine) are fetched with textureLod (grouped for the empty-space test)
     int32_t nBaked;                   // baked[0..nBaked) are the remaining steps, in step order
+    int32_t segCount, segMin;         // small frames: tile lists of >= segCount * segMin entries are cut into segCount depth segments (1: off)
     int32_t codeDim;                  // cells per axis of the need-code grid (0: no empty-space skipping)
     float codeDimF;
     FastConst f;
@@ -178,7 +179,7 @@ int launch_finish_mips(cudaStream_t st, const VolumeParams &vol, uint8_t *chain,
 int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol, const TraceParams &tp,
                  const BoardRec *recs, const Bins &b, const uint32_t *bits, const uint8_t *chain,
                  const uint32_t *bitsA, const uint8_t *chainA, const int8_t *noise, const TexSet *ts, const uint8_t *needCode, const uint32_t *tileOrder, void *image,
-                 int format, unsigned long long *stats);
+                 int format, unsigned long long *stats, float4 *segPartial, uint32_t *segArrived);
 int launch_bake_steps(cudaStream_t st, const VolumeParams &vol, const uint32_t *bits, const uint8_t *chain, const BakeTex *tex, int nTex);
 int launch_need_code(cudaStream_t st, const VolumeParams &vol, const TraceParams &tp, const uint32_t *mask, const uint32_t *worldBox, uint8_t *code);
 size_t skipmask_words(const VolumeParams &vol, uint32_t *off);

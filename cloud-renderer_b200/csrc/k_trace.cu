@@ -56,6 +56,8 @@ struct TraceArgs {
     float invDim;                 // 1 / voxelDim
     const uint8_t *code;          // need-code grid (k_conebake.cu): bit g = group g may contribute from this cell; or nullptr
     const uint32_t *order;        // launch order of the tiles, longest list first (k_bin.cu)
+    float4 *segPartial;           // small frames: (colour, alpha, transmittance) of every list segment, [tile][segment][256 pixels]
+    uint32_t *segArrived;         // ... and how many segments of a (tile, quarter) have finished
 };
 
 __device__ __forceinline__ float saturatef(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
@@ -185,7 +187,7 @@ __device__ __forceinline__ bool sun_fragment(const TraceParams &tp, const ViewPa
 }
 
 // kTex = false: explicit filtering (CRN_SAMPLER_EXPLICIT);  kTex = true: texture units (CRN_SAMPLER_TEXTURE)
-constexpr int kFastBaked = 8;         // the fast variant unrolls (and handles at most) this many baked steps
+constexpr int kFastBaked = 16;        // the fast variant unrolls (and handles at most) this many baked steps (32^3 / 64^3 volumes bake all 16)
 // resident CTAs per SM the kernel is compiled for (register cap = 65536 / 64 / MINB).  Measured at C3 (trace ms):
 // 12: 4.82, 14: 4.73, 16: 4.39, 18: 4.36, 20: 4.52, 24: 4.60 -> 16 (64 registers, no spills in the fast variant)
 #ifndef CRN_TRACE_MINB
@@ -485,12 +487,21 @@ __device__ __forceinline__ float4 tex_layer4(unsigned long long tex, int layer, 
     return t;
 }
 
-template <int NB>                      // number of baked cone steps (compile-time: no predication of the unused slots)
+// NB: number of baked cone steps (compile-time: no predication of the unused slots).
+// kSeg: small frames (1280x720: a few thousand tiles) do not fill 148 SMs and are bound by the ONE warp that walks the
+// longest list.  There the list of a tile is cut into tp.segCount contiguous depth segments, each composited on its own
+// by a separate CTA into (C_s, T_s); the last CTA to arrive merges them front to back: C = C_0 + T_0 C_1 + T_0 T_1 C_2 ...
+// Same fragments, same order; the sum is re-associated (differences of a few ulp), and the early ray termination only
+// sees its own segment's transmittance (still bounded by the cutoff).
+template <int NB, bool kSeg>
 __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_fast_kernel(const __grid_constant__ TraceArgs a, const __grid_constant__ ViewParams cam,
                                                     const __grid_constant__ TraceParams tp, const __grid_constant__ TexSet ts) {
     constexpr int kWarps = kTraceThreads / 32, kSplit = 8 / kWarps;
-    const int tile = (int)a.order[blockIdx.x / kSplit];
-    const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) + (blockIdx.x % kSplit) * kWarps;
+    const int S = kSeg ? tp.segCount : 1;
+    const int seg = kSeg ? (int)(blockIdx.x % S) : 0;
+    const int cta = kSeg ? (int)(blockIdx.x / S) : (int)blockIdx.x;           // (tile, quarter)
+    const int tile = (int)a.order[cta / kSplit];
+    const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) + (cta % kSplit) * kWarps;
     const int tx = tile % a.tilesX, ty = tile / a.tilesX;
     // 2x2-pixel quads: the texture unit works on groups of four consecutive lanes, and a disc edge leaves fewer
     // partially filled 2x2 blocks than 4x1 strips (measured at C3: trace 3.35 -> 3.30 ms)
@@ -499,7 +510,7 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_fast_kern
     const int py = ty * kTile + (warp >> 1) * 4 + ly;
     if (tp.ilvCount > 1 && (ty % tp.ilvCount) != tp.ilvIndex) return;
     const bool valid = px < cam.W && py < cam.H && py >= tp.row0 && py < tp.row1;
-    if (__all_sync(0xFFFFFFFFu, !valid)) return;
+    if (!kSeg && __all_sync(0xFFFFFFFFu, !valid)) return;           // (segmented: every thread stays for the barrier below)
 
     const float ndcx = ((float)px + 0.5f) / (float)cam.W * 2.0f - 1.0f;
     const float ndcy = ((float)py + 0.5f) / (float)cam.H * 2.0f - 1.0f;
@@ -510,8 +521,13 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_fast_kern
     const uint32_t *list = a.tileList + (cnt ? a.tileOff[tile] : 0);
     const float cutoff = tp.p.transmittanceCutoff;
     const float rx = cam.nrm[0], ry = cam.nrm[1], rz = cam.nrm[2];     // viewRay (res/conetrace_frag.glsl:138)
+    // this CTA's share of the list: short lists are not cut (segment 0 takes them whole, the other CTAs leave)
+    const int nSeg = (kSeg && cnt >= (uint32_t)(S * tp.segMin)) ? S : 1;
+    if (kSeg && seg >= nSeg) return;
+    const uint32_t eBegin = kSeg ? (uint32_t)((uint64_t)cnt * seg / nSeg) : 0u;
+    const uint32_t eEnd = kSeg ? (uint32_t)((uint64_t)cnt * (seg + 1) / nSeg) : cnt;
 
-    for (uint32_t e = 0; e < cnt; e++) {
+    for (uint32_t e = eBegin; e < eEnd; e++) {
         const bool live = valid && T > cutoff;
         if (__all_sync(0xFFFFFFFFu, !live)) break;                      // early ray termination, whole patch
         const uint32_t k = __ldg(list + e);
@@ -629,6 +645,26 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_fast_kern
         }
     }
 
+    if constexpr (kSeg) {
+        if (nSeg > 1) {
+            __shared__ uint32_t sLast;
+            float4 *part = a.segPartial + ((size_t)tile * S) * 256 + warp * 32 + lane;
+            __stcg(part + (size_t)seg * 256, make_float4(Cg, Ca, T, 0.0f));
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) sLast = atomicAdd(&a.segArrived[cta], 1u) == (uint32_t)(nSeg - 1) ? 1u : 0u;
+            __syncthreads();
+            if (!sLast) return;                                         // the last segment to finish merges all of them
+            __threadfence();
+            if (threadIdx.x == 0) a.segArrived[cta] = 0;                // re-arm for the next frame
+            Cg = 0.0f; Ca = 0.0f; T = 1.0f;
+            for (int s2 = 0; s2 < nSeg; s2++) {                         // front to back
+                const float4 p = __ldcg(part + (size_t)s2 * 256);
+                Cg = fmaf(T, p.x, Cg); Ca = fmaf(T, p.y, Ca); T *= p.z;
+            }
+        }
+    }
+
     if (valid) {
         // background = clear colour, then the sun pass blended over it
         float bg[4] = {tp.bg[0], tp.bg[1], tp.bg[2], tp.bg[3]};
@@ -660,7 +696,7 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_fast_kern
 int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol, const TraceParams &tp,
                  const BoardRec *recs, const Bins &b, const uint32_t *bits, const uint8_t *chain,
                  const uint32_t *bitsA, const uint8_t *chainA, const int8_t *noise, const TexSet *ts, const uint8_t *needCode, const uint32_t *tileOrder, void *image,
-                 int format, unsigned long long *stats) {
+                 int format, unsigned long long *stats, float4 *segPartial, uint32_t *segArrived) {
     TraceArgs a;
     a.vol = vol;
     a.recs = recs;
@@ -671,6 +707,7 @@ int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol
     a.image = image; a.format = format; a.stats = stats;
     a.code = (needCode && tp.p.skipEmptySpace && tp.codeDim > 0) ? needCode : nullptr;
     a.order = tileOrder;
+    a.segPartial = segPartial; a.segArrived = segArrived;
     a.invRange[0] = 1.0f / (vol.xB[1] - vol.xB[0]);
     a.invRange[1] = 1.0f / (vol.yB[1] - vol.yB[0]);
     a.invRange[2] = 1.0f / (vol.zB[1] - vol.zB[0]);
@@ -698,9 +735,13 @@ int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol
         else trace_kernel<false, false, true><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, none);
     }
     else if (fast) {
+        const bool segmented = tp.segCount > 1 && segPartial && segArrived;
+        const int gridF = segmented ? grid * tp.segCount : grid;
         switch (tp.nBaked) {
-#define CRN_FAST(NB) case NB: trace_fast_kernel<NB><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, *ts); break;
+#define CRN_FAST(NB) case NB: if (segmented) trace_fast_kernel<NB, true><<<gridF, kTraceThreads, 0, st>>>(a, cam, tp, *ts); \
+                              else trace_fast_kernel<NB, false><<<gridF, kTraceThreads, 0, st>>>(a, cam, tp, *ts); break;
             CRN_FAST(0) CRN_FAST(1) CRN_FAST(2) CRN_FAST(3) CRN_FAST(4) CRN_FAST(5) CRN_FAST(6) CRN_FAST(7) CRN_FAST(8)
+            CRN_FAST(9) CRN_FAST(10) CRN_FAST(11) CRN_FAST(12) CRN_FAST(13) CRN_FAST(14) CRN_FAST(15) CRN_FAST(16)
 #undef CRN_FAST
         }
     }
