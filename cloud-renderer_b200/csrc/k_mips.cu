@@ -18,7 +18,10 @@
 // Integer arithmetic throughout: results are bit-exact against the oracle.
 #include "crn_internal.cuh"
 
+#include <cuda.h>          // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include <algorithm>
+#include <cstdlib>
 
 namespace crn {
 
@@ -46,10 +49,13 @@ __device__ __forceinline__ uint32_t box8(uint32_t sum) { return (sum + 4u) >> 3;
 // value of a level-1 texel whose 2x2x2 block holds `cnt` occupied (255) voxels: (255*cnt+4)>>3
 __device__ __forceinline__ uint32_t level1_value(uint32_t cnt) { return cnt * 32u - (cnt > 4u ? 1u : 0u); }
 
-template <int WX>   // words per brick row: 1, 2 or 4
-__global__ void __launch_bounds__(256) mip_chain_kernel(MipArgs a) {
+// kTma (A/B variant, CRN_MIPS_TMA=1, WX = 4 only): the linear level-0 brick (128 x 16 x 16 bytes) is expanded into shared
+// memory and written with ONE 3-D TMA store (cp.async.bulk.tensor.3d.global.shared::cta) instead of 2048 st.global.v4
+template <int WX, bool kTma>   // words per brick row: 1, 2 or 4
+__global__ void __launch_bounds__(256) mip_chain_kernel(MipArgs a, const __grid_constant__ CUtensorMap tmL0) {
     constexpr int BX = WX * 32;
     __shared__ uint32_t sBits[256 * WX];                 // [row = z*16+y][word]
+    __shared__ __align__(128) uint8_t sL0[kTma ? 256 * BX : 16];      // [z][y][x], the TMA box
     __shared__ __align__(16) uint8_t sL1[(BX / 2) * 8 * 8];
     __shared__ uint8_t sL2[(BX / 4) * 4 * 4];
     __shared__ uint8_t sL3[(BX / 8) * 2 * 2];
@@ -87,8 +93,25 @@ __global__ void __launch_bounds__(256) mip_chain_kernel(MipArgs a) {
             uint4 o;
             o.x = spread4(h & 15u); o.y = spread4((h >> 4) & 15u); o.z = spread4((h >> 8) & 15u); o.w = spread4(h >> 12);
             const int y = row & 15, z = row >> 4;
-            if (a.writeLevel0) *reinterpret_cast<uint4 *>(l0 + ((size_t)(z0 + z) * D + (y0 + y)) * D + x0 + seg * 16) = o;
+            if (a.writeLevel0) {
+                if constexpr (kTma) *reinterpret_cast<uint4 *>(&sL0[row * BX + seg * 16]) = o;
+                else *reinterpret_cast<uint4 *>(l0 + ((size_t)(z0 + z) * D + (y0 + y)) * D + x0 + seg * 16) = o;
+            }
             if (a.useSurf) surf3Dwrite(o, a.surf[0], x0 + seg * 16, y0 + y, z0 + z);
+        }
+        if constexpr (kTma) {
+            if (a.writeLevel0) {
+                // make the generic-proxy writes to shared memory visible to the async proxy, then one thread issues the store
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncthreads();
+                if (tid == 0) {
+                    const uint32_t src = (uint32_t)__cvta_generic_to_shared(sL0);
+                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                                 :: "l"(reinterpret_cast<uint64_t>(&tmL0)), "r"(x0), "r"(y0), "r"(z0), "r"(src) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // sL0 is not reused, but the CTA must not retire under the copy
+                }
+            }
         }
     }
 
@@ -373,6 +396,24 @@ __global__ void __launch_bounds__(256) count_bits_kernel(const uint32_t *__restr
 
 } // namespace
 
+// tensor map of the linear level 0 (D^3 bytes, x fastest) with a 128 x 16 x 16 box, for the TMA-store variant
+static bool make_level0_tensor_map(CUtensorMap *tm, void *level0, int D) {
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                 const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return false;
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)D, (cuuint64_t)D};
+    const cuuint64_t strides[2] = {(cuuint64_t)D, (cuuint64_t)D * D};            // bytes, dimensions 1 and 2
+    const cuuint32_t box[3] = {128, 16, 16}, estr[3] = {1, 1, 1};
+    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, level0, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int launch_mips(cudaStream_t st, const VolumeParams &vol, const uint32_t *bits, uint8_t *chain, uint32_t *ticket,
                 bool writeLevel0, const TexSet *ts) {
     MipArgs a;
@@ -391,9 +432,15 @@ int launch_mips(cudaStream_t st, const VolumeParams &vol, const uint32_t *bits, 
         else mip_chain_f32_kernel<1><<<grid, 256, 0, st>>>(a);
         return 1;
     }
-    if (a.bx == 128) mip_chain_kernel<4><<<grid, 256, 0, st>>>(a);
-    else if (a.bx == 64) mip_chain_kernel<2><<<grid, 256, 0, st>>>(a);
-    else mip_chain_kernel<1><<<grid, 256, 0, st>>>(a);
+    CUtensorMap tm{};
+    static const bool wantTma = getenv("CRN_MIPS_TMA") && atoi(getenv("CRN_MIPS_TMA")) != 0;
+    if (wantTma && a.bx == 128 && a.writeLevel0 && make_level0_tensor_map(&tm, chain + vol.levelOff[0], vol.dim)) {
+        mip_chain_kernel<4, true><<<grid, 256, 0, st>>>(a, tm);
+        return 1;
+    }
+    if (a.bx == 128) mip_chain_kernel<4, false><<<grid, 256, 0, st>>>(a, tm);
+    else if (a.bx == 64) mip_chain_kernel<2, false><<<grid, 256, 0, st>>>(a, tm);
+    else mip_chain_kernel<1, false><<<grid, 256, 0, st>>>(a, tm);
     return 1;
 }
 
