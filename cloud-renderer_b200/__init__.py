@@ -48,7 +48,8 @@ class TraceParams(C.Structure):
                 ("vctDownScaling", f32),
                 ("showQuad", i32), ("doConeTrace", i32), ("doNoiseSample", i32),
                 ("runTime", f32),
-                ("clearColor", f32 * 4), ("drawSun", i32), ("transmittanceCutoff", f32), ("sampler", i32), ("skipEmptySpace", i32)]
+                ("clearColor", f32 * 4), ("drawSun", i32), ("transmittanceCutoff", f32), ("sampler", i32), ("skipEmptySpace", i32),
+                ("quantizeFramebuffer", i32)]
 
 
 class TraceStats(C.Structure):

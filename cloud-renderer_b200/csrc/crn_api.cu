@@ -152,36 +152,54 @@ struct crn_ctx {
     bool havePos0 = false;               // pos0 holds the un-advected offsets of the current billboard set
     DevBuf exportTmp, exportOut;         // crn_export_voxels scratch
     DevBuf bitsA, chainA;                // CRN_VOLUME_RG8: the occupancy (alpha) channel's level-0 set and R8 chain
-    DevBuf pos0, pos, scale, keyL, keyC, rankL, rankC, recTmpL, recTmpC, rectTmpL, rectTmpC, lbTmp, recL, recC, rectL, rectC,
-        lbSorted, drawOrder, bits, chain, noise, posmap, image, misc, maskNz, maskDil, mask, sortTmp, tileOrder;
+    DevBuf pos0, pos, scale, keyL, keyC, rankL, rankC, recTmpL, recTmpC, rectTmpL, rectTmpC, lbTmp, recL, rectL,
+        lbSorted, drawOrder, bits, chain, noise, posmap, image, misc, maskNz, maskDil, mask, sortTmp;
     bool maskCurrent = false;
     size_t poolMin = (size_t)1 << 20;    // initial bin-pool entries (CRN_BIN_POOL_MIN overrides: tests force the growth path)
-    Bins binsL, binsC;
+    Bins binsL;
     uint32_t *hCursors = nullptr;        // pinned: [0..2] light cursors + flags, [4..6] camera cursors + flags
     unsigned long long *hStats = nullptr;
 
-    // texture-unit copies (CRN_SAMPLER_TEXTURE)
-    cudaMipmappedArray_t volArray = nullptr, volArrayA = nullptr;
-    TexSet tsA{};                        // CRN_VOLUME_RG8: texture-unit copy of the occupancy chain
-    int volArrayDim = 0, volArrayLevels = 0, volArrayFormat = -1;
+    // Everything a trace READS and a voxelize / trace set-up WRITES exists twice, so that the set-up of frame k+1 (light
+    // side, mips, masks, baked steps, need codes on the light stream; camera-side prep / sort / bin on the side stream)
+    // overlaps the trace of frame k on the caller's stream.  The chain, the masks and the bits are read only by that
+    // set-up itself (texture sampler) and stay single.
+    struct BakeKey { uint64_t gen; int nTex; int level0[kMaxBakedTex]; float frac[kMaxBakedTex]; int n[kMaxBakedTex]; };
+    struct CodeKey { uint64_t gen; int G, nGroups; float height[kCodeGroups]; int level[kCodeGroups]; float light[3]; float bounds[6]; };
+    struct VolSet {                      // texture-unit copies (CRN_SAMPLER_TEXTURE) + per-frame cone acceleration data (k_conebake.cu)
+        cudaMipmappedArray_t volArray = nullptr, volArrayA = nullptr;
+        TexSet ts{}, tsA{};              // tsA: CRN_VOLUME_RG8, texture-unit copy of the occupancy chain
+        int volArrayDim = 0, volArrayLevels = 0, volArrayFormat = -1;
+        bool texCurrent = false;         // the arrays hold the chain of the last voxelize
+        cudaArray_t bakedArr[kMaxBakedTex] = {};
+        cudaSurfaceObject_t bakedSurf[kMaxBakedTex] = {};
+        int bakedN[kMaxBakedTex] = {};
+        DevBuf needCode;
+        BakeKey bakeKey{};
+        CodeKey codeKey{};
+        bool bakeValid = false, codeValid = false;
+        uint64_t codeBoardsGen = ~0ull;
+        cudaEvent_t evFree = nullptr;    // recorded after the last trace that read this set
+        bool freeValid = false;
+    } vset[2];
+    int vs = 0;                          // the set the last voxelize wrote = the one traces read
+    struct CamSet {                      // camera-side records, bins and tile order of one trace
+        DevBuf recC, rectC, tileOrder, sortTmpC;
+        Bins binsC;
+        cudaEvent_t evFree = nullptr;
+        bool freeValid = false;
+    } cset[2];
+    int cs = 0;
     cudaArray_t noiseArray = nullptr;
-    TexSet ts{};
-    bool texCurrent = false;             // the arrays hold the chain of the last voxelize
-
-    // per-frame cone acceleration data (k_conebake.cu): baked step textures + the need-code grid
-    cudaArray_t bakedArr[kMaxBakedTex] = {};
-    cudaSurfaceObject_t bakedSurf[kMaxBakedTex] = {};
-    int bakedN[kMaxBakedTex] = {};
+    cudaTextureObject_t noiseTex = 0;
     BakeTex bakePlan[kMaxBakedTex] = {};
     int nBakePlan = 0;
-    DevBuf needCode;
     DevBuf segPartial, segArrived;       // small frames: per-segment partial composites of the cut tile lists (k_trace.cu)
     int segOverride = -1;                // CRN_TRACE_SEGMENTS=n: force the segment count (experiments)
     uint64_t volumeGen = 0;              // bumped whenever the chain changes (voxelize, finish_mips)
-    struct BakeKey { uint64_t gen; int nTex; int level0[kMaxBakedTex]; float frac[kMaxBakedTex]; int n[kMaxBakedTex]; } bakeKey{};
-    struct CodeKey { uint64_t gen; int G, nGroups; float height[kCodeGroups]; int level[kCodeGroups]; float light[3]; float bounds[6]; } codeKey{};
-    bool bakeValid = false, codeValid = false;
-    uint64_t boardsGen = 0, codeBoardsGen = ~0ull;   // bumped whenever the billboard arrays change
+    uint64_t boardsGen = 0;              // bumped whenever the billboard arrays change
+    bool lastTraceExplicit = false;      // the last trace read the bits / the chain directly (explicit sampler)
+    cudaEvent_t evPrepared = nullptr, evVoxDone = nullptr, evAccT[2] = {};
 
     // pipelined read-back (crn_cone_trace_async): second image buffer, copy stream, frame/copy events
     DevBuf image2;
@@ -193,7 +211,6 @@ struct crn_ctx {
     cudaStream_t auxStream = nullptr;
     cudaEvent_t evBoards = nullptr, evAuxDone = nullptr, evTraceEnd = nullptr, evAuxT[3] = {};
     bool traceEndValid = false;
-    DevBuf sortTmpC;
     bool copyPending[2] = {false, false};
     int imgSel = 0;
 
@@ -207,12 +224,16 @@ struct crn_ctx {
     cudaEvent_t evCur[2] = {};           // cursor read-back done (light, camera): the next bin pass resets the cursors
     bool curValid[2] = {false, false};
     bool bitsExposed = false;            // crn_volume_bits_ptr handed the set to the caller: keep strict stream order
+    bool levelExposed = false;           // ... or crn_volume_level_ptr did
 
     cudaEvent_t evV[6] = {}, evT[4] = {};
     bool evVValid = false, evTValid = false;
 };
 
 namespace {
+
+inline crn_ctx::VolSet &VS(crn_ctx *c) { return c->vset[c->vs]; }
+inline crn_ctx::CamSet &CS(crn_ctx *c) { return c->cset[c->cs]; }
 
 int fail(crn_ctx *c, int code, const char *fmt, ...) {
     char buf[512];
@@ -298,6 +319,13 @@ int grow_if_overflowed(crn_ctx *c, Bins &b, const uint32_t *cur, bool *grew) {
     return CRN_OK;
 }
 
+void sync_all(crn_ctx *c) {
+    cudaStreamSynchronize(c->stream);
+    if (c->lightStream) cudaStreamSynchronize(c->lightStream);
+    if (c->auxStream) cudaStreamSynchronize(c->auxStream);
+    if (c->copyStream) cudaStreamSynchronize(c->copyStream);
+}
+
 void free_chain_textures(cudaMipmappedArray_t &arr, TexSet &ts) {
     for (int l = 0; l < kMaxLevels; l++) {
         if (ts.tex[l]) cudaDestroyTextureObject(ts.tex[l]);
@@ -311,17 +339,17 @@ void free_chain_textures(cudaMipmappedArray_t &arr, TexSet &ts) {
 }
 
 void free_baked(crn_ctx *c, int i) {
-    if (c->ts.baked[i]) cudaDestroyTextureObject(c->ts.baked[i]);
-    if (c->bakedSurf[i]) cudaDestroySurfaceObject(c->bakedSurf[i]);
-    if (c->bakedArr[i]) cudaFreeArray(c->bakedArr[i]);
-    c->ts.baked[i] = 0; c->bakedSurf[i] = 0; c->bakedArr[i] = nullptr; c->bakedN[i] = 0;
+    if (VS(c).ts.baked[i]) cudaDestroyTextureObject(VS(c).ts.baked[i]);
+    if (VS(c).bakedSurf[i]) cudaDestroySurfaceObject(VS(c).bakedSurf[i]);
+    if (VS(c).bakedArr[i]) cudaFreeArray(VS(c).bakedArr[i]);
+    VS(c).ts.baked[i] = 0; VS(c).bakedSurf[i] = 0; VS(c).bakedArr[i] = nullptr; VS(c).bakedN[i] = 0;
 }
 
 void free_vol_textures(crn_ctx *c) {
-    free_chain_textures(c->volArray, c->ts);
-    free_chain_textures(c->volArrayA, c->tsA);
-    c->ts.volA = 0; c->tsA.enabled = 0;
-    c->volArrayDim = c->volArrayLevels = 0; c->volArrayFormat = -1; c->ts.enabled = 0; c->texCurrent = false;
+    free_chain_textures(VS(c).volArray, VS(c).ts);
+    free_chain_textures(VS(c).volArrayA, VS(c).tsA);
+    VS(c).ts.volA = 0; VS(c).tsA.enabled = 0;
+    VS(c).volArrayDim = VS(c).volArrayLevels = 0; VS(c).volArrayFormat = -1; VS(c).ts.enabled = 0; VS(c).texCurrent = false;
 }
 
 // the R8 immutable 3D texture with `levels` mips of the reference (src/CloudVolume.cpp:18-23):
@@ -330,16 +358,16 @@ int create_chain_textures(crn_ctx *c, cudaMipmappedArray_t &arr, TexSet &ts);
 
 int ensure_vol_textures(crn_ctx *c) {
     const int D = c->vol.dimension, L = c->vol.levels;
-    if (c->volArray && c->volArrayDim == D && c->volArrayLevels == L && c->volArrayFormat == c->vol.format) return CRN_OK;
-    CRN_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (VS(c).volArray && VS(c).volArrayDim == D && VS(c).volArrayLevels == L && VS(c).volArrayFormat == c->vol.format) return CRN_OK;
+    sync_all(c);
     free_vol_textures(c);
     int r;
-    if ((r = create_chain_textures(c, c->volArray, c->ts))) return r;
+    if ((r = create_chain_textures(c, VS(c).volArray, VS(c).ts))) return r;
     if (c->vol.format == CRN_VOLUME_RG8) {
-        if ((r = create_chain_textures(c, c->volArrayA, c->tsA))) return r;
-        c->ts.volA = c->tsA.vol; c->tsA.enabled = 1;
+        if ((r = create_chain_textures(c, VS(c).volArrayA, VS(c).tsA))) return r;
+        VS(c).ts.volA = VS(c).tsA.vol; VS(c).tsA.enabled = 1;
     }
-    c->volArrayDim = D; c->volArrayLevels = L; c->volArrayFormat = c->vol.format; c->ts.enabled = 1; c->texCurrent = false;
+    VS(c).volArrayDim = D; VS(c).volArrayLevels = L; VS(c).volArrayFormat = c->vol.format; VS(c).ts.enabled = 1; VS(c).texCurrent = false;
     return CRN_OK;
 }
 
@@ -434,7 +462,7 @@ int build_masks(crn_ctx *c) {
     if ((r = reserve(c, c->maskNz, words * 4))) return r;
     if ((r = reserve(c, c->maskDil, words * 4))) return r;
     if ((r = reserve(c, c->mask, words * 4))) return r;
-    c->launches += launch_skipmask(c->stream, c->vparams, (const uint32_t *)c->bits.p, (const uint8_t *)c->chain.p,
+    c->launches += launch_skipmask(c->lightStream, c->vparams, (const uint32_t *)c->bits.p, (const uint8_t *)c->chain.p,
                                    (uint32_t *)c->maskNz.p, (uint32_t *)c->maskDil.p, (uint32_t *)c->mask.p,
                                    (uint32_t *)((char *)c->misc.p + 192));
     c->maskCurrent = true;
@@ -443,20 +471,20 @@ int build_masks(crn_ctx *c) {
 
 // layered RG16 array of one baked cone step: n x n texels, n-1 layers (layer k = node planes k and k+1)
 int ensure_baked_array(crn_ctx *c, int i, int n) {
-    if (c->bakedArr[i] && c->bakedN[i] == n) return CRN_OK;
-    CRN_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (VS(c).bakedArr[i] && VS(c).bakedN[i] == n) return CRN_OK;
+    sync_all(c);
     free_baked(c, i);
     cudaChannelFormatDesc cd = cudaCreateChannelDesc(16, 16, 0, 0, cudaChannelFormatKindUnsigned);
-    CRN_CUDA(c, cudaMalloc3DArray(&c->bakedArr[i], &cd, make_cudaExtent(n, n, n - 1), cudaArrayLayered | cudaArraySurfaceLoadStore));
+    CRN_CUDA(c, cudaMalloc3DArray(&VS(c).bakedArr[i], &cd, make_cudaExtent(n, n, n - 1), cudaArrayLayered | cudaArraySurfaceLoadStore));
     cudaResourceDesc rd{};
-    rd.resType = cudaResourceTypeArray; rd.res.array.array = c->bakedArr[i];
-    CRN_CUDA(c, cudaCreateSurfaceObject(&c->bakedSurf[i], &rd));
+    rd.resType = cudaResourceTypeArray; rd.res.array.array = VS(c).bakedArr[i];
+    CRN_CUDA(c, cudaCreateSurfaceObject(&VS(c).bakedSurf[i], &rd));
     cudaTextureDesc td{};
     td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
     td.filterMode = cudaFilterModeLinear; td.readMode = cudaReadModeNormalizedFloat; td.normalizedCoords = 1;
-    CRN_CUDA(c, cudaCreateTextureObject(&c->ts.baked[i], &rd, &td, nullptr));
-    c->bakedN[i] = n;
-    c->bakeValid = false;
+    CRN_CUDA(c, cudaCreateTextureObject(&VS(c).ts.baked[i], &rd, &td, nullptr));
+    VS(c).bakedN[i] = n;
+    VS(c).bakeValid = false;
     return CRN_OK;
 }
 
@@ -468,15 +496,16 @@ int build_cone_accel(crn_ctx *c, TraceParams &tp) {
         k.gen = c->volumeGen; k.nTex = c->nBakePlan;
         for (int i = 0; i < c->nBakePlan; i++) {
             if ((r = ensure_baked_array(c, i, c->bakePlan[i].n))) return r;
-            c->bakePlan[i].surf = c->bakedSurf[i];
+            c->bakePlan[i].surf = VS(c).bakedSurf[i];
             k.level0[i] = c->bakePlan[i].level0; k.frac[i] = c->bakePlan[i].frac; k.n[i] = c->bakePlan[i].n;
         }
-        if (!c->bakeValid || std::memcmp(&k, &c->bakeKey, sizeof k) != 0) {
-            c->launches += launch_bake_steps(c->stream, c->vparams, (const uint32_t *)c->bits.p, (const uint8_t *)c->chain.p, c->bakePlan, c->nBakePlan);
-            c->bakeKey = k; c->bakeValid = true;
+        if (!VS(c).bakeValid || std::memcmp(&k, &VS(c).bakeKey, sizeof k) != 0) {
+            if (VS(c).freeValid) cudaStreamWaitEvent(c->lightStream, VS(c).evFree, 0);     // a trace may still be reading this set's baked textures
+            c->launches += launch_bake_steps(c->lightStream, c->vparams, (const uint32_t *)c->bits.p, (const uint8_t *)c->chain.p, c->bakePlan, c->nBakePlan);
+            VS(c).bakeKey = k; VS(c).bakeValid = true;
         }
     }
-    for (int b = 0; b < tp.nBaked; b++) tp.baked[b].tex = (unsigned long long)c->ts.baked[tp.baked[b].tex];
+    for (int b = 0; b < tp.nBaked; b++) tp.baked[b].tex = (unsigned long long)VS(c).ts.baked[tp.baked[b].tex];
     return CRN_OK;
 }
 
@@ -486,7 +515,7 @@ int build_need_codes(crn_ctx *c, TraceParams &tp, const uint32_t *worldBox) {
     int r;
     if (tp.codeDim > 0) {
         const size_t cells = (size_t)tp.codeDim * tp.codeDim * tp.codeDim;
-        if ((r = reserve(c, c->needCode, cells))) return r;
+        if ((r = reserve(c, VS(c).needCode, cells))) return r;
         crn_ctx::CodeKey k{};
         k.gen = c->volumeGen; k.G = tp.codeDim; k.nGroups = std::min(tp.nGroups, kCodeGroups);
         for (int g = 0; g < k.nGroups; g++) { k.height[g] = tp.groups[g].height; k.level[g] = tp.groups[g].level; }
@@ -495,12 +524,19 @@ int build_need_codes(crn_ctx *c, TraceParams &tp, const uint32_t *worldBox) {
         std::memcpy(k.bounds, b, sizeof b);
         // (the box changes with the billboards, which the key cannot see: rebuilt every frame unless the billboards are the
         //  ones of the last build)
-        if (!c->codeValid || c->codeBoardsGen != c->boardsGen || std::memcmp(&k, &c->codeKey, sizeof k) != 0) {
-            c->launches += launch_need_code(c->stream, c->vparams, tp, (const uint32_t *)c->mask.p, worldBox, (uint8_t *)c->needCode.p);
-            c->codeKey = k; c->codeValid = true; c->codeBoardsGen = c->boardsGen;
+        if (!VS(c).codeValid || VS(c).codeBoardsGen != c->boardsGen || std::memcmp(&k, &VS(c).codeKey, sizeof k) != 0) {
+            if (VS(c).freeValid) cudaStreamWaitEvent(c->lightStream, VS(c).evFree, 0);
+            c->launches += launch_need_code(c->lightStream, c->vparams, tp, (const uint32_t *)c->mask.p, worldBox, (uint8_t *)VS(c).needCode.p);
+            VS(c).codeKey = k; VS(c).codeValid = true; VS(c).codeBoardsGen = c->boardsGen;
         }
     }
     return CRN_OK;
+}
+
+// the caller holds device pointers into the volume (crn_volume_bits_ptr / crn_volume_level_ptr) or shards it by Z-slabs:
+// its stream and the light stream are joined at every hand-over instead of running ahead of each other
+bool strict_order(const crn_ctx *c) {
+    return c->bitsExposed || c->levelExposed || (c->z1 >= 0 && !(c->z0 == 0 && c->z1 == c->vol.dimension));
 }
 
 int enqueue_voxelize(crn_ctx *c) {
@@ -535,13 +571,16 @@ int enqueue_voxelize(crn_ctx *c) {
     if (c->keepPosmap && (r = reserve(c, c->posmap, (size_t)c->W * c->H * 16))) return r;
     if ((r = ensure_bins(c, c->binsL, c->W, c->H, n))) return r;
     const bool toTex = c->tp.sampler == CRN_SAMPLER_TEXTURE;
+    c->vs ^= 1;                                                          // this frame's textures go into the other set
     if (toTex && (r = ensure_vol_textures(c))) return r;
 
-    // ---- light stream: everything up to the occupancy bits
+    // ---- light stream: the whole set-up of the frame.  Nothing here is read by a trace in flight: the bits, the chain
+    //      and the masks are consumed on this stream (texture sampler), the textures written below belong to the set
+    //      the trace before last used.
     cudaStream_t st = c->lightStream;
     cudaStreamWaitEvent(st, c->evBoards, 0);
-    if (c->bitsFreeValid) cudaStreamWaitEvent(st, c->evBitsFree, 0);     // last readers of the previous frame's bits
-    if (c->bitsExposed) {                                                // the caller may have queued work on the bits
+    if (c->bitsFreeValid) cudaStreamWaitEvent(st, c->evBitsFree, 0);     // an explicit-sampler trace reads the bits and the chain directly
+    if (strict_order(c)) {                                               // the caller may have queued work on the bits / the chain
         cudaEventRecord(c->evMainMark, c->stream);
         cudaStreamWaitEvent(st, c->evMainMark, 0);
     }
@@ -566,30 +605,30 @@ int enqueue_voxelize(crn_ctx *c) {
                                    (const float *)c->lbSorted.p, c->binsL, (uint32_t *)c->bits.p,
                                    c->keepPosmap ? (float4 *)c->posmap.p : nullptr, paper ? (uint32_t *)c->bitsA.p : nullptr);
     if (c->timingOn) cudaEventRecord(c->evV[3], st);
-    cudaEventRecord(c->evLightDone, st);
-    // ---- caller's stream: expand the bits into the chain / textures / masks the trace samples
-    st = c->stream;
-    cudaStreamWaitEvent(st, c->evLightDone, 0);
+    // ---- expand the bits into the chain / this set's textures / the masks
+    if (VS(c).freeValid) cudaStreamWaitEvent(st, VS(c).evFree, 0);       // the last trace that sampled this set's textures
     if (c->timingOn) cudaEventRecord(c->evV[5], st);
     // the linear copy of level 0 (8x the bits) is not read by anything in the pipeline: it is written only for a caller
     // that holds crn_volume_level_ptr(0), and expanded on demand for crn_read_volume
     const bool whole = c->vparams.z0 == 0 && c->vparams.z1 == c->vol.dimension;
     // (a slab's texture copy would be overwritten after the exchange anyway: the textures are filled then)
     c->launches += launch_mips(st, c->vparams, (const uint32_t *)c->bits.p, (uint8_t *)c->chain.p, (uint32_t *)c->misc.p, c->wantLinear0,
-                               (toTex && whole) ? &c->ts : nullptr);
+                               (toTex && whole) ? &VS(c).ts : nullptr);
     c->linear0Valid = c->wantLinear0; c->linear0ValidA = false;
     if (paper)
         c->launches += launch_mips(st, c->vparams, (const uint32_t *)c->bitsA.p, (uint8_t *)c->chainA.p, (uint32_t *)c->misc.p + 8,
-                                   false, toTex ? &c->tsA : nullptr);
-    c->texCurrent = toTex && whole;
+                                   false, toTex ? &VS(c).tsA : nullptr);
+    VS(c).texCurrent = toTex && whole;
     c->maskCurrent = false;
     c->volumeGen++;
     if (whole && c->tp.skipEmptySpace) {
         if ((r = build_masks(c))) return r;
     }
     if (c->timingOn) { cudaEventRecord(c->evV[4], st); c->evVValid = true; }
-    cudaEventRecord(c->evBitsFree, st);
-    c->bitsFreeValid = true;
+    cudaEventRecord(c->evVoxDone, st);
+    c->bitsFreeValid = false;
+    // a caller that holds pointers into the volume (slab exchange) consumes it on ITS stream
+    if (strict_order(c)) cudaStreamWaitEvent(c->stream, c->evVoxDone, 0);
     CRN_CUDA(c, cudaGetLastError());
     c->voxelized = true;
     return CRN_OK;
@@ -717,26 +756,27 @@ int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
     const int n = c->nBoards;
     const ViewParams cam = make_view(c->cam.P, c->cam.V, c->W, c->H);
     fill_vparams(c);
+    c->cs ^= 1;                                        // this trace's camera-side buffers: the other set
     int r;
     const size_t nn = std::max(n, 1);
     if ((r = reserve(c, c->keyC, nn * 8))) return r;
     if ((r = reserve(c, c->rankC, nn * 4))) return r;
     if ((r = reserve(c, c->recTmpC, nn * sizeof(BoardRec)))) return r;
     if ((r = reserve(c, c->rectTmpC, nn * sizeof(BoardRect)))) return r;
-    if ((r = reserve(c, c->recC, nn * sizeof(BoardRec)))) return r;
-    if ((r = reserve(c, c->rectC, nn * sizeof(BoardRect)))) return r;
+    if ((r = reserve(c, CS(c).recC, nn * sizeof(BoardRec)))) return r;
+    if ((r = reserve(c, CS(c).rectC, nn * sizeof(BoardRect)))) return r;
     if ((r = reserve(c, c->drawOrder, nn * 4))) return r;
-    if ((r = reserve(c, c->sortTmpC, sort_tmp_bytes((int)nn) + 128))) return r;
+    if ((r = reserve(c, CS(c).sortTmpC, sort_tmp_bytes((int)nn) + 128))) return r;
     if ((r = reserve(c, c->misc, 256))) return r;
     const size_t texel = format == CRN_IMAGE_RGBA32F ? 16 : 4;
     if ((r = reserve(c, img, (size_t)c->W * c->H * texel))) return r;
-    if ((r = ensure_bins(c, c->binsC, c->W, c->H, n))) return r;
-    if ((r = reserve(c, c->tileOrder, ((size_t)c->binsC.tilesX * c->binsC.tilesY + 66) * 4))) return r;
+    if ((r = ensure_bins(c, CS(c).binsC, c->W, c->H, n))) return r;
+    if ((r = reserve(c, CS(c).tileOrder, ((size_t)CS(c).binsC.tilesX * CS(c).binsC.tilesY + 66) * 4))) return r;
 
     TraceParams tp;
     build_trace_params(c, cam, &tp);
     {   // small frames leave SMs idle behind the longest tile list: cut the lists (see trace_fast_kernel)
-        const size_t tiles = (size_t)c->binsC.tilesX * c->binsC.tilesY;
+        const size_t tiles = (size_t)CS(c).binsC.tilesX * CS(c).binsC.tilesY;
         // measured trace ms at 1 / 2 / 4 segments: C1 (3600 tiles) 0.244 / 0.188 / 0.165, C2 (8160) 0.807 / 0.715 / 0.632,
         // C3 (32400) 3.015 / 2.955 / 3.086, C4 (129600) 9.46 / 10.12 / 10.65; a rank of an interleaved trace owns 1/count of the tiles
         const size_t active = tiles / (size_t)std::max(1, c->ilvCount);
@@ -748,67 +788,78 @@ int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
             if ((r = reserve(c, c->segArrived, tiles * 4 * sizeof(uint32_t)))) return r;      // zeroed by reserve, re-armed by the kernel
         }
     }
-    cudaStream_t st = c->stream;
-    bool readsBits = c->tp.sampler != CRN_SAMPLER_TEXTURE;          // the explicit sampler reads level 0 from the bits
-    for (int i = 0; i < c->nBakePlan; i++) readsBits |= c->bakePlan[i].level0 == 0;    // ... and so does a level-0 bake
+    cudaStream_t st = c->stream, ls = c->lightStream;
+    const bool useTex = c->tp.sampler == CRN_SAMPLER_TEXTURE;
+    // ---- trace set-up on the light stream: after this frame's voxelize (same stream), before the next frame's
+    if (strict_order(c)) {                             // whatever the caller queued on its stream (slab exchange, crn_finish_mips)
+        cudaEventRecord(c->evMainMark, st);
+        cudaStreamWaitEvent(ls, c->evMainMark, 0);
+    }
     if (c->tp.skipEmptySpace && !c->maskCurrent) {     // chain came from an exchange, or the option was just switched on
         if ((r = build_masks(c))) return r;
-        readsBits = true;
     }
-    const bool useTex = c->tp.sampler == CRN_SAMPLER_TEXTURE;
     if (useTex) {
         if ((r = ensure_vol_textures(c))) return r;
-        if (!c->texCurrent) {           // sampler switched after voxelize, or the chain came from an exchange
+        if (!VS(c).texCurrent) {           // sampler switched after voxelize, or the chain came from an exchange
+            if (VS(c).freeValid) cudaStreamWaitEvent(ls, VS(c).evFree, 0);
             // level 0 from the bits (they are what a slab exchange ships), the coarser levels from the linear chain
-            c->launches += launch_expand_level0(st, c->vparams, (const uint32_t *)c->bits.p, nullptr, &c->ts);
-            c->launches += launch_chain_to_surfaces(st, c->vparams, (const uint8_t *)c->chain.p, c->ts, 1);
+            c->launches += launch_expand_level0(ls, c->vparams, (const uint32_t *)c->bits.p, nullptr, &VS(c).ts);
+            c->launches += launch_chain_to_surfaces(ls, c->vparams, (const uint8_t *)c->chain.p, VS(c).ts, 1);
             if (c->vol.format == CRN_VOLUME_RG8) {
-                c->launches += launch_expand_level0(st, c->vparams, (const uint32_t *)c->bitsA.p, nullptr, &c->tsA);
-                c->launches += launch_chain_to_surfaces(st, c->vparams, (const uint8_t *)c->chainA.p, c->tsA, 1);
+                c->launches += launch_expand_level0(ls, c->vparams, (const uint32_t *)c->bitsA.p, nullptr, &VS(c).tsA);
+                c->launches += launch_chain_to_surfaces(ls, c->vparams, (const uint8_t *)c->chainA.p, VS(c).tsA, 1);
             }
-            readsBits = true;
-            c->texCurrent = true;
+            VS(c).texCurrent = true;
         }
     }
-    unsigned long long *dStats = (unsigned long long *)((char *)c->misc.p + 64);
-    if (c->statsOn) cudaMemsetAsync(dStats, 0, 8 * sizeof(unsigned long long), st);
-    if (c->timingOn) cudaEventRecord(c->evT[2], st);                // the cone acceleration data is part of the trace stage
+    if (c->timingOn) cudaEventRecord(c->evT[2], ls);                // the cone acceleration data is part of the trace stage
     if ((r = build_cone_accel(c, tp))) return r;
-    // ---- camera-side set-up on the side stream: after the billboard upload and after the previous trace (which reads
-    //      the same records / bins), concurrently with whatever voxelize work is still queued on the main stream
+    if (c->timingOn) cudaEventRecord(c->evT[1], ls);
+    // ---- camera-side set-up on the side stream, into the camera set the trace before last used: concurrent with the
+    //      light stream's work AND with the previous trace
     cudaStream_t ax = c->auxStream;
     cudaStreamWaitEvent(ax, c->evBoards, 0);
-    if (c->traceEndValid) cudaStreamWaitEvent(ax, c->evTraceEnd, 0);
+    if (CS(c).freeValid) cudaStreamWaitEvent(ax, CS(c).evFree, 0);
     if (c->curValid[1]) cudaStreamWaitEvent(ax, c->evCur[1], 0);
     if (c->timingOn) cudaEventRecord(c->evAuxT[0], ax);
     const float zero3[3] = {0, 0, 0};
     c->launches += launch_prep_sort(ax, (const float *)c->pos.p, (const float *)c->scale.p, n, c->vol.fluffiness, c->vol.position, cam,
                                     zero3, 1.0f, cam, c->cam.position, false, true, nullptr, (uint32_t *)c->rankC.p, nullptr,
                                     (uint64_t *)c->keyC.p, nullptr, (BoardRec *)c->recTmpC.p, nullptr, (BoardRect *)c->rectTmpC.p,
-                                    nullptr, nullptr, (BoardRec *)c->recC.p, nullptr, (BoardRect *)c->rectC.p, nullptr,
-                                    (int32_t *)c->drawOrder.p, c->sortTmpC.p);
+                                    nullptr, nullptr, (BoardRec *)CS(c).recC.p, nullptr, (BoardRect *)CS(c).rectC.p, nullptr,
+                                    (int32_t *)c->drawOrder.p, CS(c).sortTmpC.p);
     if (c->timingOn) cudaEventRecord(c->evAuxT[1], ax);
-    c->launches += launch_bin(ax, (const BoardRect *)c->rectC.p, sort_tmp_bounds(c->sortTmpC.p, (int)nn, 1), n, c->W, c->H, c->binsC);
+    c->launches += launch_bin(ax, (const BoardRect *)CS(c).rectC.p, sort_tmp_bounds(CS(c).sortTmpC.p, (int)nn, 1), n, c->W, c->H, CS(c).binsC);
     cudaEventRecord(c->evBin[1], ax);
     cudaStreamWaitEvent(c->copyStream, c->evBin[1], 0);
-    cudaMemcpyAsync(c->hCursors + 4, c->binsC.cursors, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->copyStream);
+    cudaMemcpyAsync(c->hCursors + 4, CS(c).binsC.cursors, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->copyStream);
     cudaEventRecord(c->evCur[1], c->copyStream); c->curValid[1] = true;
-    c->launches += launch_tile_order(ax, c->binsC, (uint32_t *)c->tileOrder.p);
+    c->launches += launch_tile_order(ax, CS(c).binsC, (uint32_t *)CS(c).tileOrder.p);
     if (c->timingOn) cudaEventRecord(c->evAuxT[2], ax);
     cudaEventRecord(c->evAuxDone, ax);
-    cudaStreamWaitEvent(st, c->evAuxDone, 0);
-    if ((r = build_need_codes(c, tp, n > 0 ? sort_tmp_world_box(c->sortTmpC.p, (int)nn) : nullptr))) return r;
-    if (c->timingOn) { cudaEventRecord(c->evT[1], st); cudaEventRecord(c->evT[0], st); }
-    c->launches += launch_trace(st, cam, c->vparams, tp, (const BoardRec *)c->recC.p, c->binsC, (const uint32_t *)c->bits.p,
+    // ---- need codes: inside the billboards' world box, which the camera-side prep kernel has just produced
+    cudaStreamWaitEvent(ls, c->evAuxDone, 0);
+    if (c->timingOn) cudaEventRecord(c->evAccT[0], ls);
+    if ((r = build_need_codes(c, tp, n > 0 ? sort_tmp_world_box(CS(c).sortTmpC.p, (int)nn) : nullptr))) return r;
+    if (c->timingOn) cudaEventRecord(c->evAccT[1], ls);
+    cudaEventRecord(c->evPrepared, ls);
+    // ---- the trace itself, on the caller's stream
+    cudaStreamWaitEvent(st, c->evPrepared, 0);                      // (the light stream has already waited for the side stream)
+    unsigned long long *dStats = (unsigned long long *)((char *)c->misc.p + 64);
+    if (c->statsOn) cudaMemsetAsync(dStats, 0, 8 * sizeof(unsigned long long), st);
+    if (c->timingOn) cudaEventRecord(c->evT[0], st);
+    c->launches += launch_trace(st, cam, c->vparams, tp, (const BoardRec *)CS(c).recC.p, CS(c).binsC, (const uint32_t *)c->bits.p,
                                 (const uint8_t *)c->chain.p, c->vol.format == CRN_VOLUME_RG8 ? (const uint32_t *)c->bitsA.p : nullptr,
-                                (const uint8_t *)c->chainA.p, (const int8_t *)c->noise.p, useTex ? &c->ts : nullptr,
-                                tp.codeDim > 0 ? (const uint8_t *)c->needCode.p : nullptr, (const uint32_t *)c->tileOrder.p,
+                                (const uint8_t *)c->chainA.p, (const int8_t *)c->noise.p, useTex ? &VS(c).ts : nullptr,
+                                tp.codeDim > 0 ? (const uint8_t *)VS(c).needCode.p : nullptr, (const uint32_t *)CS(c).tileOrder.p,
                                 img.p, format, dStats, tp.segCount > 1 ? (float4 *)c->segPartial.p : nullptr,
                                 tp.segCount > 1 ? (uint32_t *)c->segArrived.p : nullptr);
+    cudaEventRecord(VS(c).evFree, st); VS(c).freeValid = true;
+    cudaEventRecord(CS(c).evFree, st); CS(c).freeValid = true;
     cudaEventRecord(c->evTraceEnd, st);
     c->traceEndValid = true;
     c->auxDoneValid = true;
-    if (readsBits) {                                   // the next voxelize must not clear the bits under this trace
+    if (!useTex) {                                     // the explicit sampler reads the bits and the chain under the next voxelize
         cudaEventRecord(c->evBitsFree, st);
         c->bitsFreeValid = true;
     }
@@ -856,10 +907,22 @@ int crn_create(int device, void *stream, crn_ctx **out) {
     cudaMallocHost(&c->hStats, 8 * sizeof(unsigned long long));
     std::memset(c->hCursors, 0, 8 * sizeof(uint32_t));
     std::memset(c->hStats, 0, 8 * sizeof(unsigned long long));
-    cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&c->auxStream, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&c->lightStream, cudaStreamNonBlocking);
+    // The set-up streams run small kernels next to a trace kernel that has hundreds of thousands of CTAs queued: at equal
+    // priority the block scheduler finishes dispatching the trace grid first and the "overlap" happens at its tail only
+    // (measured: pipelined == serialised frame time).  Highest priority lets their CTAs in as soon as trace CTAs retire.
+    int prLo = 0, prHi = 0;
+    cudaDeviceGetStreamPriorityRange(&prLo, &prHi);                 // numerically lower = higher priority
+    cudaStreamCreateWithPriority(&c->copyStream, cudaStreamNonBlocking, prHi);
+    cudaStreamCreateWithPriority(&c->auxStream, cudaStreamNonBlocking, prHi);
+    cudaStreamCreateWithPriority(&c->lightStream, cudaStreamNonBlocking, prHi);
     cudaEventCreateWithFlags(&c->evLightDone, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->evPrepared, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->evVoxDone, cudaEventDisableTiming);
+    for (auto &ev : c->evAccT) cudaEventCreate(&ev);
+    for (int k = 0; k < 2; k++) {
+        cudaEventCreateWithFlags(&c->vset[k].evFree, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c->cset[k].evFree, cudaEventDisableTiming);
+    }
     cudaEventCreateWithFlags(&c->evBitsFree, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->evMainMark, cudaEventDisableTiming);
     for (auto &ev : c->evCur) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
@@ -894,14 +957,25 @@ void crn_destroy(crn_ctx *c) {
     if (c->auxStream) cudaStreamSynchronize(c->auxStream);
     if (c->lightStream) cudaStreamSynchronize(c->lightStream);
     DevBuf *bufs[] = {&c->exportTmp, &c->exportOut, &c->pos0, &c->bitsA, &c->chainA, &c->pos, &c->scale, &c->keyL, &c->keyC, &c->rankL, &c->rankC, &c->recTmpL, &c->recTmpC, &c->rectTmpL,
-                      &c->rectTmpC, &c->lbTmp, &c->recL, &c->recC, &c->rectL, &c->rectC, &c->lbSorted, &c->drawOrder, &c->bits, &c->segPartial, &c->segArrived,
-                      &c->chain, &c->noise, &c->posmap, &c->image, &c->image2, &c->misc, &c->maskNz, &c->maskDil, &c->mask, &c->sortTmp, &c->sortTmpC, &c->tileOrder};
+                      &c->rectTmpC, &c->lbTmp, &c->recL, &c->rectL, &c->lbSorted, &c->drawOrder, &c->bits, &c->segPartial, &c->segArrived,
+                      &c->chain, &c->noise, &c->posmap, &c->image, &c->image2, &c->misc, &c->maskNz, &c->maskDil, &c->mask, &c->sortTmp,
+                      &c->cset[0].recC, &c->cset[0].rectC, &c->cset[0].sortTmpC, &c->cset[0].tileOrder,
+                      &c->cset[1].recC, &c->cset[1].rectC, &c->cset[1].sortTmpC, &c->cset[1].tileOrder, &c->vset[0].needCode, &c->vset[1].needCode};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
-    free_bins(c->binsL); free_bins(c->binsC);
-    free_vol_textures(c);
-    for (int i = 0; i < kMaxBakedTex; i++) free_baked(c, i);
-    if (c->needCode.p) cudaFree(c->needCode.p);
-    if (c->ts.noise) cudaDestroyTextureObject(c->ts.noise);
+    free_bins(c->binsL); free_bins(c->cset[0].binsC); free_bins(c->cset[1].binsC);
+    for (c->vs = 0; c->vs < 2; c->vs++) {
+        free_vol_textures(c);
+        for (int i = 0; i < kMaxBakedTex; i++) free_baked(c, i);
+    }
+    c->vs = 0;
+    for (int k = 0; k < 2; k++) {
+        if (c->vset[k].evFree) cudaEventDestroy(c->vset[k].evFree);
+        if (c->cset[k].evFree) cudaEventDestroy(c->cset[k].evFree);
+    }
+    if (c->evPrepared) cudaEventDestroy(c->evPrepared);
+    if (c->evVoxDone) cudaEventDestroy(c->evVoxDone);
+    for (auto &ev : c->evAccT) if (ev) cudaEventDestroy(ev);
+    if (c->noiseTex) cudaDestroyTextureObject(c->noiseTex);
     if (c->noiseArray) cudaFreeArray(c->noiseArray);
     if (c->hCursors) cudaFreeHost(c->hCursors);
     if (c->hStats) cudaFreeHost(c->hStats);
@@ -937,6 +1011,7 @@ int crn_sync(crn_ctx *c) {
     CRN_CUDA(c, cudaSetDevice(c->device));
     if (c->voxelized) return settle(c, false, 0);           // also re-runs a voxelize whose bin pool was too small
     if (c->lightStream) CRN_CUDA(c, cudaStreamSynchronize(c->lightStream));
+    if (c->auxStream) CRN_CUDA(c, cudaStreamSynchronize(c->auxStream));
     CRN_CUDA(c, cudaStreamSynchronize(c->stream));
     if (c->copyStream) CRN_CUDA(c, cudaStreamSynchronize(c->copyStream));
     return CRN_OK;
@@ -1130,7 +1205,8 @@ int crn_set_noise(crn_ctx *c, const int8_t *rgba, int32_t dim) {
     // stored as a LAYERED 2D array whose layer z holds (g_z, a_z, g_z+1, a_z+1) (z+1 wrapped): one bilinear pass
     // returns both slices, the kernel blends them with the z weight in full float precision.  Same texel bytes, same
     // SNORM8 decode, REPEAT in x and y by the sampler, in z by the layer index.
-    if (c->ts.noise) { cudaDestroyTextureObject(c->ts.noise); c->ts.noise = 0; }
+    sync_all(c);
+    if (c->noiseTex) { cudaDestroyTextureObject(c->noiseTex); c->noiseTex = 0; }
     if (c->noiseArray) { cudaFreeArray(c->noiseArray); c->noiseArray = nullptr; }
     std::vector<int8_t> pairs(n * 4);
     for (int z = 0; z < dim; z++) {
@@ -1151,7 +1227,8 @@ int crn_set_noise(crn_ctx *c, const int8_t *rgba, int32_t dim) {
     cudaTextureDesc td{};
     td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeWrap;
     td.filterMode = cudaFilterModeLinear; td.readMode = cudaReadModeNormalizedFloat; td.normalizedCoords = 1;
-    CRN_CUDA(c, cudaCreateTextureObject(&c->ts.noise, &rd, &td, nullptr));
+    CRN_CUDA(c, cudaCreateTextureObject(&c->noiseTex, &rd, &td, nullptr));
+    c->vset[0].ts.noise = c->vset[1].ts.noise = c->noiseTex;
     c->noiseDim = dim; c->haveNoise = true;
     return CRN_OK;
 }
@@ -1211,20 +1288,26 @@ static int copy_image(crn_ctx *c, void *out, cudaMemcpyKind kind, int format, co
 static int settle(crn_ctx *c, bool haveTrace, int format, bool slabNotShippedYet) {
     for (int attempt = 0; attempt < 4; attempt++) {
         CRN_CUDA(c, cudaStreamSynchronize(c->lightStream));
+        CRN_CUDA(c, cudaStreamSynchronize(c->auxStream));
         CRN_CUDA(c, cudaStreamSynchronize(c->stream));
         CRN_CUDA(c, cudaStreamSynchronize(c->copyStream));         // the cursors travel on the copy stream
         bool grewL = false, grewC = false;
         int r;
         if (c->voxelized && (r = grow_if_overflowed(c, c->binsL, c->hCursors, &grewL))) return r;
-        if (haveTrace && (r = grow_if_overflowed(c, c->binsC, c->hCursors + 4, &grewC))) return r;
+        if (haveTrace && (r = grow_if_overflowed(c, CS(c).binsC, c->hCursors + 4, &grewC))) return r;
         // bit 1 of the flags word: a coarse tile ran out of flush segments (k_bin.cu kMaxSegs: > ~147k rectangles over one
         // 64-pixel tile).  Growing the pools cannot fix that: report it instead of returning an incomplete frame.
         const bool segL = c->voxelized && (c->hCursors[2] & 2u), segC = haveTrace && (c->hCursors[6] & 2u);
         if (segL || segC) {
             if (segL) { CRN_CUDA(c, cudaMemsetAsync(c->binsL.cursors + 2, 0, sizeof(uint32_t), c->lightStream)); c->hCursors[2] = 0; }
-            if (segC) { CRN_CUDA(c, cudaMemsetAsync(c->binsC.cursors + 2, 0, sizeof(uint32_t), c->stream)); c->hCursors[6] = 0; }
+            if (segC) { CRN_CUDA(c, cudaMemsetAsync(CS(c).binsC.cursors + 2, 0, sizeof(uint32_t), c->stream)); c->hCursors[6] = 0; }
             return fail(c, CRN_ERR_UNSUPPORTED, "more billboards overlap one 64-pixel tile than the binning pass can stage (%s pass); the frame is incomplete",
                         segL ? "light" : "camera");
+        }
+        if (grewC) {                                   // keep the other camera set's pools as large: the re-run below uses it
+            Bins &o = c->cset[c->cs ^ 1].binsC;
+            if ((r = alloc_u32(c, o.coarseList, o.coarseCap, CS(c).binsC.coarseCap))) return r;
+            if ((r = alloc_u32(c, o.tileList, o.tileCap, CS(c).binsC.tileCap))) return r;
         }
         if (!grewL && !grewC) return CRN_OK;
         if (grewL && !slabNotShippedYet && c->z1 >= 0 && !(c->z0 == 0 && c->z1 == c->vol.dimension)) {
@@ -1234,7 +1317,7 @@ static int settle(crn_ctx *c, bool haveTrace, int format, bool slabNotShippedYet
         }
         // the truncated attempt left the sticky overflow flag behind; this frame is being redone, so clear it
         if (grewL) CRN_CUDA(c, cudaMemsetAsync(c->binsL.cursors + 2, 0, sizeof(uint32_t), c->lightStream));
-        if (grewC) CRN_CUDA(c, cudaMemsetAsync(c->binsC.cursors + 2, 0, sizeof(uint32_t), c->stream));
+        if (grewC) CRN_CUDA(c, cudaMemsetAsync(CS(c).binsC.cursors + 2, 0, sizeof(uint32_t), c->stream));
         if (grewL && (r = enqueue_voxelize(c))) return r;
         if (haveTrace && (r = enqueue_trace(c, format))) return r;
     }
@@ -1317,8 +1400,9 @@ int crn_wait_images(crn_ctx *c) {
     c->copyPending[0] = c->copyPending[1] = false;
     // a frame enqueued without a host round trip may have run with a truncated bin pool: the kernels leave a sticky flag
     bool overflow = false;
-    Bins *bins[2] = {&c->binsL, &c->binsC};
-    for (int p = 0; p < 2; p++) {
+    if (c->lightStream) CRN_CUDA(c, cudaStreamSynchronize(c->lightStream));
+    Bins *bins[3] = {&c->binsL, &c->cset[0].binsC, &c->cset[1].binsC};
+    for (int p = 0; p < 3; p++) {
         if (!bins[p]->cursors) continue;
         uint32_t cur[4] = {0, 0, 0, 0};
         CRN_CUDA(c, cudaMemcpy(cur, bins[p]->cursors, sizeof cur, cudaMemcpyDeviceToHost));
@@ -1367,6 +1451,7 @@ int crn_volume_level_ptr(crn_ctx *c, int32_t level, void **dev_ptr, size_t *byte
     const size_t s = c->vparams.levelSize[level];
     *dev_ptr = (char *)c->chain.p + c->vparams.levelOff[level];
     *bytes = s * s * s * c->vparams.texelBytes;
+    c->levelExposed = true;             // the caller consumes / produces chain levels on its stream: strict stream order from now on
     if (level == 0) {                   // from now on every voxelize keeps the linear level 0 current
         c->wantLinear0 = true;
         if (c->voxelized && !c->linear0Valid) {
@@ -1394,10 +1479,12 @@ int crn_finish_mips(crn_ctx *c, int32_t first_level) {
     if (first_level < 1 || first_level > c->vol.levels) return fail(c, CRN_ERR_INVALID_ARG, "first_level %d out of range", first_level);
     CRN_CUDA(c, cudaSetDevice(c->device));
     fill_vparams(c);
+    CRN_CUDA(c, cudaStreamWaitEvent(c->stream, c->evVoxDone, 0));       // the chain is produced on the light stream
+    c->levelExposed = true;                                             // ... and from here on consumed in the caller's order
     c->launches += launch_finish_mips(c->stream, c->vparams, (uint8_t *)c->chain.p, first_level);
     CRN_CUDA(c, cudaGetLastError());
     c->voxelized = true;
-    c->texCurrent = false;              // the texture-unit copy is refreshed from the chain at the next trace
+    VS(c).texCurrent = false;              // the texture-unit copy is refreshed from the chain at the next trace
     c->maskCurrent = false;
     c->volumeGen++;
     return CRN_OK;
@@ -1512,8 +1599,8 @@ int crn_read_bins(crn_ctx *c, int32_t which, int32_t *tiles_x, int32_t *tiles_y,
     if ((which == 0 && !c->voxelized) || (which == 1 && !c->traced)) return fail(c, CRN_ERR_STATE, "that pass has not run yet");
     CRN_CUDA(c, cudaSetDevice(c->device));
     int r = settle(c, false, 0); if (r) return r;
-    const Bins &b = which == 0 ? c->binsL : c->binsC;
-    const DevBuf &recs = which == 0 ? c->recL : c->recC;
+    const Bins &b = which == 0 ? c->binsL : CS(c).binsC;
+    const DevBuf &recs = which == 0 ? c->recL : CS(c).recC;
     const size_t tiles = (size_t)b.tilesX * b.tilesY;
     if (tiles_x) *tiles_x = b.tilesX;
     if (tiles_y) *tiles_y = b.tilesY;
@@ -1570,6 +1657,7 @@ int crn_get_timings(crn_ctx *c, crn_timings *out) {
     if (!c || !out) return CRN_ERR_INVALID_ARG;
     std::memset(out, 0, sizeof *out);
     CRN_CUDA(c, cudaSetDevice(c->device));
+    CRN_CUDA(c, cudaStreamSynchronize(c->lightStream));
     CRN_CUDA(c, cudaStreamSynchronize(c->stream));
     if (c->evVValid) {
         CRN_CUDA(c, cudaEventElapsedTime(&out->prepSortMs, c->evV[0], c->evV[1]));
@@ -1583,7 +1671,10 @@ int crn_get_timings(crn_ctx *c, crn_timings *out) {
         CRN_CUDA(c, cudaEventElapsedTime(&t, c->evAuxT[0], c->evAuxT[1]));        // side stream: overlaps the voxelize stage
         out->prepSortMs += t;
         CRN_CUDA(c, cudaEventElapsedTime(&out->camBinMs, c->evAuxT[1], c->evAuxT[2]));
-        CRN_CUDA(c, cudaEventElapsedTime(&out->coneAccelMs, c->evT[2], c->evT[1]));
+        float t2 = 0;
+        CRN_CUDA(c, cudaEventElapsedTime(&out->coneAccelMs, c->evT[2], c->evT[1]));          // baked steps
+        CRN_CUDA(c, cudaEventElapsedTime(&t2, c->evAccT[0], c->evAccT[1]));                   // need codes
+        out->coneAccelMs += t2;
         CRN_CUDA(c, cudaEventElapsedTime(&out->traceMs, c->evT[0], c->evT[3]));
     }
     return CRN_OK;

@@ -226,6 +226,24 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_kernel(co
         }
     }
 
+    // quantizeFramebuffer: the reference's 8-bit window framebuffer.  dst starts as the quantised background and every
+    // blend result goes back through 8 bits, so the list is walked BACK TO FRONT (the reference's draw order) and there
+    // is no transmittance to terminate on.
+    const bool fb8 = tp.p.quantizeFramebuffer != 0;
+    auto q8 = [](float x) { return floorf(saturatef(x) * 255.0f + 0.5f) / 255.0f; };
+    float dst8[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (fb8) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) dst8[k] = q8(tp.bg[k]);
+        if (tp.p.drawSun) {
+            float sc[4];
+            if (sun_fragment(tp, cam, ndcx, ndcy, px, py, sc)) {
+                const float sa = saturatef(sc[3]);
+#pragma unroll
+                for (int k = 0; k < 4; k++) dst8[k] = q8(saturatef(sc[k]) * sa + dst8[k] * (1.0f - sa));
+            }
+        }
+    }
     float C[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     float T = 1.0f;
     unsigned long long nFrag = 0, nCone = 0, nNoise = 0, nSkip = 0, nFetch = 0, nBakedF = 0;
@@ -242,9 +260,9 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_kernel(co
     const float rx = cam.nrm[0], ry = cam.nrm[1], rz = cam.nrm[2];
 
     for (uint32_t e = 0; e < cnt; e++) {
-        const bool live = valid && T > cutoff;                          // T starts at 1: cutoff 0 keeps everything live
+        const bool live = valid && (fb8 || T > cutoff);                 // T starts at 1: cutoff 0 keeps everything live
         if (__all_sync(0xFFFFFFFFu, !live)) break;                      // early ray termination, whole patch
-        const uint32_t k = a.tileList[off + e];
+        const uint32_t k = a.tileList[off + (fb8 ? cnt - 1u - e : e)];  // the list is front to back; the framebuffer mode needs far first
         const float4 r0 = __ldg(reinterpret_cast<const float4 *>(&a.recs[k].cx));
         const float4 r1 = __ldg(reinterpret_cast<const float4 *>(&a.recs[k].xv));
         const float radius = r0.w;
@@ -411,7 +429,12 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_kernel(co
             }
         }
 
-        if (shade) {                                                    // blend, front to back
+        if (shade && fb8) {                                             // SRC_ALPHA / ONE_MINUS_SRC_ALPHA onto the 8-bit target
+            const float sa = saturatef(col[3]);
+#pragma unroll
+            for (int k = 0; k < 4; k++) dst8[k] = q8(saturatef(col[k]) * sa + dst8[k] * (1.0f - sa));
+            nFrag++;
+        } else if (shade) {                                             // blend, front to back
             const float sa = saturatef(col[3]);
             const float w = T * sa;
             C[0] = fmaf(w, saturatef(col[0]), C[0]);
@@ -426,7 +449,7 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_kernel(co
     if (valid) {
         float o[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) o[k] = fmaf(T, bg[k], C[k]);
+        for (int k = 0; k < 4; k++) o[k] = fb8 ? dst8[k] : fmaf(T, bg[k], C[k]);
         const size_t p = (size_t)py * cam.W + px;
         if (a.format == CRN_IMAGE_RGBA32F) {
             reinterpret_cast<float4 *>(a.image)[p] = make_float4(o[0], o[1], o[2], o[3]);
@@ -726,7 +749,7 @@ int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol
     float zmax = 0.0f;
     for (int o = 0; o < 4; o++) zmax = fmaxf(zmax, (4.0f * extent + 64.0f) / fmaxf(fabsf(tp.p.adjustSize), 1e-20f) * fabsf(tp.octFreqZ[o]) + fabsf(tp.octBiasZ[o]));
     const bool zOk = zmax < 2097152.0f;
-    const bool fast = zOk && useTex && !gate && !tp.stats && tp.active && tp.p.numOctaves == 4 && tp.noiseDim == 32 && tp.p.doNoiseSample &&
+    const bool fast = zOk && useTex && !gate && !tp.stats && tp.active && !tp.p.quantizeFramebuffer && tp.p.numOctaves == 4 && tp.noiseDim == 32 && tp.p.doNoiseSample &&
                       tp.p.doConeTrace && !tp.p.showQuad && !cam.ortho && tp.nBaked <= kFastBaked && vol.texelBytes <= 4 && !getenv("CRN_NO_FAST");
     if (gate) {                                                   // opt-in paper variant: stats variant only when asked
         if (useTex && tp.stats) trace_kernel<true, true, true><<<grid, kTraceThreads, 0, st>>>(a, cam, tp, *ts);

@@ -86,7 +86,7 @@ def reference_default_trace_params():
     p.showQuad, p.doConeTrace, p.doNoiseSample = 0, 1, 1
     p.runTime = 0.0
     p.clearColor[:] = (0.2, 0.3, 0.5, 1.0)
-    p.drawSun, p.transmittanceCutoff, p.sampler, p.skipEmptySpace = 1, 0.0, 0, 1
+    p.drawSun, p.transmittanceCutoff, p.sampler, p.skipEmptySpace, p.quantizeFramebuffer = 1, 0.0, 0, 1, 0
     return p
 
 

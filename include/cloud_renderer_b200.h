@@ -136,6 +136,10 @@ typedef struct crn_trace_params {
     int32_t sampler;                /* CRN_SAMPLER_*                                   */
     int32_t skipEmptySpace;         /* skip cone samples whose whole filter footprint is
                                        provably zero (exact: they contribute 0). 1 = on  */
+    int32_t quantizeFramebuffer;    /* 1: emulate the reference's 8-bit window framebuffer (src/main.cpp:94-95): the
+                                       billboards are blended BACK TO FRONT and every blend result is written back
+                                       through 8 bits per channel (no early ray termination in this mode).  0 (default):
+                                       float accumulation, quantised once at the end.                                  */
 } crn_trace_params;
 
 /* Counters of one crn_cone_trace call (read back on demand). */

@@ -192,6 +192,28 @@ def test_reference_8bit_framebuffer_mode(pkg, scenes, orc, renderer):
     assert p >= 45.0
 
 
+@pytest.mark.parametrize("name,sampler", [("tiny", 0), ("small", 0), ("C1", 0), ("C1", 1)])
+def test_quantized_framebuffer_mode(name, sampler, pkg, scenes, orc):
+    """crn_trace_params.quantizeFramebuffer: the reference's 8-bit window framebuffer on the device (back-to-front blends,
+    every result written back through 8 bits, src/main.cpp:94-95) against the oracle's quantize_fb8 path.  A fragment
+    colour that differs in the 5th decimal can flip a rounding, which later blends attenuate: <= 1 LSB everywhere."""
+    s = steady_state(scenes.make_scene(name), orc)
+    s.tp.sampler, s.tp.quantizeFramebuffer = sampler, 1
+    r = pkg.Renderer(0)
+    r.set_scene(s)
+    r.voxelize()
+    u8 = r.cone_trace(fmt=pkg.IMAGE_RGBA8)
+    img = r.cone_trace(fmt=pkg.IMAGE_RGBA32F)
+    r.close()
+    _, _, l0 = orc.voxelize(s, want_posmap=False)
+    ref8, ref_u8, _ = orc.cone_trace(s, orc.mips(l0, s.vol.levels), quantize_fb8=True)
+    d = np.abs(u8.astype(np.int32) - ref_u8.astype(np.int32))
+    print(f"{name}/sampler{sampler}: 8-bit framebuffer mode vs oracle: {100.0 * (d == 0).mean():.3f}% of channels identical, max {d.max()} LSB, "
+          f"PSNR {psnr(img, ref8):.1f} dB")
+    assert np.allclose(img * 255.0, np.round(img * 255.0), atol=1e-3), "the float image of this mode holds 8-bit values"
+    assert d.max() <= (1 if sampler == 0 else 2) and (d == 0).mean() >= (0.995 if sampler == 0 else 0.97)
+
+
 def test_sharding_hooks_do_not_change_results(pkg, scenes, orc, renderer):
     """row bands and Z-slabs executed one after the other on one GPU reproduce the unsharded frame bit for bit"""
     s = steady_state(scenes.make_scene("small"), orc)
