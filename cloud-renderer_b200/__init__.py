@@ -423,7 +423,11 @@ MICROBENCH = {0: "tex3D trilinear RGBA8_SNORM 32^3 (L1)", 1: "tex3D trilinear R8
               7: "tex2DLayered bilinear RG16 UNORM 129x129x128", 8: "tex2DLayered bilinear RG8 UNORM 129x129x128",
               9: "tex2DLayered bilinear RGBA8_SNORM f16x2 return", 10: "tex3D trilinear R16 UNORM 129^3",
               11: "tex3DLod R8 mipmapped 256^3 LOD 4.5", 12: "tex3DLod R8 mipmapped 256^3 LOD 2.5",
-              13: "tex2DLayered bilinear RG16F 129x129x128", 14: "tex3D RGBA8_SNORM 32^3, z on slice centres"}
+              13: "tex2DLayered bilinear RG16F 129x129x128", 14: "tex3D RGBA8_SNORM 32^3, z on slice centres",
+              15: "tex2DLayered bilinear RGBA16_SNORM 161x161x160, strided (L1 misses)",
+              16: "tex2DLayered bilinear RGBA8_SNORM 161x161x160, strided (L1 misses)",
+              17: "tex3D trilinear RG16_SNORM 161^3, strided (L1 misses)",
+              18: "tex2DLayered bilinear RGBA16_SNORM 161x161, one layer (L1 hits)"}
 
 
 def microbench(which, device=0):

@@ -192,6 +192,19 @@ struct crn_ctx {
     int cs = 0;
     cudaArray_t noiseArray = nullptr;
     cudaTextureObject_t noiseTex = 0;
+    // combined-octave noise lattice (k_noiselat.cu): baked when the noise texture, the octave parameters or the window change
+    struct LatKey { uint64_t noiseGen; int dim, octaves; float freqStep, persStep, adjust; int n[3]; long long base[3]; };
+    cudaArray_t latArray = nullptr;
+    cudaSurfaceObject_t latSurf = 0;
+    cudaTextureObject_t latTex = 0;
+    int latN[3] = {0, 0, 0};
+    LatKey latKey{};
+    bool latValid = false;
+    bool noLattice = false;              // CRN_NO_LATTICE=1: every octave through its own lookup (A/B and tests)
+    uint64_t noiseGen = 0;
+    // host-known bounds over the billboards: max(|(x,z)|, |y|) of the offsets (unchanged by crn_animate_billboards' rotation
+    // about Y, so an animated set keeps its window) and the largest scale (< 0: unknown, device-resident source)
+    float boardPosMax = -1.0f, boardScaleMax = 0.0f;
     BakeTex bakePlan[kMaxBakedTex] = {};
     int nBakePlan = 0;
     DevBuf segPartial, segArrived;       // small frames: per-segment partial composites of the cut tile lists (k_trace.cu)
@@ -343,6 +356,14 @@ void free_baked(crn_ctx *c, int i) {
     if (VS(c).bakedSurf[i]) cudaDestroySurfaceObject(VS(c).bakedSurf[i]);
     if (VS(c).bakedArr[i]) cudaFreeArray(VS(c).bakedArr[i]);
     VS(c).ts.baked[i] = 0; VS(c).bakedSurf[i] = 0; VS(c).bakedArr[i] = nullptr; VS(c).bakedN[i] = 0;
+}
+
+void free_lattice(crn_ctx *c) {
+    if (c->latTex) cudaDestroyTextureObject(c->latTex);
+    if (c->latSurf) cudaDestroySurfaceObject(c->latSurf);
+    if (c->latArray) cudaFreeArray(c->latArray);
+    c->latTex = 0; c->latSurf = 0; c->latArray = nullptr; c->latValid = false;
+    c->latN[0] = c->latN[1] = c->latN[2] = 0;
 }
 
 void free_vol_textures(crn_ctx *c) {
@@ -751,6 +772,98 @@ void build_trace_params(crn_ctx *c, const ViewParams &cam, TraceParams *tp) {
     }
 }
 
+// The combined-octave noise lattice (k_noiselat.cu) for this frame's parameters, or tp.lat.on = 0 when they do not
+// qualify: texture sampler, 4 octaves (what the fast trace variant handles), freqStep an odd integer (every coarser
+// octave's texel centres then fall on the finest octave's), no wind offset on octaves 1 and 2, adjustSize > 0, and a
+// window that fits the memory cap.  The window is the volume's box grown by the billboards' reach when the host knows it
+// (host uploads, generated sets), by 20 % otherwise; the kernel checks every billboard against it, so a set that pokes
+// out of the window is still rendered exactly (those billboards take the per-octave lookups).
+int ensure_noise_lattice(crn_ctx *c, const ViewParams &cam, TraceParams &tp) {
+    NoiseLat &L = tp.lat;
+    L.on = 0;
+    const crn_trace_params &p = c->tp;
+    if (c->noLattice || p.sampler != CRN_SAMPLER_TEXTURE || !p.doNoiseSample || p.numOctaves != 4 || c->noiseDim <= 0) return CRN_OK;
+    const float fs = p.freqStep;
+    if (!(fs >= 1.0f && fs <= 9.0f) || fs != floorf(fs) || ((int)fs & 1) == 0) return CRN_OK;
+    if (!(p.adjustSize > 0.0f) || tp.octaveOffsets[1] != 0.0f || tp.octaveOffsets[2] != 0.0f) return CRN_OK;
+    const int F = p.numOctaves - 1;
+    const double K = (double)tp.octFreq[F] * c->noiseDim;               // lattice units per unit of uv
+    // window, world units
+    const float lo[3] = {c->vparams.xB[0], c->vparams.yB[0], c->vparams.zB[0]}, hi[3] = {c->vparams.xB[1], c->vparams.yB[1], c->vparams.zB[1]};
+    int n[3]; long long base[3];
+    double wlo[3], whi[3];
+    size_t nodes = 1;
+    for (int k = 0; k < 3; k++) {
+        const double half = 0.5 * ((double)hi[k] - lo[k]), mid = 0.5 * ((double)hi[k] + lo[k]);
+        double reach = 1.2 * half;
+        if (c->boardPosMax >= 0.0f)       // the march runs from the near hit (-h along the ray) to at most 3h: |o_k + s ray_k| <= r sqrt(1 + 9 ray_k^2)
+            reach = std::max(reach, std::ceil((double)c->boardPosMax + 3.2 * c->boardScaleMax * c->vol.fluffiness + std::fabs(mid - c->vol.position[k])));
+        reach = std::min(reach, 2.5 * half);                               // (a cap: billboards beyond it take the per-octave path)
+        wlo[k] = mid - reach; whi[k] = mid + reach;
+        const long long b = (long long)std::floor(wlo[k] / p.adjustSize * K - 0.5) - 1;
+        const long long t = (long long)std::ceil(whi[k] / p.adjustSize * K - 0.5) + 1;
+        base[k] = b; n[k] = (int)(t - b + 1);
+        nodes *= (size_t)n[k];
+    }
+    if (nodes * 8 > ((size_t)512 << 20)) {                                 // memory cap: shrink the window around the volume's centre
+        const double f = std::cbrt((double)((size_t)512 << 20) / (double)(nodes * 8)) * 0.99;
+        nodes = 1;
+        for (int k = 0; k < 3; k++) {
+            const double mid = 0.5 * (wlo[k] + whi[k]), reach = 0.5 * (whi[k] - wlo[k]) * f;
+            wlo[k] = mid - reach; whi[k] = mid + reach;
+            const long long b = (long long)std::floor(wlo[k] / p.adjustSize * K - 0.5) - 1;
+            const long long t = (long long)std::ceil(whi[k] / p.adjustSize * K - 0.5) + 1;
+            base[k] = b; n[k] = (int)(t - b + 1);
+            nodes *= (size_t)n[k];
+        }
+    }
+    for (int k = 0; k < 3; k++)
+        if (n[k] < 4 || n[k] > 2000) return CRN_OK;
+    if ((size_t)n[1] * n[2] / 8 + 1 > 65535) return CRN_OK;
+    crn_ctx::LatKey key{};
+    key.noiseGen = c->noiseGen; key.dim = c->noiseDim; key.octaves = p.numOctaves; key.freqStep = fs; key.persStep = p.persStep; key.adjust = p.adjustSize;
+    for (int k = 0; k < 3; k++) { key.n[k] = n[k]; key.base[k] = base[k]; }
+    float scale = 0.0f;
+    for (int o = 1; o <= F; o++) scale += fabsf(tp.octPers[o]);
+    if (!(scale > 0.0f)) return CRN_OK;
+    if (!c->latValid || std::memcmp(&key, &c->latKey, sizeof key) != 0) {
+        if (!c->latArray || c->latN[0] != n[0] || c->latN[1] != n[1] || c->latN[2] != n[2]) {
+            sync_all(c);
+            free_lattice(c);
+            cudaChannelFormatDesc cd = cudaCreateChannelDesc(16, 16, 16, 16, cudaChannelFormatKindSigned);
+            CRN_CUDA(c, cudaMalloc3DArray(&c->latArray, &cd, make_cudaExtent(n[0], n[1], n[2] - 1), cudaArrayLayered | cudaArraySurfaceLoadStore));
+            cudaResourceDesc rd{};
+            rd.resType = cudaResourceTypeArray; rd.res.array.array = c->latArray;
+            CRN_CUDA(c, cudaCreateSurfaceObject(&c->latSurf, &rd));
+            cudaTextureDesc td{};
+            td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+            td.filterMode = cudaFilterModeLinear; td.readMode = cudaReadModeNormalizedFloat; td.normalizedCoords = 0;
+            CRN_CUDA(c, cudaCreateTextureObject(&c->latTex, &rd, &td, nullptr));
+            for (int k = 0; k < 3; k++) c->latN[k] = n[k];
+        }
+        // every trace in flight may be reading the old lattice
+        if (c->traceEndValid) cudaStreamWaitEvent(c->lightStream, c->evTraceEnd, 0);
+        double m[kMaxOctaves] = {};
+        for (int o = 0; o <= F; o++) m[o] = (double)tp.octFreq[F] / (double)tp.octFreq[o];
+        c->launches += launch_noise_lattice(c->lightStream, (const float2 *)c->noise.p, c->noiseDim, n, base, 1, F, m, tp.octPers, 1.0f / scale, c->latSurf);
+        CRN_CUDA(c, cudaGetLastError());
+        c->latKey = key; c->latValid = true;
+    }
+    L.on = 1;
+    L.K = (float)K;
+    for (int k = 0; k < 3; k++) {
+        // uv = world / adjustSize; lattice coordinate = uv * K - 1/2; node index = that - base
+        L.B[k] = (float)(-0.5 - (double)base[k] + (k < 2 ? 0.5 : 0.0));
+        // the window the kernel tests against: one node inside the baked box on every side
+        const double a = ((double)base[k] + 1.0 + 0.5) / K * p.adjustSize, b = ((double)base[k] + n[k] - 2.0 + 0.5) / K * p.adjustSize;
+        L.winC[k] = (float)(0.5 * (a + b)); L.winH[k] = (float)(0.5 * (b - a) * (1.0 - 1e-5));
+        L.ext[k] = sqrtf(1.0f + 9.0f * cam.nrm[k] * cam.nrm[k]) * 1.001f;
+    }
+    L.scale = scale;
+    L.tex = (unsigned long long)c->latTex;
+    return CRN_OK;
+}
+
 int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
     DevBuf &img = target ? *target : c->image;
     const int n = c->nBoards;
@@ -813,6 +926,7 @@ int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
         }
     }
     if (c->timingOn) cudaEventRecord(c->evT[2], ls);                // the cone acceleration data is part of the trace stage
+    if ((r = ensure_noise_lattice(c, cam, tp))) return r;
     if ((r = build_cone_accel(c, tp))) return r;
     if (c->timingOn) cudaEventRecord(c->evT[1], ls);
     // ---- camera-side set-up on the side stream, into the camera set the trace before last used: concurrent with the
@@ -939,6 +1053,7 @@ int crn_create(int device, void *stream, crn_ctx **out) {
     for (auto &ev : c->evT) cudaEventCreate(&ev);
     crn_default_trace_params(&c->tp);
     if (const char *nb = getenv("CRN_NO_BAKE")) c->noBake = atoi(nb) != 0;
+    if (const char *nl = getenv("CRN_NO_LATTICE")) c->noLattice = atoi(nl) != 0;
     if (const char *sg = getenv("CRN_TRACE_SEGMENTS")) c->segOverride = atoi(sg);
     if (const char *pm = getenv("CRN_BIN_POOL_MIN")) { const long v = atol(pm); if (v > 0) c->poolMin = (size_t)v; }
     if ((e = cudaGetLastError()) != cudaSuccess) {
@@ -977,6 +1092,7 @@ void crn_destroy(crn_ctx *c) {
     for (auto &ev : c->evAccT) if (ev) cudaEventDestroy(ev);
     if (c->noiseTex) cudaDestroyTextureObject(c->noiseTex);
     if (c->noiseArray) cudaFreeArray(c->noiseArray);
+    free_lattice(c);
     if (c->hCursors) cudaFreeHost(c->hCursors);
     if (c->hStats) cudaFreeHost(c->hStats);
     for (auto &ev : c->evV) if (ev) cudaEventDestroy(ev);
@@ -1062,6 +1178,16 @@ int crn_set_billboards(crn_ctx *c, const float *positions3, const float *scales,
     c->nBoards = count;
     c->havePos0 = false;
     c->boardsGen++;
+    c->boardPosMax = -1.0f; c->boardScaleMax = 0.0f;
+    if (mem == CRN_MEM_HOST) {                           // what the noise-lattice window is sized from (ensure_noise_lattice)
+        float pm = 0.0f, sm = 0.0f;
+        for (int i = 0; i < count; i++) {
+            const float x = positions3[3 * i], y = positions3[3 * i + 1], z = positions3[3 * i + 2];
+            pm = fmaxf(pm, fmaxf(x * x + z * z, y * y));
+            sm = fmaxf(sm, fabsf(scales[i]));
+        }
+        c->boardPosMax = sqrtf(pm); c->boardScaleMax = sm;
+    }
     return CRN_OK;
 }
 
@@ -1081,6 +1207,12 @@ int crn_regenerate_billboards(crn_ctx *c, int32_t count, const float minOffset[3
     c->nBoards = count;
     c->havePos0 = true;
     c->boardsGen++;
+    {
+        float m[3];
+        for (int k = 0; k < 3; k++) m[k] = fmaxf(fabsf(minOffset[k]), fabsf(maxOffset[k]));
+        c->boardPosMax = fmaxf(sqrtf(m[0] * m[0] + m[2] * m[2]), m[1]);
+    }
+    c->boardScaleMax = (float)(fmax(fabs((double)minScale), fabs((double)maxScale)) * fabs(radiusFactor));
     return CRN_OK;
 }
 
@@ -1230,6 +1362,7 @@ int crn_set_noise(crn_ctx *c, const int8_t *rgba, int32_t dim) {
     CRN_CUDA(c, cudaCreateTextureObject(&c->noiseTex, &rd, &td, nullptr));
     c->vset[0].ts.noise = c->vset[1].ts.noise = c->noiseTex;
     c->noiseDim = dim; c->haveNoise = true;
+    c->noiseGen++;
     return CRN_OK;
 }
 

@@ -92,6 +92,19 @@ struct FastConst {
     float invDim;
 };
 
+// The combined-octave noise lattice (k_noiselat.cu): octaves [1, numOctaves) of noise3D pre-summed on the texel lattice of the
+// finest octave, inside a world-space window.  A billboard whose noise march stays inside the window (centre +- radius *
+// ext[k] within winC[k] +- winH[k]) reads it with one bilinear pass per march step instead of one per octave.
+struct NoiseLat {
+    int32_t on;
+    float K;                          // lattice units per unit of uv (= world / adjustSize): freq_F * noiseDim
+    float B[3];                       // x, y: unnormalized texel coordinate = uv * K + B (node i at i + 1/2);  z: node coordinate = uv * K + B
+    float scale;                      // stored value * scale = the octave sum
+    float winC[3], winH[3];           // window centre and half size, world units
+    float ext[3];                     // reach of a billboard's march per unit radius: sqrt(1 + 9 viewRay_k^2) (the march overshoots the far hit by up to a chord)
+    unsigned long long tex;           // layered RGBA16_SNORM, LINEAR, CLAMP, unnormalized coordinates
+};
+
 struct TraceParams {
     crn_trace_params p;
     float lightPos[3];
@@ -119,6 +132,7 @@ struct TraceParams {
     int32_t codeDim;                  // cells per axis of the need-code grid (0: no empty-space skipping)
     float codeDimF;
     FastConst f;
+    NoiseLat lat;
     BakedStep baked[kMaxBakedSteps];
     ConeStep steps[kMaxConeSteps];
     ConeGroup groups[kMaxConeSteps];
@@ -182,6 +196,8 @@ int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol
                  int format, unsigned long long *stats, float4 *segPartial, uint32_t *segArrived);
 int launch_bake_steps(cudaStream_t st, const VolumeParams &vol, const uint32_t *bits, const uint8_t *chain, const BakeTex *tex, int nTex);
 int launch_need_code(cudaStream_t st, const VolumeParams &vol, const TraceParams &tp, const uint32_t *mask, const uint32_t *worldBox, uint8_t *code);
+int launch_noise_lattice(cudaStream_t st, const float2 *noise, int dim, const int n[3], const long long base[3], int first, int last,
+                         const double *m, const float *pers, float invScale, cudaSurfaceObject_t surf);
 size_t skipmask_words(const VolumeParams &vol, uint32_t *off);
 int launch_skipmask(cudaStream_t st, const VolumeParams &vol, const uint32_t *bits, const uint8_t *chain, uint32_t *nz,
                     uint32_t *dil, uint32_t *mask, uint32_t *fill);

@@ -16,6 +16,11 @@
 //  12  tex3DLod on the mipmapped R8 256^3 volume at LOD 2.5
 //  13  tex2DLayered bilinear, RG16F 129x129x128 layers
 //  14  tex3D RGBA8_SNORM 32^3 sampled exactly AT slice centres in z (does the filter skip the zero-weight slice?)
+//  15  tex2DLayered bilinear, RGBA16_SNORM 161x161x160 layers (64-bit texels, 33 MB: L2-resident), strided: every fetch of a warp
+//      lands several texels from the last one (the combined-octave noise lattice's access pattern)
+//  16  the same pattern on RGBA8_SNORM 161x161x160 (32-bit texels)
+//  17  tex3D trilinear, RG16_SNORM 161^3, the same pattern
+//  18  as 15 but L1-friendly steps (the format's filter rate without misses)
 // Each returns giga-operations per second (lane-level operations), timed with CUDA events.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -101,6 +106,40 @@ __global__ void __launch_bounds__(256) tex_layered_h2_kernel(cudaTextureObject_t
         u += step; v += step * 0.7f; layer = (layer + (i & 1)) & 31;
     }
     if (a0 + a1 == 0x12345678u) out[0] = 1.0f;
+}
+
+// four-channel layered texture, every iteration jumps `step` (normalized) in u/v and to another layer
+__global__ void __launch_bounds__(256) tex_layered4_kernel(cudaTextureObject_t tex, float *out, float step, int layers) {
+    const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    float u = 0.1f + (lane & 7) * 0.0013f + (warp % 97) * 0.008f, v = 0.1f + (lane >> 3) * 0.0013f + (warp % 89) * 0.009f;
+    int layer = warp % layers;
+    float4 acc = make_float4(0, 0, 0, 0);
+#pragma unroll 8
+    for (int i = 0; i < kIters; i++) {
+        const float4 t = tex2DLayered<float4>(tex, u, v, layer);
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        u += step; v += step * 0.7f; layer += 3; if (layer >= layers) layer -= layers;
+        if (u > 0.9f) u -= 0.8f;
+        if (v > 0.9f) v -= 0.8f;
+    }
+    if (acc.x + acc.y + acc.z + acc.w == 12345.678f) out[0] = acc.x;
+}
+
+__global__ void __launch_bounds__(256) tex_vol2_kernel(cudaTextureObject_t tex, float *out, float step) {
+    const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    float u = 0.1f + (lane & 7) * 0.0013f + (warp % 97) * 0.008f, v = 0.1f + (lane >> 3) * 0.0013f + (warp % 89) * 0.009f,
+          w = 0.1f + (warp % 83) * 0.0095f;
+    float2 acc = make_float2(0, 0);
+#pragma unroll 8
+    for (int i = 0; i < kIters; i++) {
+        const float2 t = tex3D<float2>(tex, u, v, w);
+        acc.x += t.x; acc.y += t.y;
+        u += step; v += step * 0.7f; w += 0.019f;
+        if (u > 0.9f) u -= 0.8f;
+        if (v > 0.9f) v -= 0.8f;
+        if (w > 0.9f) w -= 0.8f;
+    }
+    if (acc.x + acc.y == 12345.678f) out[0] = acc.x;
 }
 
 __global__ void __launch_bounds__(256) tex_lod_kernel(cudaTextureObject_t tex, float *out, float step, float lod) {
@@ -274,6 +313,26 @@ extern "C" int crn_microbench(int device, int which, double *gops) {
         cudaTextureObject_t tex = 0;
         cudaCreateTextureObject(&tex, &rd, &td, nullptr);
         ms = time_ms([&] { tex_layered2_kernel<<<blocks, threads>>>(tex, dOut, 0.0009f, layers); }, 5);
+        cudaDestroyTextureObject(tex);
+        cudaFreeArray(arr);
+    } else if (which >= 15 && which <= 18) {
+        const int n = 161, layers = 160;
+        const bool vol = which == 17;
+        const int bits = which == 16 ? 8 : 16, chans = vol ? 2 : 4;
+        cudaChannelFormatDesc cd = cudaCreateChannelDesc(bits, bits, chans == 4 ? bits : 0, chans == 4 ? bits : 0, cudaChannelFormatKindSigned);
+        cudaArray_t arr = nullptr;
+        const int depth = vol ? n : layers;
+        if (cudaMalloc3DArray(&arr, &cd, make_cudaExtent(n, n, depth), vol ? 0 : cudaArrayLayered) != cudaSuccess) { cudaFree(dOut); return CRN_ERR_CUDA; }
+        const size_t texel = (size_t)bits / 8 * chans;
+        std::vector<uint8_t> h((size_t)n * n * depth * texel);
+        for (size_t i = 0; i < h.size(); i++) h[i] = (uint8_t)(i * 2654435761u >> 24);
+        cudaMemcpy3DParms cp{};
+        cp.srcPtr = make_cudaPitchedPtr(h.data(), n * texel, n, n);
+        cp.dstArray = arr; cp.extent = make_cudaExtent(n, n, depth); cp.kind = cudaMemcpyHostToDevice;
+        cudaMemcpy3D(&cp);
+        cudaTextureObject_t tex = make_tex(arr, false);
+        if (vol) ms = time_ms([&] { tex_vol2_kernel<<<blocks, threads>>>(tex, dOut, 0.031f); }, 5);
+        else ms = time_ms([&] { tex_layered4_kernel<<<blocks, threads>>>(tex, dOut, which == 18 ? 0.0009f : 0.031f, which == 18 ? 1 : layers); }, 5);
         cudaDestroyTextureObject(tex);
         cudaFreeArray(arr);
     } else if (which == 9) {

@@ -1,0 +1,100 @@
+// k_noiselat.cu — the combined-octave noise lattice of noise3D (res/conetrace_frag.glsl:103-120).
+//
+// noise3D sums `octaves` lookups of ONE 32^3 REPEAT/LINEAR texture at coordinates (uv + offset_o) * freq_o.  Each term
+// is piecewise trilinear in uv with its kinks on the planes through that octave's texel centres,
+//     (uv + offset_o) * freq_o * n - 1/2  in Z.
+// When freq_F / freq_o is an odd integer and the offsets agree, every kink plane of octave o is also a kink plane of
+// the finest octave F (texel centre k of octave o = texel centre m*k + (m-1)/2 of octave F, m = freq_F / freq_o).  The
+// SUM of those octaves is then trilinear inside every texel cell of octave F, so linear interpolation of its values at
+// the nodes of that lattice reproduces it exactly.  With the reference's parameters (freqStep 3, wind along x only:
+// octaveOffsets = (windVel.x * t, 0, 0), octave 3 reads past the vec3, 0 by decree) octaves 1, 2 and 3 qualify; octave 0
+// carries the wind offset and stays a lookup of its own.
+//
+// This kernel evaluates  sum_{o in 1..3} pers_o * texture(noiseMap, uv * freq_o).ga  at the lattice nodes of a window
+// around the volume (in double: the filter weights are exact rationals k / (2m)) and stores it as SNORM16 slice pairs:
+// layer k of the layered RGBA16 array holds (g, a) of node plane k in .xy and of plane k+1 in .zw, like the noise
+// texture itself (crn_set_noise), so the trace kernel needs ONE bilinear pass + a z blend where it needed three.
+// The lattice depends on the noise texture, freqStep, persStep and the window only: it is baked once, not per frame.
+// SNORM16 storage: 1.5e-5 absolute, far below the 8-bit filter weights of the texture unit.
+#include "crn_internal.cuh"
+
+namespace crn {
+
+namespace {
+
+struct LatArgs {
+    const float2 *noise;          // (g, a) decoded, dim^3
+    int dim;
+    int n[3];                     // nodes per axis
+    long long base[3];            // lattice index of node 0 (texel index of the finest combined octave, unwrapped)
+    int first, last;              // combined octaves [first, last]
+    double m[kMaxOctaves];        // freq_last / freq_o
+    float pers[kMaxOctaves];
+    float invScale;
+    cudaSurfaceObject_t surf;
+};
+
+struct Axis {
+    int i0, i1;
+    double w;
+};
+
+// texel coordinate t (texel centres at integers) on a REPEAT axis of n texels
+__device__ __forceinline__ Axis repeat_axis(double t, int n) {
+    Axis a;
+    const double fl = floor(t);
+    a.w = t - fl;
+    long long i = (long long)fl % n;
+    if (i < 0) i += n;
+    a.i0 = (int)i;
+    a.i1 = a.i0 + 1 == n ? 0 : a.i0 + 1;
+    return a;
+}
+
+__global__ void __launch_bounds__(256) noise_lattice_kernel(const __grid_constant__ LatArgs a) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int yk = blockIdx.y * 8 + (threadIdx.x >> 5);             // y + n[1] * k
+    if (x >= a.n[0] || yk >= a.n[1] * a.n[2]) return;
+    const int y = yk % a.n[1], k = yk / a.n[1];
+    const int node[3] = {x, y, k};
+    double g = 0.0, al = 0.0;
+    for (int o = a.first; o <= a.last; o++) {
+        Axis ax[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            // texel coordinate of octave `last` at this node = base + node; of octave o: (lambda + 1/2) / m - 1/2
+            const double lam = (double)(a.base[d] + node[d]);
+            ax[d] = repeat_axis((lam + 0.5) / a.m[o] - 0.5, a.dim);
+        }
+        double sg = 0.0, sa = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int ix = (q & 1) ? ax[0].i1 : ax[0].i0, iy = (q & 2) ? ax[1].i1 : ax[1].i0, iz = (q & 4) ? ax[2].i1 : ax[2].i0;
+            const double w = ((q & 1) ? ax[0].w : 1.0 - ax[0].w) * ((q & 2) ? ax[1].w : 1.0 - ax[1].w) * ((q & 4) ? ax[2].w : 1.0 - ax[2].w);
+            const float2 t = __ldg(a.noise + ((size_t)iz * a.dim + iy) * a.dim + ix);
+            sg += w * (double)t.x; sa += w * (double)t.y;
+        }
+        g += (double)a.pers[o] * sg; al += (double)a.pers[o] * sa;
+    }
+    const int qg = max(-32767, min(32767, (int)rint(g * (double)a.invScale * 32767.0)));
+    const int qa = max(-32767, min(32767, (int)rint(al * (double)a.invScale * 32767.0)));
+    const short2 v = make_short2((short)qg, (short)qa);
+    if (k < a.n[2] - 1) surf2DLayeredwrite(v, a.surf, x * 8, y, k);
+    if (k > 0) surf2DLayeredwrite(v, a.surf, x * 8 + 4, y, k - 1);
+}
+
+} // namespace
+
+int launch_noise_lattice(cudaStream_t st, const float2 *noise, int dim, const int n[3], const long long base[3], int first, int last,
+                         const double *m, const float *pers, float invScale, cudaSurfaceObject_t surf) {
+    LatArgs a{};
+    a.noise = noise; a.dim = dim;
+    for (int d = 0; d < 3; d++) { a.n[d] = n[d]; a.base[d] = base[d]; }
+    a.first = first; a.last = last;
+    for (int o = 0; o < kMaxOctaves; o++) { a.m[o] = m[o]; a.pers[o] = pers[o]; }
+    a.invScale = invScale; a.surf = surf;
+    noise_lattice_kernel<<<dim3((n[0] + 31) / 32, (n[1] * n[2] + 7) / 8), 256, 0, st>>>(a);
+    return 1;
+}
+
+} // namespace crn

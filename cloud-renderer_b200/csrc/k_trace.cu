@@ -585,6 +585,41 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_fast_kern
         float s1 = -h * invAdjust;                                      // texture-space distance from the plane point
         float s2 = -h * invr;                                           // unit-sphere distance from the plane (sic: advanced by the texture-space step)
         float opacity = 0.0f, light = 0.0f;
+        // the combined-octave lattice (k_noiselat.cu) covers this billboard's whole march if the sphere, stretched along the
+        // view ray by the march's overshoot, lies inside the baked window (r0 is warp-uniform, so is the branch)
+        const bool inLat = tp.lat.on && fmaf(radius, tp.lat.ext[0], fabsf(r0.x - tp.lat.winC[0])) <= tp.lat.winH[0] &&
+                           fmaf(radius, tp.lat.ext[1], fabsf(r0.y - tp.lat.winC[1])) <= tp.lat.winH[1] &&
+                           fmaf(radius, tp.lat.ext[2], fabsf(r0.z - tp.lat.winC[2])) <= tp.lat.winH[2];
+        if (inLat) {
+            // every lookup coordinate is affine in the march distance: six running sums, no constants inside the loop
+            const float K = tp.lat.K;
+            const float c0x = fmaf(s1, rx, qax), c0y = fmaf(s1, ry, qay), c0z = fmaf(s1, rz, qaz);
+            float u0 = c0x + tp.octBias[0], v0 = c0y + tp.octBias[0], z0 = fmaf(c0z, tp.octFreqZ[0], tp.octBiasZ[0]);
+            float u1 = fmaf(c0x, K, tp.lat.B[0]), v1 = fmaf(c0y, K, tp.lat.B[1]), z1 = fmaf(c0z, K, tp.lat.B[2]);
+            const float du0 = sStep * rx, dv0 = sStep * ry, dz0 = sStep * (rz * tp.octFreqZ[0]);
+            const float du1 = du0 * K, dv1 = dv0 * K, dz1 = sStep * (rz * K);
+            for (int i = 0; i < nMax; i++) {
+                if (i < nIter) {
+                    // octave 0 (it alone carries the wind offset): the noise texture's slice pairs, as below
+                    const float m = __fadd_rd(z0, 12582912.0f);
+                    const float az = __fadd_rn(z0, -__fadd_rn(m, -12582912.0f));
+                    const float4 t = tex_layer4(ts.noise, __float_as_int(m) & 31, u0, v0);
+                    // octaves 1..3, pre-summed on the finest octave's texel lattice: node planes floor(z) and floor(z)+1
+                    const float ml = __fadd_rd(z1, 12582912.0f);
+                    const float al = __fadd_rn(z1, -__fadd_rn(ml, -12582912.0f));
+                    const float4 q = tex_layer4(tp.lat.tex, __float_as_int(ml) & 0x7FF, u1, v1);
+                    const float sg = fmaf(az, t.z - t.x, t.x), sa = fmaf(az, t.w - t.y, t.y);
+                    float ng = fmaf(tp.lat.scale, fmaf(al, q.z - q.x, q.x), sg);
+                    const float na = fmaf(tp.lat.scale, fmaf(al, q.w - q.y, q.y), sa);
+                    const float uu = fmaf(s2, s2, uu0);
+                    ng = fmaf(fmaf(s2, ry, vy0), rsqrtf(uu), ng);
+                    opacity = fmaf(fabsf(na), 1.0f - uu, opacity);
+                    light += fma_sat(ng, 0.5f, 0.5f);
+                    u0 += du0; v0 += dv0; z0 += dz0; u1 += du1; v1 += dv1; z1 += dz1;
+                    s2 += sStep;
+                }
+            }
+        } else
         for (int i = 0; i < nMax; i++) {
             if (i < nIter) {
                 const float cx = fmaf(s1, rx, qax), cy = fmaf(s1, ry, qay), cz = fmaf(s1, rz, qaz);

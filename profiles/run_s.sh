@@ -1,0 +1,7 @@
+#!/bin/bash
+# full ncu capture (with source) of the C3 trace kernel
+mkdir -p gpurun_out
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:trace_fast_kernel -s 3 -c 1 -f -o gpurun_out/trace_s \
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras > gpurun_out/ncu_s.log 2>&1
+tail -3 gpurun_out/ncu_s.log | head -c 600
+ls -la gpurun_out/

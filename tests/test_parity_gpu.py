@@ -795,10 +795,12 @@ def test_noise_sizes_and_cone_settings_off_the_fast_path(dim, octaves, steps, an
 
 @pytest.mark.parametrize("name", ["small", "C1", "C2crop"])
 def test_fast_generic_baked_and_textureLod_paths_agree(name, pkg, scenes, orc):
-    """Three routes to the same image with the texture sampler: the fast kernel, the generic kernel (CRN_NO_FAST) and the
-    generic kernel with every cone step fetched by textureLod instead of the baked step textures (CRN_NO_BAKE).  Fast and
-    generic issue the same lookups (differences: float re-association only); baked and textureLod differ by the texture
-    unit's filter precision (the baked lattice is finer than the level it replaces).  All three >= 45 dB vs the oracle."""
+    """Four routes to the same image with the texture sampler: the fast kernel with the combined-octave noise lattice
+    (k_noiselat.cu), the fast kernel with one lookup per octave (CRN_NO_LATTICE), the generic kernel (CRN_NO_FAST) and the
+    generic kernel with every cone step fetched by textureLod instead of the baked step textures (CRN_NO_BAKE).  Fast
+    without the lattice and generic issue the same lookups (differences: float re-association only); lattice vs
+    per-octave and baked vs textureLod differ by the texture unit's filter precision (both lattices are finer than what
+    they replace).  All four >= 45 dB vs the oracle."""
     import os
     s = scenes.make_scene("C2", boards=600, size=(640, 360)) if name == "C2crop" else scenes.make_scene(name)
     s = steady_state(s, orc)
@@ -807,6 +809,11 @@ def test_fast_generic_baked_and_textureLod_paths_agree(name, pkg, scenes, orc):
     ref, _, _ = orc.cone_trace(s, orc.mips(l0, s.vol.levels))
     imgs = {}
     try:
+        r = pkg.Renderer(0)
+        r.set_scene(s); r.voxelize()
+        imgs["lattice"] = r.cone_trace(fmt=pkg.IMAGE_RGBA32F).copy()
+        r.close()
+        os.environ["CRN_NO_LATTICE"] = "1"
         r = pkg.Renderer(0)
         r.set_scene(s); r.voxelize()
         imgs["fast"] = r.cone_trace(fmt=pkg.IMAGE_RGBA32F).copy()
@@ -824,10 +831,12 @@ def test_fast_generic_baked_and_textureLod_paths_agree(name, pkg, scenes, orc):
     finally:
         os.environ.pop("CRN_NO_FAST", None)
         os.environ.pop("CRN_NO_BAKE", None)
+        os.environ.pop("CRN_NO_LATTICE", None)
     for k, im in imgs.items():
         p = psnr(im, ref)
         print(f"{name}/{k}: PSNR {p:.2f} dB vs oracle, max err {np.abs(im - ref).max():.3e}")
         assert p >= 45.0
-    pf, pb = psnr(imgs["fast"], imgs["generic"]), psnr(imgs["generic"], imgs["textureLod"])
-    print(f"{name}: fast vs generic {pf:.1f} dB, baked vs textureLod {pb:.1f} dB")
-    assert pf >= 99.0 and pb >= 60.0
+    pf, pb, pl = psnr(imgs["fast"], imgs["generic"]), psnr(imgs["generic"], imgs["textureLod"]), psnr(imgs["lattice"], imgs["fast"])
+    print(f"{name}: fast vs generic {pf:.1f} dB, baked vs textureLod {pb:.1f} dB, lattice vs per-octave {pl:.1f} dB")
+    assert pf >= 99.0 and pb >= 60.0 and pl >= 80.0
+    assert not np.array_equal(imgs["lattice"], imgs["fast"]), "the lattice route was not taken"
