@@ -190,8 +190,8 @@ struct crn_ctx {
         bool freeValid = false;
     } cset[2];
     int cs = 0;
-    cudaArray_t noiseArray = nullptr;
-    cudaTextureObject_t noiseTex = 0;
+    cudaArray_t noiseArray = nullptr, noiseArrayD = nullptr;
+    cudaTextureObject_t noiseTex = 0, noiseTexD = 0;
     // combined-octave noise lattice (k_noiselat.cu): baked when the noise texture, the octave parameters or the window change
     struct LatKey { uint64_t noiseGen; int dim, octaves; float freqStep, persStep, adjust; int n[3]; long long base[3]; };
     cudaArray_t latArray = nullptr;
@@ -495,7 +495,7 @@ int ensure_baked_array(crn_ctx *c, int i, int n) {
     if (VS(c).bakedArr[i] && VS(c).bakedN[i] == n) return CRN_OK;
     sync_all(c);
     free_baked(c, i);
-    cudaChannelFormatDesc cd = cudaCreateChannelDesc(16, 16, 0, 0, cudaChannelFormatKindUnsigned);
+    cudaChannelFormatDesc cd = cudaCreateChannelDesc(16, 16, 0, 0, cudaChannelFormatKindSigned);     // (value, step to the next plane)
     CRN_CUDA(c, cudaMalloc3DArray(&VS(c).bakedArr[i], &cd, make_cudaExtent(n, n, n - 1), cudaArrayLayered | cudaArraySurfaceLoadStore));
     cudaResourceDesc rd{};
     rd.resType = cudaResourceTypeArray; rd.res.array.array = VS(c).bakedArr[i];
@@ -941,7 +941,7 @@ int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
                                     zero3, 1.0f, cam, c->cam.position, false, true, nullptr, (uint32_t *)c->rankC.p, nullptr,
                                     (uint64_t *)c->keyC.p, nullptr, (BoardRec *)c->recTmpC.p, nullptr, (BoardRect *)c->rectTmpC.p,
                                     nullptr, nullptr, (BoardRec *)CS(c).recC.p, nullptr, (BoardRect *)CS(c).rectC.p, nullptr,
-                                    (int32_t *)c->drawOrder.p, CS(c).sortTmpC.p);
+                                    (int32_t *)c->drawOrder.p, CS(c).sortTmpC.p, &tp.lat);
     if (c->timingOn) cudaEventRecord(c->evAuxT[1], ax);
     c->launches += launch_bin(ax, (const BoardRect *)CS(c).rectC.p, sort_tmp_bounds(CS(c).sortTmpC.p, (int)nn, 1), n, c->W, c->H, CS(c).binsC);
     cudaEventRecord(c->evBin[1], ax);
@@ -1092,6 +1092,8 @@ void crn_destroy(crn_ctx *c) {
     for (auto &ev : c->evAccT) if (ev) cudaEventDestroy(ev);
     if (c->noiseTex) cudaDestroyTextureObject(c->noiseTex);
     if (c->noiseArray) cudaFreeArray(c->noiseArray);
+    if (c->noiseTexD) cudaDestroyTextureObject(c->noiseTexD);
+    if (c->noiseArrayD) cudaFreeArray(c->noiseArrayD);
     free_lattice(c);
     if (c->hCursors) cudaFreeHost(c->hCursors);
     if (c->hStats) cudaFreeHost(c->hStats);
@@ -1340,6 +1342,8 @@ int crn_set_noise(crn_ctx *c, const int8_t *rgba, int32_t dim) {
     sync_all(c);
     if (c->noiseTex) { cudaDestroyTextureObject(c->noiseTex); c->noiseTex = 0; }
     if (c->noiseArray) { cudaFreeArray(c->noiseArray); c->noiseArray = nullptr; }
+    if (c->noiseTexD) { cudaDestroyTextureObject(c->noiseTexD); c->noiseTexD = 0; }
+    if (c->noiseArrayD) { cudaFreeArray(c->noiseArrayD); c->noiseArrayD = nullptr; }
     std::vector<int8_t> pairs(n * 4);
     for (int z = 0; z < dim; z++) {
         const size_t z0 = (size_t)z * dim * dim, z1 = (size_t)((z + 1) % dim) * dim * dim;
@@ -1361,6 +1365,31 @@ int crn_set_noise(crn_ctx *c, const int8_t *rgba, int32_t dim) {
     td.filterMode = cudaFilterModeLinear; td.readMode = cudaReadModeNormalizedFloat; td.normalizedCoords = 1;
     CRN_CUDA(c, cudaCreateTextureObject(&c->noiseTex, &rd, &td, nullptr));
     c->vset[0].ts.noise = c->vset[1].ts.noise = c->noiseTex;
+    {   // the fast trace variant's copy: RGBA16_SNORM (g_z, a_z, g_z+1 - g_z, a_z+1 - a_z) / 2, so the z blend is one FMA per
+        // channel.  Codes round(v * 16383.5) read back as v / 2 (to 1.5e-5); the step is the difference of the CODES, so
+        // plane z + its step is exactly plane z+1.
+        std::vector<int16_t> d(n * 4);
+        auto code = [](int8_t v) { return std::max(-16383, std::min(16383, (int)lrintf(fmaxf((float)v / 127.0f, -1.0f) * 16383.5f))); };   // |step| <= 32766
+        for (int z = 0; z < dim; z++) {
+            const size_t z0 = (size_t)z * dim * dim, z1 = (size_t)((z + 1) % dim) * dim * dim;
+            for (size_t i = 0; i < (size_t)dim * dim; i++) {
+                const int g0 = code(rgba[4 * (z0 + i) + 1]), a0 = code(rgba[4 * (z0 + i) + 3]);
+                const int g1 = code(rgba[4 * (z1 + i) + 1]), a1 = code(rgba[4 * (z1 + i) + 3]);
+                d[4 * (z0 + i) + 0] = (int16_t)g0; d[4 * (z0 + i) + 1] = (int16_t)a0;
+                d[4 * (z0 + i) + 2] = (int16_t)(g1 - g0); d[4 * (z0 + i) + 3] = (int16_t)(a1 - a0);
+            }
+        }
+        cudaChannelFormatDesc cdD = cudaCreateChannelDesc(16, 16, 16, 16, cudaChannelFormatKindSigned);
+        CRN_CUDA(c, cudaMalloc3DArray(&c->noiseArrayD, &cdD, make_cudaExtent(dim, dim, dim), cudaArrayLayered));
+        cudaMemcpy3DParms cpD{};
+        cpD.srcPtr = make_cudaPitchedPtr((void *)d.data(), (size_t)dim * 8, dim, dim);
+        cpD.dstArray = c->noiseArrayD; cpD.extent = make_cudaExtent(dim, dim, dim); cpD.kind = cudaMemcpyHostToDevice;
+        CRN_CUDA(c, cudaMemcpy3D(&cpD));
+        cudaResourceDesc rdD{};
+        rdD.resType = cudaResourceTypeArray; rdD.res.array.array = c->noiseArrayD;
+        CRN_CUDA(c, cudaCreateTextureObject(&c->noiseTexD, &rdD, &td, nullptr));
+        c->vset[0].ts.noiseD = c->vset[1].ts.noiseD = c->noiseTexD;
+    }
     c->noiseDim = dim; c->haveNoise = true;
     c->noiseGen++;
     return CRN_OK;
@@ -1754,7 +1783,7 @@ int crn_read_bins(crn_ctx *c, int32_t which, int32_t *tiles_x, int32_t *tiles_y,
         CRN_CUDA(c, cudaMemcpy(rec.data(), recs.p, (size_t)c->nBoards * sizeof(BoardRec), cudaMemcpyDeviceToHost));
         size_t o = 0;
         for (size_t t = 0; t < tiles; t++)
-            for (uint32_t e = 0; e < cnt[t]; e++) entries[o++] = rec[list[off[t] + e]].idx;
+            for (uint32_t e = 0; e < cnt[t]; e++) entries[o++] = rec[list[off[t] + e]].idx & kRecIndexMask;
     }
     return CRN_OK;
 }

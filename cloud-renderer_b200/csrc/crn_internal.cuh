@@ -27,8 +27,10 @@ constexpr int kCodeGroups = 8;       // empty-space groups with a bit in the nee
 struct BoardRec {
     float cx, cy, cz, r;     // world-space centre (volumePosition + boardPosition), radius (scale * fluffiness)
     float xv, yv, zv;        // V * (centre, 1)
-    int32_t idx;             // instance index in the caller's arrays
+    int32_t idx;             // instance index in the caller's arrays (low 30 bits) | kRecInLattice (camera pass)
 };
+constexpr int32_t kRecInLattice = 1 << 30;    // the billboard's noise march stays inside the noise-lattice window (k_noiselat.cu)
+constexpr int32_t kRecIndexMask = kRecInLattice - 1;
 
 // inclusive pixel rectangle of the quad (i1 < i0: clipped away)
 struct BoardRect {
@@ -99,7 +101,7 @@ struct NoiseLat {
     int32_t on;
     float K;                          // lattice units per unit of uv (= world / adjustSize): freq_F * noiseDim
     float B[3];                       // x, y: unnormalized texel coordinate = uv * K + B (node i at i + 1/2);  z: node coordinate = uv * K + B
-    float scale;                      // stored value * scale = the octave sum
+    float scale;                      // stored value * 2 * scale = the octave sum (texels hold (g, a, dg, da) / (2 scale), d = next plane - this one)
     float winC[3], winH[3];           // window centre and half size, world units
     float ext[3];                     // reach of a billboard's march per unit radius: sqrt(1 + 9 viewRay_k^2) (the march overshoots the far hit by up to a chord)
     unsigned long long tex;           // layered RGBA16_SNORM, LINEAR, CLAMP, unnormalized coordinates
@@ -155,7 +157,7 @@ int launch_prep_sort(cudaStream_t st, const float *pos, const float *scale, int 
                      const float camPos[3], bool doLight, bool doCam, uint32_t *rankL, uint32_t *rankC,
                      uint64_t *keyL, uint64_t *keyC, BoardRec *recTmpL, BoardRec *recTmpC, BoardRect *rectTmpL,
                      BoardRect *rectTmpC, float *lbTmp, BoardRec *recL, BoardRec *recC, BoardRect *rectL,
-                     BoardRect *rectC, float *lbSorted, int32_t *drawOrder, void *sortTmp);
+                     BoardRect *rectC, float *lbSorted, int32_t *drawOrder, void *sortTmp, const NoiseLat *lat = nullptr);
 size_t sort_tmp_bytes(int n);      // sortTmp must hold sort_tmp_bytes(n) + 16 bytes
 int launch_bin(cudaStream_t st, const BoardRect *rects, const int32_t *bounds, int n, int W, int H, Bins &b);
 int launch_tile_order(cudaStream_t st, const Bins &b, uint32_t *order);     // order[tilesX*tilesY]: longest lists first
@@ -171,6 +173,7 @@ struct TexSet {
     cudaTextureObject_t vol;                // the whole mipmapped array: LINEAR in-level and between levels (tex3DLod)
     cudaTextureObject_t volA;               // CRN_VOLUME_RG8: the occupancy channel's chain, same sampling state
     cudaTextureObject_t noise;              // layered 2D RGBA8_SNORM, LINEAR, REPEAT: layer z holds (g_z, a_z, g_z+1, a_z+1)
+    cudaTextureObject_t noiseD;             // the same as RGBA16_SNORM differences: (g_z, a_z, g_z+1 - g_z, a_z+1 - a_z) / 2 (fast trace variant)
     cudaTextureObject_t baked[kMaxBakedTex]; // layered 2D RG16 UNORM, LINEAR, CLAMP: layer k holds (B(x,y,k), B(x,y,k+1)) of one baked step
     int32_t enabled;
 };

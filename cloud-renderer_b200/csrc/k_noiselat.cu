@@ -12,8 +12,9 @@
 //
 // This kernel evaluates  sum_{o in 1..3} pers_o * texture(noiseMap, uv * freq_o).ga  at the lattice nodes of a window
 // around the volume (in double: the filter weights are exact rationals k / (2m)) and stores it as SNORM16 slice pairs:
-// layer k of the layered RGBA16 array holds (g, a) of node plane k in .xy and of plane k+1 in .zw, like the noise
-// texture itself (crn_set_noise), so the trace kernel needs ONE bilinear pass + a z blend where it needed three.
+// layer k of the layered RGBA16 array holds (g, a) of node plane k in .xy and the step to plane k+1 in .zw (halved, so
+// that a difference fits [-1, 1]; the difference is taken between the QUANTISED planes, so layer k + its step is
+// exactly layer k+1), so the trace kernel needs ONE bilinear pass + one FMA per channel where it needed three passes.
 // The lattice depends on the noise texture, freqStep, persStep and the window only: it is baked once, not per frame.
 // SNORM16 storage: 1.5e-5 absolute, far below the 8-bit filter weights of the texture unit.
 #include "crn_internal.cuh"
@@ -51,11 +52,8 @@ __device__ __forceinline__ Axis repeat_axis(double t, int n) {
     return a;
 }
 
-__global__ void __launch_bounds__(256) noise_lattice_kernel(const __grid_constant__ LatArgs a) {
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int yk = blockIdx.y * 8 + (threadIdx.x >> 5);             // y + n[1] * k
-    if (x >= a.n[0] || yk >= a.n[1] * a.n[2]) return;
-    const int y = yk % a.n[1], k = yk / a.n[1];
+// quantised (g, a) / (2 scale) of one lattice node
+__device__ __forceinline__ int2 lattice_node(const LatArgs &a, int x, int y, int k) {
     const int node[3] = {x, y, k};
     double g = 0.0, al = 0.0;
     for (int o = a.first; o <= a.last; o++) {
@@ -76,11 +74,27 @@ __global__ void __launch_bounds__(256) noise_lattice_kernel(const __grid_constan
         }
         g += (double)a.pers[o] * sg; al += (double)a.pers[o] * sa;
     }
-    const int qg = max(-32767, min(32767, (int)rint(g * (double)a.invScale * 32767.0)));
-    const int qa = max(-32767, min(32767, (int)rint(al * (double)a.invScale * 32767.0)));
-    const short2 v = make_short2((short)qg, (short)qa);
-    if (k < a.n[2] - 1) surf2DLayeredwrite(v, a.surf, x * 8, y, k);
-    if (k > 0) surf2DLayeredwrite(v, a.surf, x * 8 + 4, y, k - 1);
+    const int qg = max(-16383, min(16383, (int)rint(g * (double)a.invScale * 16383.5)));
+    const int qa = max(-16383, min(16383, (int)rint(al * (double)a.invScale * 16383.5)));
+    return make_int2(qg, qa);
+}
+
+// one thread per (x, y) and run of kRun layers: kRun + 1 node evaluations for kRun texels
+constexpr int kRun = 4;
+__global__ void __launch_bounds__(256) noise_lattice_kernel(const __grid_constant__ LatArgs a) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int runs = (a.n[2] - 1 + kRun - 1) / kRun;
+    const int yk = blockIdx.y * 8 + (threadIdx.x >> 5);             // y + n[1] * run
+    if (x >= a.n[0] || yk >= a.n[1] * runs) return;
+    const int y = yk % a.n[1], k0 = (yk / a.n[1]) * kRun;
+    int2 cur = lattice_node(a, x, y, k0);
+    for (int k = k0; k < min(k0 + kRun, a.n[2] - 1); k++) {
+        const int2 nxt = lattice_node(a, x, y, k + 1);
+        // |value| <= 16383 and |step| <= 32766: SNORM16 codes (c / 32767 on read), i.e. value / (2 scale) * (1 + 1.5e-5)
+        const short4 v = make_short4((short)cur.x, (short)cur.y, (short)(nxt.x - cur.x), (short)(nxt.y - cur.y));
+        surf2DLayeredwrite(v, a.surf, x * 8, y, k);
+        cur = nxt;
+    }
 }
 
 } // namespace
@@ -93,7 +107,8 @@ int launch_noise_lattice(cudaStream_t st, const float2 *noise, int dim, const in
     a.first = first; a.last = last;
     for (int o = 0; o < kMaxOctaves; o++) { a.m[o] = m[o]; a.pers[o] = pers[o]; }
     a.invScale = invScale; a.surf = surf;
-    noise_lattice_kernel<<<dim3((n[0] + 31) / 32, (n[1] * n[2] + 7) / 8), 256, 0, st>>>(a);
+    const int runs = (n[2] - 1 + kRun - 1) / kRun;
+    noise_lattice_kernel<<<dim3((n[0] + 31) / 32, (n[1] * runs + 7) / 8), 256, 0, st>>>(a);
     return 1;
 }
 

@@ -68,6 +68,7 @@ struct PrepArgs {
     float *lb;
     uint32_t *range;          // [minL, maxL, minC, maxC] of the sortable key bits
     int32_t *bounds;          // [minI, maxI, minJ, maxJ] light, then camera: union of the unclipped rectangles
+    NoiseLat lat;             // window of the combined-octave noise lattice (k_noiselat.cu): camera records carry an "inside" flag
     uint32_t *wbox;           // sortable bits of [min x, y, z of (centre - r) | max x, y, z of (centre + r)] over all billboards (camera pass)
 };
 
@@ -122,6 +123,11 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepArgs a, ViewParams light,
     if (a.recC) {
         mul_point(cam.V, cx, cy, cz, cv);
         BoardRec rec = {cx, cy, cz, r, cv[0], cv[1], cv[2], i};
+        // the whole noise march of this billboard (sphere stretched along the view ray by the march's overshoot) stays
+        // inside the lattice window: the trace kernel reads the pre-summed octaves for it
+        if (a.lat.on && r * a.lat.ext[0] + fabsf(cx - a.lat.winC[0]) <= a.lat.winH[0] && r * a.lat.ext[1] + fabsf(cy - a.lat.winC[1]) <= a.lat.winH[1] &&
+            r * a.lat.ext[2] + fabsf(cz - a.lat.winC[2]) <= a.lat.winH[2])
+            rec.idx |= kRecInLattice;
         const BoardRect q = quad_rect(cam, cv, r);
         if (live) { a.recC[i] = rec; a.rectC[i] = q; }
         warp_bounds(q, live, a.bounds + 4);
@@ -256,9 +262,10 @@ int launch_prep_sort(cudaStream_t st, const float *pos, const float *scale, int 
                      const float camPos[3], bool doLight, bool doCam, uint32_t *rankL, uint32_t *rankC,
                      uint64_t *keyL, uint64_t *keyC, BoardRec *recTmpL, BoardRec *recTmpC, BoardRect *rectTmpL,
                      BoardRect *rectTmpC, float *lbTmp, BoardRec *recL, BoardRec *recC, BoardRect *rectL,
-                     BoardRect *rectC, float *lbSorted, int32_t *drawOrder, void *sortTmp) {
+                     BoardRect *rectC, float *lbSorted, int32_t *drawOrder, void *sortTmp, const NoiseLat *lat) {
     if (n <= 0) return 0;
     PrepArgs pa;
+    if (lat) pa.lat = *lat; else pa.lat.on = 0;
     pa.pos = pos; pa.scale = scale; pa.n = n; pa.fluff = fluff;
     for (int k = 0; k < 3; k++) { pa.volpos[k] = volpos[k]; pa.nearPlane[k] = nearPlane[k]; pa.camPos[k] = camPos[k]; }
     pa.clip = clip;

@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_kernel(co
                         asm("tex.a2d.v4.f32.f32 {%0, %1, %2, %3}, [%4, {%5, %6, %7, %7}];"
                             : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
                             : "l"(bs.tex), "r"(layer), "f"(fmaf(sx, bs.A, bs.B)), "f"(fmaf(sy, bs.A, bs.B)));
-                        if (shade) indirect = fmaf(fmaf(az, t.y - t.x, t.x), bs.weight, indirect);
+                        if (shade) indirect = fmaf(fmaf(az, t.y, t.x), bs.weight, indirect);
                         if (kStats && shade) nBakedF++;
                     };
                     for (int b = 0; b < tp.nBaked; b++) bakedStep(b);
@@ -581,15 +581,14 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_fast_kern
         const int nIter = shade ? (int)ceilf(iSteps) : 0;
         const int nMax = __reduce_max_sync(0xFFFFFFFFu, nIter);
         const float qax = qx * invAdjust, qay = qy * invAdjust, qaz = qz * invAdjust;
-        const float uu0 = d2 * invr * invr, vy0 = oy * invr;
+        // (the noise textures return HALF the noise value, see TexSet::noiseD: the march carries ng / 2 and na / 2)
+        const float uu0 = d2 * invr * invr, vy0 = 0.5f * oy * invr;
         float s1 = -h * invAdjust;                                      // texture-space distance from the plane point
         float s2 = -h * invr;                                           // unit-sphere distance from the plane (sic: advanced by the texture-space step)
         float opacity = 0.0f, light = 0.0f;
-        // the combined-octave lattice (k_noiselat.cu) covers this billboard's whole march if the sphere, stretched along the
-        // view ray by the march's overshoot, lies inside the baked window (r0 is warp-uniform, so is the branch)
-        const bool inLat = tp.lat.on && fmaf(radius, tp.lat.ext[0], fabsf(r0.x - tp.lat.winC[0])) <= tp.lat.winH[0] &&
-                           fmaf(radius, tp.lat.ext[1], fabsf(r0.y - tp.lat.winC[1])) <= tp.lat.winH[1] &&
-                           fmaf(radius, tp.lat.ext[2], fabsf(r0.z - tp.lat.winC[2])) <= tp.lat.winH[2];
+        // the combined-octave lattice (k_noiselat.cu) covers this billboard's whole march: decided per billboard by the
+        // camera-side prep kernel (k_prep_sort.cu), warp-uniform
+        const bool inLat = (__float_as_int(r1.w) & kRecInLattice) != 0;
         if (inLat) {
             // every lookup coordinate is affine in the march distance: six running sums, no constants inside the loop
             const float K = tp.lat.K;
@@ -598,23 +597,23 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_fast_kern
             float u1 = fmaf(c0x, K, tp.lat.B[0]), v1 = fmaf(c0y, K, tp.lat.B[1]), z1 = fmaf(c0z, K, tp.lat.B[2]);
             const float du0 = sStep * rx, dv0 = sStep * ry, dz0 = sStep * (rz * tp.octFreqZ[0]);
             const float du1 = du0 * K, dv1 = dv0 * K, dz1 = sStep * (rz * K);
+            const float ryh = 0.5f * ry;
             for (int i = 0; i < nMax; i++) {
                 if (i < nIter) {
-                    // octave 0 (it alone carries the wind offset): the noise texture's slice pairs, as below
+                    // octave 0 (it alone carries the wind offset): plane floor(z) of the noise texture and the step to the next
                     const float m = __fadd_rd(z0, 12582912.0f);
                     const float az = __fadd_rn(z0, -__fadd_rn(m, -12582912.0f));
-                    const float4 t = tex_layer4(ts.noise, __float_as_int(m) & 31, u0, v0);
-                    // octaves 1..3, pre-summed on the finest octave's texel lattice: node planes floor(z) and floor(z)+1
+                    const float4 t = tex_layer4(ts.noiseD, __float_as_int(m) & 31, u0, v0);
+                    // octaves 1..3, pre-summed on the finest octave's texel lattice: node plane floor(z) and the step to the next
                     const float ml = __fadd_rd(z1, 12582912.0f);
                     const float al = __fadd_rn(z1, -__fadd_rn(ml, -12582912.0f));
                     const float4 q = tex_layer4(tp.lat.tex, __float_as_int(ml) & 0x7FF, u1, v1);
-                    const float sg = fmaf(az, t.z - t.x, t.x), sa = fmaf(az, t.w - t.y, t.y);
-                    float ng = fmaf(tp.lat.scale, fmaf(al, q.z - q.x, q.x), sg);
-                    const float na = fmaf(tp.lat.scale, fmaf(al, q.w - q.y, q.y), sa);
+                    float ng = fmaf(tp.lat.scale, fmaf(al, q.z, q.x), fmaf(az, t.z, t.x));
+                    const float na = fmaf(tp.lat.scale, fmaf(al, q.w, q.y), fmaf(az, t.w, t.y));
                     const float uu = fmaf(s2, s2, uu0);
-                    ng = fmaf(fmaf(s2, ry, vy0), rsqrtf(uu), ng);
+                    ng = fmaf(fmaf(s2, ryh, vy0), rsqrtf(uu), ng);      // (noiseCell.y + normalize(unitTex).y) / 2
                     opacity = fmaf(fabsf(na), 1.0f - uu, opacity);
-                    light += fma_sat(ng, 0.5f, 0.5f);
+                    light += __saturatef(ng + 0.5f);
                     u0 += du0; v0 += dv0; z0 += dz0; u1 += du1; v1 += dv1; z1 += dz1;
                     s2 += sStep;
                 }
@@ -635,20 +634,20 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_fast_kern
                     const int layer = __float_as_int(m) & 31;
                     const float tu = o == 0 ? cx + tp.octBias[0] : o == 3 ? cx * tp.octFreq[o] : fmaf(cx, tp.octFreq[o], tp.octBias[o]);
                     const float tv = o == 0 ? cy + tp.octBias[0] : o == 3 ? cy * tp.octFreq[o] : fmaf(cy, tp.octFreq[o], tp.octBias[o]);
-                    const float4 t = tex_layer4(ts.noise, layer, tu, tv);
-                    const float sg = fmaf(az, t.z - t.x, t.x), sa = fmaf(az, t.w - t.y, t.y);
+                    const float4 t = tex_layer4(ts.noiseD, layer, tu, tv);
+                    const float sg = fmaf(az, t.z, t.x), sa = fmaf(az, t.w, t.y);
                     if (o == 0) { ng = sg; na = sa; }
                     else { ng = fmaf(tp.octPers[o], sg, ng); na = fmaf(tp.octPers[o], sa, na); }
                 }
                 const float uu = fmaf(s2, s2, uu0);                     // |unitTex|^2: the plane offset is perpendicular to the ray
-                ng = fmaf(fmaf(s2, ry, vy0), rsqrtf(uu), ng);           // noiseCell.xyz += normalize(unitTex)
+                ng = fmaf(fmaf(s2, 0.5f * ry, vy0), rsqrtf(uu), ng);    // (noiseCell.y + normalize(unitTex).y) / 2
                 opacity = fmaf(fabsf(na), 1.0f - uu, opacity);
-                light += fma_sat(ng, 0.5f, 0.5f);
+                light += __saturatef(ng + 0.5f);
                 s1 += sStep; s2 += sStep;
             }
         }
         const float grey = fmaf(tp.p.noiseColorScale * light, inv, tp.p.minNoiseColor);
-        const float alpha = __saturatef(opacity * tp.p.noiseOpacity * inv) * (1.0f - sqrtf(d2) * invr);
+        const float alpha = __saturatef(opacity * (2.0f * tp.p.noiseOpacity) * inv) * (1.0f - sqrtf(d2) * invr);
 
         // ---- cone trace towards the sun (res/conetrace_frag.glsl:176-200, traceCone :64-79)
         const float wx3 = fmaf(rx, h, qx), wy3 = fmaf(ry, h, qy), wz3 = fmaf(rz, h, qz);   // camera-facing sphere surface
@@ -692,7 +691,7 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_fast_kern
             const float m = __fadd_rd(zl, 12582912.0f);                                     // floor in the low mantissa bits
             const float az = __fadd_rn(zl, -__fadd_rn(m, -12582912.0f));
             const float4 t = tex_layer4(bs.tex, __float_as_int(m) & 0xFF, fmaf(bs.hA, ex, fmaf(nx, bs.A, bs.B)), fmaf(bs.hA, ey, fmaf(ny, bs.A, bs.B)));
-            indirect = fmaf(fmaf(az, t.y - t.x, t.x), bs.weight, indirect);
+            indirect = fmaf(fmaf(az, t.y, t.x), bs.weight, indirect);
         }
 
         if (shade) {                                                    // blend, front to back

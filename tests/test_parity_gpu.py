@@ -798,9 +798,9 @@ def test_fast_generic_baked_and_textureLod_paths_agree(name, pkg, scenes, orc):
     """Four routes to the same image with the texture sampler: the fast kernel with the combined-octave noise lattice
     (k_noiselat.cu), the fast kernel with one lookup per octave (CRN_NO_LATTICE), the generic kernel (CRN_NO_FAST) and the
     generic kernel with every cone step fetched by textureLod instead of the baked step textures (CRN_NO_BAKE).  Fast
-    without the lattice and generic issue the same lookups (differences: float re-association only); lattice vs
-    per-octave and baked vs textureLod differ by the texture unit's filter precision (both lattices are finer than what
-    they replace).  All four >= 45 dB vs the oracle."""
+    without the lattice and generic issue the same lookups, from an RGBA16 (plane, step to the next plane) copy of the
+    noise texture and from the RGBA8 slice pairs; lattice vs per-octave and baked vs textureLod differ by the texture
+    unit's filter precision (both lattices are finer than what they replace).  All four >= 45 dB vs the oracle."""
     import os
     s = scenes.make_scene("C2", boards=600, size=(640, 360)) if name == "C2crop" else scenes.make_scene(name)
     s = steady_state(s, orc)
@@ -838,5 +838,5 @@ def test_fast_generic_baked_and_textureLod_paths_agree(name, pkg, scenes, orc):
         assert p >= 45.0
     pf, pb, pl = psnr(imgs["fast"], imgs["generic"]), psnr(imgs["generic"], imgs["textureLod"]), psnr(imgs["lattice"], imgs["fast"])
     print(f"{name}: fast vs generic {pf:.1f} dB, baked vs textureLod {pb:.1f} dB, lattice vs per-octave {pl:.1f} dB")
-    assert pf >= 99.0 and pb >= 60.0 and pl >= 80.0
+    assert pf >= 80.0 and pb >= 60.0 and pl >= 80.0
     assert not np.array_equal(imgs["lattice"], imgs["fast"]), "the lattice route was not taken"
