@@ -175,6 +175,9 @@ struct crn_ctx {
         cudaSurfaceObject_t bakedSurf[kMaxBakedTex] = {};
         int bakedN[kMaxBakedTex] = {};
         DevBuf needCode;
+        cudaArray_t codeArr = nullptr;   // the need codes as a 3D R8UI texture of skip bits (fast trace variant)
+        cudaSurfaceObject_t codeSurf = 0;
+        int codeG = 0;
         BakeKey bakeKey{};
         CodeKey codeKey{};
         bool bakeValid = false, codeValid = false;
@@ -358,6 +361,13 @@ void free_baked(crn_ctx *c, int i) {
     VS(c).ts.baked[i] = 0; VS(c).bakedSurf[i] = 0; VS(c).bakedArr[i] = nullptr; VS(c).bakedN[i] = 0;
 }
 
+void free_code_texture(crn_ctx::VolSet &v) {
+    if (v.ts.code) cudaDestroyTextureObject(v.ts.code);
+    if (v.codeSurf) cudaDestroySurfaceObject(v.codeSurf);
+    if (v.codeArr) cudaFreeArray(v.codeArr);
+    v.ts.code = 0; v.codeSurf = 0; v.codeArr = nullptr; v.codeG = 0;
+}
+
 void free_lattice(crn_ctx *c) {
     if (c->latTex) cudaDestroyTextureObject(c->latTex);
     if (c->latSurf) cudaDestroySurfaceObject(c->latSurf);
@@ -537,6 +547,21 @@ int build_need_codes(crn_ctx *c, TraceParams &tp, const uint32_t *worldBox) {
     if (tp.codeDim > 0) {
         const size_t cells = (size_t)tp.codeDim * tp.codeDim * tp.codeDim;
         if ((r = reserve(c, VS(c).needCode, cells))) return r;
+        if (VS(c).codeG != tp.codeDim) {
+            sync_all(c);
+            free_code_texture(VS(c));
+            cudaChannelFormatDesc cd = cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned);
+            CRN_CUDA(c, cudaMalloc3DArray(&VS(c).codeArr, &cd, make_cudaExtent(tp.codeDim, tp.codeDim, tp.codeDim), cudaArraySurfaceLoadStore));
+            cudaResourceDesc rd{};
+            rd.resType = cudaResourceTypeArray; rd.res.array.array = VS(c).codeArr;
+            CRN_CUDA(c, cudaCreateSurfaceObject(&VS(c).codeSurf, &rd));
+            cudaTextureDesc td{};
+            td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeBorder;     // outside the volume: no skip bit
+            td.filterMode = cudaFilterModePoint; td.readMode = cudaReadModeElementType; td.normalizedCoords = 1;
+            CRN_CUDA(c, cudaCreateTextureObject(&VS(c).ts.code, &rd, &td, nullptr));
+            VS(c).codeG = tp.codeDim;
+            VS(c).codeValid = false;
+        }
         crn_ctx::CodeKey k{};
         k.gen = c->volumeGen; k.G = tp.codeDim; k.nGroups = std::min(tp.nGroups, kCodeGroups);
         for (int g = 0; g < k.nGroups; g++) { k.height[g] = tp.groups[g].height; k.level[g] = tp.groups[g].level; }
@@ -547,7 +572,7 @@ int build_need_codes(crn_ctx *c, TraceParams &tp, const uint32_t *worldBox) {
         //  ones of the last build)
         if (!VS(c).codeValid || VS(c).codeBoardsGen != c->boardsGen || std::memcmp(&k, &VS(c).codeKey, sizeof k) != 0) {
             if (VS(c).freeValid) cudaStreamWaitEvent(c->lightStream, VS(c).evFree, 0);
-            c->launches += launch_need_code(c->lightStream, c->vparams, tp, (const uint32_t *)c->mask.p, worldBox, (uint8_t *)VS(c).needCode.p);
+            c->launches += launch_need_code(c->lightStream, c->vparams, tp, (const uint32_t *)c->mask.p, worldBox, (uint8_t *)VS(c).needCode.p, VS(c).codeSurf);
             VS(c).codeKey = k; VS(c).codeValid = true; VS(c).codeBoardsGen = c->boardsGen;
         }
     }
@@ -1081,6 +1106,7 @@ void crn_destroy(crn_ctx *c) {
     for (c->vs = 0; c->vs < 2; c->vs++) {
         free_vol_textures(c);
         for (int i = 0; i < kMaxBakedTex; i++) free_baked(c, i);
+        free_code_texture(c->vset[c->vs]);
     }
     c->vs = 0;
     for (int k = 0; k < 2; k++) {

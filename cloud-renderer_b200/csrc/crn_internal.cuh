@@ -174,6 +174,7 @@ struct TexSet {
     cudaTextureObject_t volA;               // CRN_VOLUME_RG8: the occupancy channel's chain, same sampling state
     cudaTextureObject_t noise;              // layered 2D RGBA8_SNORM, LINEAR, REPEAT: layer z holds (g_z, a_z, g_z+1, a_z+1)
     cudaTextureObject_t noiseD;             // the same as RGBA16_SNORM differences: (g_z, a_z, g_z+1 - g_z, a_z+1 - a_z) / 2 (fast trace variant)
+    cudaTextureObject_t code;               // 3D R8UI, POINT, BORDER: the need-code grid as SKIP bits (bit g set: group g cannot contribute from this cell; outside the volume: 0)
     cudaTextureObject_t baked[kMaxBakedTex]; // layered 2D RG16 UNORM, LINEAR, CLAMP: layer k holds (B(x,y,k), B(x,y,k+1)) of one baked step
     int32_t enabled;
 };
@@ -198,7 +199,8 @@ int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol
                  const uint32_t *bitsA, const uint8_t *chainA, const int8_t *noise, const TexSet *ts, const uint8_t *needCode, const uint32_t *tileOrder, void *image,
                  int format, unsigned long long *stats, float4 *segPartial, uint32_t *segArrived);
 int launch_bake_steps(cudaStream_t st, const VolumeParams &vol, const uint32_t *bits, const uint8_t *chain, const BakeTex *tex, int nTex);
-int launch_need_code(cudaStream_t st, const VolumeParams &vol, const TraceParams &tp, const uint32_t *mask, const uint32_t *worldBox, uint8_t *code);
+int launch_need_code(cudaStream_t st, const VolumeParams &vol, const TraceParams &tp, const uint32_t *mask, const uint32_t *worldBox, uint8_t *code,
+                     cudaSurfaceObject_t codeSurf);
 int launch_noise_lattice(cudaStream_t st, const float2 *noise, int dim, const int n[3], const long long base[3], int first, int last,
                          const double *m, const float *pers, float invScale, cudaSurfaceObject_t surf);
 size_t skipmask_words(const VolumeParams &vol, uint32_t *off);

@@ -133,6 +133,7 @@ struct CodeArgs {
     const uint32_t *worldBox;                 // sortable bits of the billboards' world bounding box (k_prep_sort.cu), or nullptr
     float lightPos[3], b0[3], range[3];
     uint8_t *code;
+    cudaSurfaceObject_t codeSurf;             // the same grid as skip bits (~code) in a 3D array, for the fast trace variant's texture lookup
 };
 
 __device__ __forceinline__ float unsortable(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u); }
@@ -153,7 +154,9 @@ __global__ void __launch_bounds__(256) need_code_kernel(const __grid_constant__ 
             if (fmaxf(c0, c1) < lo || fminf(c0, c1) > hi) return;
         }
     }
-    const float half = 0.5f * invG * 1.001f + 1.0e-6f;           // half a cell, in normalized coordinates, with slack
+    // half a cell, in normalized coordinates, with slack: the fast trace variant finds its cell with a point-sampled texture
+    // fetch, whose fixed-point coordinate may land in the neighbouring cell within 1/256 of a cell border
+    const float half = 0.5f * invG * (1.0f + 1.0f / 64.0f) + 1.0e-6f;
     const float nc[3] = {((float)ix + 0.5f) * invG, ((float)iy + 0.5f) * invG, ((float)iz + 0.5f) * invG};
     float toL[3], hw2 = 0.0f, d2 = 0.0f;
 #pragma unroll
@@ -170,6 +173,7 @@ __global__ void __launch_bounds__(256) need_code_kernel(const __grid_constant__ 
     const float dmin = dist - hw;
     if (!(dmin > 4.0f * hw) || !(dist > 0.0f)) {
         a.code[cell] = 0xFF;
+        if (a.codeSurf) surf3Dwrite((unsigned char)0, a.codeSurf, ix, iy, iz);
         return;
     }
     const float invDist = 1.0f / dist, turn = (hw / dmin) * 1.01f;
@@ -220,6 +224,7 @@ __global__ void __launch_bounds__(256) need_code_kernel(const __grid_constant__ 
         if (any) bitsOut |= 1u << g;
     }
     a.code[cell] = (uint8_t)bitsOut;
+    if (a.codeSurf) surf3Dwrite((unsigned char)(~bitsOut & ((1u << a.nGroups) - 1u)), a.codeSurf, ix, iy, iz);
 }
 
 } // namespace
@@ -251,7 +256,8 @@ int launch_bake_steps(cudaStream_t st, const VolumeParams &vol, const uint32_t *
     return 1;
 }
 
-int launch_need_code(cudaStream_t st, const VolumeParams &vol, const TraceParams &tp, const uint32_t *mask, const uint32_t *worldBox, uint8_t *code) {
+int launch_need_code(cudaStream_t st, const VolumeParams &vol, const TraceParams &tp, const uint32_t *mask, const uint32_t *worldBox, uint8_t *code,
+                     cudaSurfaceObject_t codeSurf) {
     CodeArgs a{};
     a.G = tp.codeDim;
     a.nGroups = std::min(tp.nGroups, kCodeGroups);
@@ -259,7 +265,7 @@ int launch_need_code(cudaStream_t st, const VolumeParams &vol, const TraceParams
         a.g[g].reach = tp.groups[g].height / (float)vol.dim; a.g[g].size = tp.groups[g].size; a.g[g].sizeF = (float)tp.groups[g].size;
         a.g[g].wpr = tp.groups[g].wpr; a.g[g].maskOff = tp.groups[g].maskOff;
     }
-    a.mask = mask; a.code = code; a.worldBox = worldBox;
+    a.mask = mask; a.code = code; a.worldBox = worldBox; a.codeSurf = codeSurf;
     a.b0[0] = vol.xB[0]; a.b0[1] = vol.yB[0]; a.b0[2] = vol.zB[0];
     a.range[0] = vol.xB[1] - vol.xB[0]; a.range[1] = vol.yB[1] - vol.yB[0]; a.range[2] = vol.zB[1] - vol.zB[0];
     for (int k = 0; k < 3; k++) a.lightPos[k] = tp.lightPos[k];

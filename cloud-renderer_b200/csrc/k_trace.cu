@@ -659,16 +659,17 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_fast_kern
         ex *= il; ey *= il; ez *= il;
         float indirect = 0.0f;
         if (tp.nGroups > 0) {
-            // bit g of the start cell's need code: can group g reach a non-zero texel from a start position in this cell?
-            // Groups beyond kCodeGroups have no bit and start positions outside the volume no cell: always fetched.
-            uint32_t code = 0xFFFFFFFFu;
+            // bit g of the start cell's SKIP code: no start position in this cell can reach a non-zero texel with group g.  One
+            // point-sampled fetch of the code grid (k_conebake.cu) at the start position; outside the volume the border
+            // returns 0: everything is fetched.  Groups beyond kCodeGroups have no bit.
+            uint32_t code = tp.nGroups >= 32 ? 0xFFFFFFFFu : (1u << tp.nGroups) - 1u;
             if (a.code) {
-                const int ix = __float2int_rd(nx * tp.codeDimF), iy = __float2int_rd(ny * tp.codeDimF), iz = __float2int_rd(nz * tp.codeDimF);
-                const uint32_t G = (uint32_t)tp.codeDim;
-                if (shade && (uint32_t)ix < G && (uint32_t)iy < G && (uint32_t)iz < G)
-                    code = __ldg(a.code + ((uint32_t)iz * G + (uint32_t)iy) * G + (uint32_t)ix) | ~((1u << kCodeGroups) - 1u);
+                uint32_t skip, u1_, u2_, u3_;
+                asm("tex.level.3d.v4.u32.f32 {%0, %1, %2, %3}, [%4, {%5, %6, %7, %7}], 0f00000000;"
+                    : "=r"(skip), "=r"(u1_), "=r"(u2_), "=r"(u3_) : "l"(ts.code), "f"(nx), "f"(ny), "f"(nz));
+                code &= ~skip;
             }
-            code = shade ? code & (tp.nGroups >= 32 ? 0xFFFFFFFFu : (1u << tp.nGroups) - 1u) : 0u;
+            code = shade ? code : 0u;
             if (__any_sync(0xFFFFFFFFu, code != 0)) {                   // most patches need no fine step at all
                 for (int g = 0; g < tp.nGroups; g++) {
                     const ConeGroup &gr = tp.groups[g];
