@@ -153,7 +153,7 @@ struct crn_ctx {
     DevBuf exportTmp, exportOut;         // crn_export_voxels scratch
     DevBuf bitsA, chainA;                // CRN_VOLUME_RG8: the occupancy (alpha) channel's level-0 set and R8 chain
     DevBuf pos0, pos, scale, keyL, keyC, rankL, rankC, recTmpL, recTmpC, rectTmpL, rectTmpC, lbTmp, recL, rectL,
-        lbSorted, drawOrder, bits, chain, noise, posmap, image, misc, maskNz, maskDil, mask, sortTmp;
+        lbSorted, drawOrder, bits, chain, noise, posmap, image, misc, maskNz, sortTmp;
     bool maskCurrent = false;
     size_t poolMin = (size_t)1 << 20;    // initial bin-pool entries (CRN_BIN_POOL_MIN overrides: tests force the growth path)
     Bins binsL;
@@ -165,7 +165,7 @@ struct crn_ctx {
     // overlaps the trace of frame k on the caller's stream.  The chain, the masks and the bits are read only by that
     // set-up itself (texture sampler) and stay single.
     struct BakeKey { uint64_t gen; int nTex; int level0[kMaxBakedTex]; float frac[kMaxBakedTex]; int n[kMaxBakedTex]; };
-    struct CodeKey { uint64_t gen; int G, nGroups; float height[kCodeGroups]; int level[kCodeGroups]; float light[3]; float bounds[6]; };
+    struct CodeKey { uint64_t gen; int G, nGroups; float height[kCodeGroups]; int level[kCodeGroups], first[kCodeGroups], count[kCodeGroups]; float light[3]; float bounds[6]; };
     struct VolSet {                      // texture-unit copies (CRN_SAMPLER_TEXTURE) + per-frame cone acceleration data (k_conebake.cu)
         cudaMipmappedArray_t volArray = nullptr, volArrayA = nullptr;
         TexSet ts{}, tsA{};              // tsA: CRN_VOLUME_RG8, texture-unit copy of the occupancy chain
@@ -487,15 +487,12 @@ int require(crn_ctx *c, bool ok, const char *what) {
     return ok ? CRN_OK : fail(c, CRN_ERR_STATE, "%s has not been set", what);
 }
 
+// non-zero bits of the levels >= 1 (level 0 is the occupancy set itself): what the need codes are tested against
 int build_masks(crn_ctx *c) {
     const size_t words = skipmask_words(c->vparams, nullptr);
     int r;
     if ((r = reserve(c, c->maskNz, words * 4))) return r;
-    if ((r = reserve(c, c->maskDil, words * 4))) return r;
-    if ((r = reserve(c, c->mask, words * 4))) return r;
-    c->launches += launch_skipmask(c->lightStream, c->vparams, (const uint32_t *)c->bits.p, (const uint8_t *)c->chain.p,
-                                   (uint32_t *)c->maskNz.p, (uint32_t *)c->maskDil.p, (uint32_t *)c->mask.p,
-                                   (uint32_t *)((char *)c->misc.p + 192));
+    c->launches += launch_skipmask(c->lightStream, c->vparams, (const uint8_t *)c->chain.p, (uint32_t *)c->maskNz.p);
     c->maskCurrent = true;
     return CRN_OK;
 }
@@ -564,7 +561,7 @@ int build_need_codes(crn_ctx *c, TraceParams &tp, const uint32_t *worldBox) {
         }
         crn_ctx::CodeKey k{};
         k.gen = c->volumeGen; k.G = tp.codeDim; k.nGroups = std::min(tp.nGroups, kCodeGroups);
-        for (int g = 0; g < k.nGroups; g++) { k.height[g] = tp.groups[g].height; k.level[g] = tp.groups[g].level; }
+        for (int g = 0; g < k.nGroups; g++) { k.height[g] = tp.groups[g].height; k.level[g] = tp.groups[g].level; k.first[g] = tp.groups[g].first; k.count[g] = tp.groups[g].count; }
         for (int i = 0; i < 3; i++) k.light[i] = tp.lightPos[i];
         const float b[6] = {c->vparams.xB[0], c->vparams.xB[1], c->vparams.yB[0], c->vparams.yB[1], c->vparams.zB[0], c->vparams.zB[1]};
         std::memcpy(k.bounds, b, sizeof b);
@@ -572,7 +569,7 @@ int build_need_codes(crn_ctx *c, TraceParams &tp, const uint32_t *worldBox) {
         //  ones of the last build)
         if (!VS(c).codeValid || VS(c).codeBoardsGen != c->boardsGen || std::memcmp(&k, &VS(c).codeKey, sizeof k) != 0) {
             if (VS(c).freeValid) cudaStreamWaitEvent(c->lightStream, VS(c).evFree, 0);
-            c->launches += launch_need_code(c->lightStream, c->vparams, tp, (const uint32_t *)c->mask.p, worldBox, (uint8_t *)VS(c).needCode.p, VS(c).codeSurf);
+            c->launches += launch_need_code(c->lightStream, c->vparams, tp, (const uint32_t *)c->bits.p, (const uint32_t *)c->maskNz.p, worldBox, (uint8_t *)VS(c).needCode.p, VS(c).codeSurf);
             VS(c).codeKey = k; VS(c).codeValid = true; VS(c).codeBoardsGen = c->boardsGen;
         }
     }
@@ -754,25 +751,33 @@ void build_trace_params(crn_ctx *c, const ViewParams &cam, TraceParams *tp) {
         for (int i = first; i < S; i++) used[texOf[i]] = true;
         while (c->nBakePlan > 0 && !used[c->nBakePlan - 1]) c->nBakePlan--;
     }
-    // groups for the empty-space test: consecutive textureLod steps with the same lower level whose sample points
-    // all lie within one level-l texel of the group's mid height (so M_l's 5x5x5 dilation covers them)
+    // groups for the empty-space test (k_conebake.cu need codes): one per textureLod step; while there are more than the
+    // code has bits, the two neighbours of the same level(s) that lie closest together are merged
     tp->nGroups = 0;
-    uint32_t maskOff[kMaxLevels] = {};
-    skipmask_words(c->vparams, maskOff);
-    for (int i = 0; i < tp->nFine;) {
-        const int l = tp->steps[i].level0;
-        const float texel = 0.98f * (float)(1 << l);
-        int j = i;
-        while (j + 1 < tp->nFine && tp->steps[j + 1].level0 == l &&
-               0.5f * fabsf(tp->steps[j + 1].height - tp->steps[i].height) < texel) j++;
+    for (int i = 0; i < tp->nFine; i++) {
         ConeGroup &g = tp->groups[tp->nGroups++];
-        g.height = 0.5f * (tp->steps[i].height + tp->steps[j].height);
-        g.size = c->vparams.levelSize[l];
-        g.wpr = g.size >= 32 ? g.size / 32 : 1;
-        g.maskOff = maskOff[l];
-        g.first = i; g.count = j - i + 1;
-        g.level = l;
-        i = j + 1;
+        g.first = i; g.count = 1; g.level = tp->steps[i].level0; g.two = tp->steps[i].frac != 0.0f ? 1 : 0;
+        g.height = tp->steps[i].height;
+    }
+    while (tp->nGroups > kCodeGroups) {
+        int best = -1;
+        float bestSpan = 0.0f;
+        for (int g = 0; g + 1 < tp->nGroups; g++) {
+            const ConeGroup &p = tp->groups[g], &q = tp->groups[g + 1];
+            if (p.level != q.level) continue;
+            const float span = tp->steps[q.first + q.count - 1].height - tp->steps[p.first].height;
+            if (best < 0 || span < bestSpan) { best = g; bestSpan = span; }
+        }
+        if (best < 0) break;                               // (groups past kCodeGroups have no bit: always fetched)
+        ConeGroup &p = tp->groups[best];
+        const ConeGroup &q = tp->groups[best + 1];
+        p.count += q.count; p.two |= q.two;
+        for (int g = best + 1; g + 1 < tp->nGroups; g++) tp->groups[g] = tp->groups[g + 1];
+        tp->nGroups--;
+    }
+    for (int g = 0; g < tp->nGroups; g++) {
+        ConeGroup &p = tp->groups[g];
+        p.height = 0.5f * (tp->steps[p.first].height + tp->steps[p.first + p.count - 1].height);
     }
     // need-code grid: cells of two voxels; only worth a kernel when some step is still fetched with textureLod
     tp->codeDim = (c->tp.skipEmptySpace && tp->nGroups > 0 && c->tp.doConeTrace) ? std::max(16, D / 2) : 0;
@@ -1098,7 +1103,7 @@ void crn_destroy(crn_ctx *c) {
     if (c->lightStream) cudaStreamSynchronize(c->lightStream);
     DevBuf *bufs[] = {&c->exportTmp, &c->exportOut, &c->pos0, &c->bitsA, &c->chainA, &c->pos, &c->scale, &c->keyL, &c->keyC, &c->rankL, &c->rankC, &c->recTmpL, &c->recTmpC, &c->rectTmpL,
                       &c->rectTmpC, &c->lbTmp, &c->recL, &c->rectL, &c->lbSorted, &c->drawOrder, &c->bits, &c->segPartial, &c->segArrived,
-                      &c->chain, &c->noise, &c->posmap, &c->image, &c->image2, &c->misc, &c->maskNz, &c->maskDil, &c->mask, &c->sortTmp,
+                      &c->chain, &c->noise, &c->posmap, &c->image, &c->image2, &c->misc, &c->maskNz, &c->sortTmp,
                       &c->cset[0].recC, &c->cset[0].rectC, &c->cset[0].sortTmpC, &c->cset[0].tileOrder,
                       &c->cset[1].recC, &c->cset[1].rectC, &c->cset[1].sortTmpC, &c->cset[1].tileOrder, &c->vset[0].needCode, &c->vset[1].needCode};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);

@@ -65,13 +65,11 @@ struct ConeStep {                     // traceCone's per-step constants (identic
     float lod;                        // level0 + frac: the tex3DLod operand (mip-linear blend in the texture unit)
 };
 
-struct ConeGroup {                    // consecutive cone steps decided by ONE empty-space bit (k_skipmask.cu, k_conebake.cu)
-    float height;                     // lookup point along the cone, voxels
-    int32_t size;                     // level size
-    int32_t wpr;                      // mask words per row
-    uint32_t maskOff;                 // word offset of M_level
+struct ConeGroup {                    // consecutive cone steps decided by ONE bit of the need code (k_conebake.cu)
+    float height;                     // mid height, voxels
     int32_t first, count;             // steps [first, first+count)
-    int32_t level;                    // mip level of the mask
+    int32_t level;                    // lower mip level its steps sample
+    int32_t two;                      // some step also blends in level + 1
 };
 
 // A cone step whose (lower level, mip fraction) pair was baked into its own texture for this frame (k_conebake.cu):
@@ -199,13 +197,12 @@ int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol
                  const uint32_t *bitsA, const uint8_t *chainA, const int8_t *noise, const TexSet *ts, const uint8_t *needCode, const uint32_t *tileOrder, void *image,
                  int format, unsigned long long *stats, float4 *segPartial, uint32_t *segArrived);
 int launch_bake_steps(cudaStream_t st, const VolumeParams &vol, const uint32_t *bits, const uint8_t *chain, const BakeTex *tex, int nTex);
-int launch_need_code(cudaStream_t st, const VolumeParams &vol, const TraceParams &tp, const uint32_t *mask, const uint32_t *worldBox, uint8_t *code,
-                     cudaSurfaceObject_t codeSurf);
+int launch_need_code(cudaStream_t st, const VolumeParams &vol, const TraceParams &tp, const uint32_t *bits, const uint32_t *nz, const uint32_t *worldBox,
+                     uint8_t *code, cudaSurfaceObject_t codeSurf);
 int launch_noise_lattice(cudaStream_t st, const float2 *noise, int dim, const int n[3], const long long base[3], int first, int last,
                          const double *m, const float *pers, float invScale, cudaSurfaceObject_t surf);
 size_t skipmask_words(const VolumeParams &vol, uint32_t *off);
-int launch_skipmask(cudaStream_t st, const VolumeParams &vol, const uint32_t *bits, const uint8_t *chain, uint32_t *nz,
-                    uint32_t *dil, uint32_t *mask, uint32_t *fill);
+int launch_skipmask(cudaStream_t st, const VolumeParams &vol, const uint8_t *chain, uint32_t *nz);
 int launch_generate_boards(cudaStream_t st, int n, const float minOff[3], const float maxOff[3], float minScale,
                            float maxScale, double radiusFactor, uint64_t seed, float *pos0, float *pos, float *scale);
 size_t export_scratch_words(size_t words);

@@ -13,12 +13,13 @@
 //     mip-linear 3D fetch (measured: 288 G/s for tex3DLod at a fractional LOD, 1121 G/s for RG16 layered bilinear).
 //     SNORM16 storage: 1.5e-5 absolute, far below the 8-bit filter weights of the texture unit.
 //
-// (2) Need codes.  The empty-space masks M_l (k_skipmask.cu) decide whether a GROUP of cone steps can contribute;
-//     the old kernel tested every group per fragment (8 lookups of ~30 instructions).  The lookup point of group g,
-//     P_g(pos) = pos + h_g * normalize(light - pos) / dim, is a function of the start position only, so a coarse grid
-//     over the volume (cells of 2 voxels) stores, per cell, one bit per group: the OR of M_l over every texel P_g can
-//     reach from a start position inside the cell (cell box pushed along the cone, widened by the variation of the
-//     light direction over the cell).  A fragment reads one byte.  Conservative by construction, so still exact.
+// (2) Need codes.  Only the sun-facing shell of the cloud is lit, so most of the fine (textureLod) cone steps read nothing
+//     but zero texels and contribute exactly 0.  The sample point of step i, pos + h_i * normalize(light - pos) / dim, is a
+//     function of the start position only, so a coarse grid over the volume (cells of 2 voxels) stores, per cell, one bit
+//     per group of consecutive steps: can a step of the group, started inside the cell, read a non-zero texel?  The test is
+//     the footprint itself (cell box pushed along the cone, widened by the variation of the light direction over the cell,
+//     converted to the 2x2x2-per-sample texel range) against the non-zero bits of the sampled level(s) (k_skipmask.cu).
+//     A fragment reads one byte.  Conservative by construction, so still exact.
 #include "crn_internal.cuh"
 
 #include <algorithm>
@@ -119,17 +120,24 @@ __global__ void __launch_bounds__(256) bake_steps_kernel(const __grid_constant__
 }
 
 struct CodeGroup {
-    float reach;                              // group height / dim: |P - pos| in normalized coordinates
+    float hMin, hMax;                         // heights of the group's first and last step / dim: |P - pos| in normalized coordinates
+    int lv0, nLv;                             // mip levels its steps sample: lv0 (and lv0 + 1 when nLv == 2)
+};
+
+struct CodeLevel {
+    int size, wpr;                            // texels per axis, words per row of the non-zero bit volume
+    uint32_t off;                             // word offset in `nz` (level 0: the occupancy set itself)
     float sizeF;
-    int size, wpr;
-    uint32_t maskOff;
 };
 
 struct CodeArgs {
     int G;
     int nGroups;
+    int coarse;                               // level of the early-out test (groups whose levels are all <= coarse)
     CodeGroup g[kCodeGroups];
-    const uint32_t *mask;
+    CodeLevel lv[kMaxLevels];
+    const uint32_t *bits;                     // level 0: one bit per voxel
+    const uint32_t *nz;                       // levels >= 1: one bit per non-zero texel (k_skipmask.cu)
     const uint32_t *worldBox;                 // sortable bits of the billboards' world bounding box (k_prep_sort.cu), or nullptr
     float lightPos[3], b0[3], range[3];
     uint8_t *code;
@@ -138,6 +146,42 @@ struct CodeArgs {
 
 __device__ __forceinline__ float unsortable(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u); }
 
+struct TexelBox {
+    int lo[3], hi[3];
+};
+
+// texels of a level a LINEAR, CLAMP_TO_EDGE lookup can read when its normalized coordinate lies in [pmin, pmax]:
+// floor(p * n - 1/2) and the one after, with 1/64 texel of slack for the texture unit's fixed-point coordinates
+__device__ __forceinline__ TexelBox footprint(const float pmin[3], const float pmax[3], const CodeLevel &L) {
+    TexelBox b;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        b.lo[k] = min(max(__float2int_rd(fmaf(pmin[k], L.sizeF, -0.515625f)), 0), L.size - 1);
+        b.hi[k] = min(max(__float2int_rd(fmaf(pmax[k], L.sizeF, -0.484375f)) + 1, 0), L.size - 1);
+    }
+    return b;
+}
+
+__device__ __forceinline__ bool any_set(const uint32_t *__restrict__ m, const CodeLevel &L, const TexelBox &b) {
+    const int w0 = b.lo[0] >> 5, w1 = b.hi[0] >> 5;
+    uint32_t any = 0;
+    for (int z = b.lo[2]; z <= b.hi[2]; z++)
+        for (int y = b.lo[1]; y <= b.hi[1]; y++) {
+            const uint32_t *row = m + (uint32_t)(z * L.size + y) * (uint32_t)L.wpr;
+            for (int w = w0; w <= w1; w++) {
+                uint32_t sel = 0xFFFFFFFFu;
+                if (w == w0) sel &= 0xFFFFFFFFu << (b.lo[0] & 31);
+                if (w == w1) sel &= 0xFFFFFFFFu >> (31 - (b.hi[0] & 31));
+                any |= __ldg(row + w) & sel;
+            }
+        }
+    return any != 0;
+}
+
+// One thread per cell.  Bit g of the cell's code: some step of group g, started anywhere inside the cell, can read a non-zero
+// texel.  The test is the footprint itself: the cell's box pushed along the cone by the group's height range (widened by
+// the variation of the light direction over the cell), converted to the texel range a trilinear lookup touches, against
+// the non-zero bits of the level(s) the group samples.  Conservative by construction, so skipping on a clear bit is exact.
 __global__ void __launch_bounds__(256) need_code_kernel(const __grid_constant__ CodeArgs a) {
     const int G = a.G;
     const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = blockIdx.y * 8 + (threadIdx.x >> 5), iz = blockIdx.z;
@@ -171,60 +215,65 @@ __global__ void __launch_bounds__(256) need_code_kernel(const __grid_constant__ 
     // the unit vector towards the light turns by at most |dw| / (distance to the light) over the cell; a light inside
     // or next to the cell gives no useful bound: every group stays needed there
     const float dmin = dist - hw;
+    const uint32_t all = (1u << a.nGroups) - 1u;
     if (!(dmin > 4.0f * hw) || !(dist > 0.0f)) {
-        a.code[cell] = 0xFF;
+        a.code[cell] = (uint8_t)all;
         if (a.codeSurf) surf3Dwrite((unsigned char)0, a.codeSurf, ix, iy, iz);
         return;
     }
     const float invDist = 1.0f / dist, turn = (hw / dmin) * 1.01f;
-    uint32_t bitsOut = 0;
-    for (int g = 0; g < a.nGroups; g++) {
+    float dir[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) dir[k] = toL[k] * invDist;
+
+    // range of sample positions of every group, and an early out on the union of the fine groups at a coarse level: a
+    // non-zero texel of level l has a non-zero ancestor up to three levels above it (255 -> 32 -> 4 -> 1 through
+    // (sum + 4) >> 3; floats never vanish), so an all-zero coarse range clears every group inside it at once
+    float pmin[kCodeGroups][3], pmax[kCodeGroups][3];
+    const CodeLevel &LC = a.lv[a.coarse];
+    int clo[3] = {1 << 30, 1 << 30, 1 << 30}, chi[3] = {-1, -1, -1};
+    uint32_t fineSet = 0;
+#pragma unroll
+    for (int g = 0; g < kCodeGroups; g++) {
+        if (g >= a.nGroups) break;
         const CodeGroup &cg = a.g[g];
-        const float ext = half + cg.reach * turn + 2.0e-5f;
-        const int n = cg.size;
-        int lo[3], hi[3];
+        const float spread = cg.hMax * turn + 2.0e-5f;
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            const float p = nc[k] + cg.reach * toL[k] * invDist;
-            // the trace kernel looks the point up with CLAMP_TO_EDGE semantics: clamp the texel range the same way
-            lo[k] = min(max(__float2int_rd((p - ext) * cg.sizeF), 0), n - 1);
-            hi[k] = min(max(__float2int_rd((p + ext) * cg.sizeF), 0), n - 1);
+            const float p0 = cg.hMin * dir[k], p1 = cg.hMax * dir[k];
+            pmin[g][k] = nc[k] - half + fminf(p0, p1) - spread;
+            pmax[g][k] = nc[k] + half + fmaxf(p0, p1) + spread;
         }
-        const uint32_t *m = a.mask + cg.maskOff;
-        const int w0 = lo[0] >> 5, w1 = hi[0] >> 5;
-        const uint32_t sel0 = (0xFFFFFFFFu << (lo[0] & 31)) & (w1 == w0 ? 0xFFFFFFFFu >> (31 - (hi[0] & 31)) : 0xFFFFFFFFu);
-        uint32_t any = 0;
-        // The range is at most 4 texels per axis unless the light is very close: 16 independent loads, no loop
-        // (rows past hi are clamped onto hi: duplicates do not change an OR)
-        const bool small = hi[1] - lo[1] < 4 && hi[2] - lo[2] < 4 && w1 - w0 < 2;
-        if (__all_sync(__activemask(), small)) {
-            uint32_t a0 = 0, a1 = 0;
-            const bool two = __any_sync(__activemask(), w1 != w0);
+        if (cg.lv0 + cg.nLv - 1 <= a.coarse && a.coarse - cg.lv0 <= 3) {
+            fineSet |= 1u << g;
+            for (int j = 0; j < cg.nLv; j++) {                       // (the upper level's footprint is not the parents of the lower one's)
+                const TexelBox b = footprint(pmin[g], pmax[g], a.lv[cg.lv0 + j]);
+                const int sh = a.coarse - cg.lv0 - j;
 #pragma unroll
-            for (int dz = 0; dz < 4; dz++)
+                for (int k = 0; k < 3; k++) { clo[k] = min(clo[k], b.lo[k] >> sh); chi[k] = max(chi[k], b.hi[k] >> sh); }
+            }
+        }
+    }
+    uint32_t candidates = all;
+    if (fineSet) {
+        TexelBox cb;
 #pragma unroll
-                for (int dy = 0; dy < 4; dy++) {
-                    const uint32_t *row = m + (uint32_t)(min(lo[2] + dz, hi[2]) * n + min(lo[1] + dy, hi[1])) * (uint32_t)cg.wpr;
-                    a0 |= __ldg(row + w0);
-                    if (two) a1 |= __ldg(row + w1);
-                }
-            any = (a0 & sel0) | (w1 != w0 ? a1 & (0xFFFFFFFFu >> (31 - (hi[0] & 31))) : 0u);
-        } else {
-            for (int z = lo[2]; z <= hi[2]; z++)
-                for (int y = lo[1]; y <= hi[1]; y++) {
-                    const uint32_t *row = m + (uint32_t)(z * n + y) * (uint32_t)cg.wpr;
-                    for (int w = w0; w <= w1; w++) {
-                        uint32_t sel = 0xFFFFFFFFu;
-                        if (w == w0) sel &= 0xFFFFFFFFu << (lo[0] & 31);
-                        if (w == w1) sel &= 0xFFFFFFFFu >> (31 - (hi[0] & 31));
-                        any |= __ldg(row + w) & sel;
-                    }
-                }
+        for (int k = 0; k < 3; k++) { cb.lo[k] = clo[k]; cb.hi[k] = min(chi[k], LC.size - 1); }
+        if (!any_set(a.coarse == 0 ? a.bits : a.nz + LC.off, LC, cb)) candidates &= ~fineSet;
+    }
+    uint32_t bitsOut = 0;
+    for (int g = 0; g < a.nGroups; g++) {
+        if (!((candidates >> g) & 1u)) continue;
+        const CodeGroup &cg = a.g[g];
+        bool any = false;
+        for (int j = 0; j < cg.nLv && !any; j++) {
+            const CodeLevel &L = a.lv[cg.lv0 + j];
+            any = any_set(cg.lv0 + j == 0 ? a.bits : a.nz + L.off, L, footprint(pmin[g], pmax[g], L));
         }
         if (any) bitsOut |= 1u << g;
     }
     a.code[cell] = (uint8_t)bitsOut;
-    if (a.codeSurf) surf3Dwrite((unsigned char)(~bitsOut & ((1u << a.nGroups) - 1u)), a.codeSurf, ix, iy, iz);
+    if (a.codeSurf) surf3Dwrite((unsigned char)(~bitsOut & all), a.codeSurf, ix, iy, iz);
 }
 
 } // namespace
@@ -256,16 +305,26 @@ int launch_bake_steps(cudaStream_t st, const VolumeParams &vol, const uint32_t *
     return 1;
 }
 
-int launch_need_code(cudaStream_t st, const VolumeParams &vol, const TraceParams &tp, const uint32_t *mask, const uint32_t *worldBox, uint8_t *code,
-                     cudaSurfaceObject_t codeSurf) {
+int launch_need_code(cudaStream_t st, const VolumeParams &vol, const TraceParams &tp, const uint32_t *bits, const uint32_t *nz, const uint32_t *worldBox,
+                     uint8_t *code, cudaSurfaceObject_t codeSurf) {
     CodeArgs a{};
     a.G = tp.codeDim;
     a.nGroups = std::min(tp.nGroups, kCodeGroups);
+    int top = 0;
     for (int g = 0; g < a.nGroups; g++) {
-        a.g[g].reach = tp.groups[g].height / (float)vol.dim; a.g[g].size = tp.groups[g].size; a.g[g].sizeF = (float)tp.groups[g].size;
-        a.g[g].wpr = tp.groups[g].wpr; a.g[g].maskOff = tp.groups[g].maskOff;
+        const ConeGroup &gr = tp.groups[g];
+        a.g[g].hMin = tp.steps[gr.first].height / (float)vol.dim; a.g[g].hMax = tp.steps[gr.first + gr.count - 1].height / (float)vol.dim;
+        a.g[g].lv0 = gr.level; a.g[g].nLv = (gr.two && gr.level + 1 < vol.levels) ? 2 : 1;
+        top = std::max(top, gr.level + a.g[g].nLv - 1);
     }
-    a.mask = mask; a.code = code; a.worldBox = worldBox; a.codeSurf = codeSurf;
+    a.coarse = std::min(std::min(std::max(top, 2), 3), vol.levels - 1);
+    uint32_t off[kMaxLevels] = {};
+    skipmask_words(vol, off);
+    for (int l = 0; l < vol.levels; l++) {
+        a.lv[l].size = vol.levelSize[l]; a.lv[l].sizeF = (float)vol.levelSize[l];
+        a.lv[l].wpr = vol.levelSize[l] >= 32 ? vol.levelSize[l] / 32 : 1; a.lv[l].off = off[l];
+    }
+    a.bits = bits; a.nz = nz; a.code = code; a.worldBox = worldBox; a.codeSurf = codeSurf;
     a.b0[0] = vol.xB[0]; a.b0[1] = vol.yB[0]; a.b0[2] = vol.zB[0];
     a.range[0] = vol.xB[1] - vol.xB[0]; a.range[1] = vol.yB[1] - vol.yB[0]; a.range[2] = vol.zB[1] - vol.zB[0];
     for (int k = 0; k < 3; k++) a.lightPos[k] = tp.lightPos[k];

@@ -1,22 +1,13 @@
-// k_skipmask.cu — conservative empty-space masks for the cone trace.
+// k_skipmask.cu — non-zero bit volumes of the mip levels, for the cone trace's empty-space skipping.
 //
 // traceCone (res/conetrace_frag.glsl:64-79) always takes all `steps` samples, but in a cloud
-// only the sun-facing shell is lit (1 % of the voxels at C3), so ~80 % of the samples read
+// only the sun-facing shell is lit (1 % of the voxels at C3), so most of the samples read
 // nothing but zero texels and contribute exactly 0 to the sum.  Skipping those is EXACT as long
-// as the skip test is conservative.  For every level l this file builds one bit per texel:
-//
-//     M_l(t) = 1  iff  some texel of level l within the 5x5x5 neighbourhood of t is non-zero,
-//                 or   some texel of level l+1 within the 5x5x5 neighbourhood of parent(t) is.
-//
-// The trace kernel groups consecutive cone steps that share the lower mip level and lie within
-// one level-l texel of a common point; if M_l at the texel containing that point is 0, every
-// trilinear footprint (level l and level l+1, CLAMP_TO_EDGE) of every step in the group lies
-// inside the all-zero neighbourhood, so all of them return exactly 0 and are skipped.
-//
-// Three tiny launches per frame (bit-parallel, word = 32 texels along x):
-//   nonzero_kernel : R8 levels >= 1 -> bit volumes (level 0 is already the occupancy set)
-//   dilate_kernel  : S_l = 5x5x5 dilation of the non-zero bits of level l
-//   combine_kernel : M_l = S_l | upsample(S_{l+1})
+// as the skip test is conservative.  The test itself lives in k_conebake.cu (need codes: the
+// texel footprint a group of cone steps can reach from a cell of start positions); this file
+// supplies what it is tested against: one bit per texel of every level >= 1, set iff the texel
+// is non-zero (level 0 is already the 1-bit occupancy set).  One tiny launch per frame
+// (bit-parallel, word = 32 texels along x).
 #include "crn_internal.cuh"
 
 namespace crn {
@@ -30,13 +21,9 @@ struct MaskArgs {
     uint32_t off[kMaxLevels];      // word offset of the level in each mask buffer
     uint32_t chainOff[kMaxLevels];
     uint32_t totalWords;
-    const uint32_t *bits;          // level-0 occupancy
     const uint8_t *chain;
     int texelBytes;
-    uint32_t *nz;                  // non-zero bits, levels >= 1 (level 0 slot unused)
-    uint32_t *dil;                 // S_l
-    uint32_t *mask;                // M_l
-    uint32_t *fill;                // fill[l] = number of set bits of M_l (the trace kernel skips tests that cannot pay off)
+    uint32_t *nz;                  // non-zero bits, levels >= 1 (level 0 slot unused: the occupancy set is that level's)
 };
 
 __device__ __forceinline__ bool locate(const MaskArgs &a, uint32_t w, int &l, int &z, int &y, int &wx) {
@@ -79,63 +66,6 @@ __global__ void __launch_bounds__(256) nonzero_kernel(MaskArgs a) {
     a.nz[w] = m;
 }
 
-__global__ void __launch_bounds__(256) dilate_kernel(MaskArgs a) {
-    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    int l, z, y, wx;
-    if (!locate(a, w, l, z, y, wx)) return;
-    const int n = a.size[l], wpr = a.wpr[l];
-    const uint32_t *src = (l == 0 ? a.bits : a.nz + a.off[l]);
-    // dilation commutes with OR: gather the 5x5 (y,z) rows first, spread along x once
-    uint32_t c = 0, lo = 0, hi = 0;
-    const bool hasLo = wx > 0, hasHi = wx + 1 < wpr;
-    for (int dz = -2; dz <= 2; dz++) {
-        const int zz = z + dz;
-        if (zz < 0 || zz >= n) continue;
-#pragma unroll
-        for (int dy = -2; dy <= 2; dy++) {
-            const int yy = y + dy;
-            if (yy < 0 || yy >= n) continue;
-            const uint32_t *row = src + ((size_t)zz * n + yy) * wpr + wx;
-            c |= row[0];
-            if (hasLo) lo |= row[-1];
-            if (hasHi) hi |= row[1];
-        }
-    }
-    uint32_t acc = c | (c << 1) | (c << 2) | (c >> 1) | (c >> 2) | (lo >> 31) | (lo >> 30) | (hi << 31) | (hi << 30);
-    if (n < 32) acc &= (1u << n) - 1u;
-    a.dil[w] = acc;
-}
-
-__device__ __forceinline__ uint32_t double_bits16(uint32_t h) {     // 16 bits -> each bit twice (32 bits)
-    uint32_t x = h & 0xFFFFu;
-    x = (x | (x << 8)) & 0x00FF00FFu;
-    x = (x | (x << 4)) & 0x0F0F0F0Fu;
-    x = (x | (x << 2)) & 0x33333333u;
-    x = (x | (x << 1)) & 0x55555555u;
-    return x | (x << 1);
-}
-
-__global__ void __launch_bounds__(256) combine_kernel(MaskArgs a) {
-    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    int l = -1, z, y, wx;
-    uint32_t m = 0;
-    if (locate(a, w, l, z, y, wx)) {
-        m = a.dil[w];
-        if (l + 1 < a.levels) {
-            const int np = a.size[l + 1], wprp = a.wpr[l + 1];
-            const uint32_t *prow = a.dil + a.off[l + 1] + ((size_t)(z >> 1) * np + (y >> 1)) * wprp;
-            const uint32_t pw = prow[wx >> 1];
-            m |= double_bits16((wx & 1) ? (pw >> 16) : pw);
-            if (a.size[l] < 32) m &= (1u << a.size[l]) - 1u;
-        }
-        a.mask[w] = m;
-    }
-    // per-level population of M_l: one atomic per (warp, level)
-    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, l);
-    const uint32_t sum = __reduce_add_sync(peers, (uint32_t)__popc(m));
-    if (l >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1 && sum) atomicAdd(&a.fill[l], sum);
-}
-
 } // namespace
 
 size_t skipmask_words(const VolumeParams &vol, uint32_t *off) {
@@ -148,8 +78,8 @@ size_t skipmask_words(const VolumeParams &vol, uint32_t *off) {
     return total;
 }
 
-int launch_skipmask(cudaStream_t st, const VolumeParams &vol, const uint32_t *bits, const uint8_t *chain, uint32_t *nz,
-                    uint32_t *dil, uint32_t *mask, uint32_t *fill) {
+int launch_skipmask(cudaStream_t st, const VolumeParams &vol, const uint8_t *chain, uint32_t *nz) {
+    if (vol.levels <= 1) return 0;
     MaskArgs a{};
     a.levels = vol.levels;
     for (int l = 0; l < vol.levels; l++) {
@@ -158,18 +88,11 @@ int launch_skipmask(cudaStream_t st, const VolumeParams &vol, const uint32_t *bi
         a.chainOff[l] = vol.levelOff[l];
     }
     a.totalWords = (uint32_t)skipmask_words(vol, a.off);
-    a.bits = bits; a.chain = chain; a.nz = nz; a.dil = dil; a.mask = mask; a.fill = fill;
-    cudaMemsetAsync(fill, 0, kMaxLevels * sizeof(uint32_t), st);
+    a.chain = chain; a.nz = nz;
     a.texelBytes = vol.texelBytes;
-    int launches = 0;
-    if (vol.levels > 1) {
-        const uint32_t upper = a.totalWords - a.off[1];
-        nonzero_kernel<<<(upper + 255) / 256, 256, 0, st>>>(a);
-        launches++;
-    }
-    dilate_kernel<<<(a.totalWords + 255) / 256, 256, 0, st>>>(a);
-    combine_kernel<<<(a.totalWords + 255) / 256, 256, 0, st>>>(a);
-    return launches + 2;
+    const uint32_t upper = a.totalWords - a.off[1];
+    nonzero_kernel<<<(upper + 255) / 256, 256, 0, st>>>(a);
+    return 1;
 }
 
 } // namespace crn

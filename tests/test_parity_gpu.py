@@ -325,7 +325,7 @@ def test_tile_row_interleave_is_result_invariant(pkg, scenes, orc, renderer):
 
 @pytest.mark.parametrize("name", ["small", "C1", "C2crop"])
 def test_empty_space_skipping_is_exact(name, pkg, scenes, orc, renderer):
-    """cone samples proven all-zero by the dilated occupancy masks (through the need-code grid) contribute exactly 0: the
+    """cone samples proven all-zero by the need-code grid (texel footprints against the non-zero bits) contribute exactly 0: the
     image with skipping on is bit-identical to the image with every sample fetched, for both samplers.  With the texture
     sampler the coarse steps are baked (never skipped); at 32^3 / 64^3 that is every step, at 128^3 the level-0 steps
     remain textureLod fetches and are skipped."""
