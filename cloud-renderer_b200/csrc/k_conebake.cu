@@ -133,7 +133,9 @@ struct CodeLevel {
 struct CodeArgs {
     int G;
     int nGroups;
-    int coarse;                               // level of the early-out test (groups whose levels are all <= coarse)
+    int coarse;                               // level of the early-out test
+    uint32_t fineSet;                         // groups it covers: all levels <= coarse and at most three levels below it
+    float fineMin, fineMax;                   // height range of those groups / dim
     CodeGroup g[kCodeGroups];
     CodeLevel lv[kMaxLevels];
     const uint32_t *bits;                     // level 0: one bit per voxel
@@ -162,31 +164,47 @@ __device__ __forceinline__ TexelBox footprint(const float pmin[3], const float p
     return b;
 }
 
-__device__ __forceinline__ bool any_set(const uint32_t *__restrict__ m, const CodeLevel &L, const TexelBox &b) {
-    const int w0 = b.lo[0] >> 5, w1 = b.hi[0] >> 5;
-    uint32_t any = 0;
-    for (int z = b.lo[2]; z <= b.hi[2]; z++)
-        for (int y = b.lo[1]; y <= b.hi[1]; y++) {
-            const uint32_t *row = m + (uint32_t)(z * L.size + y) * (uint32_t)L.wpr;
-            for (int w = w0; w <= w1; w++) {
-                uint32_t sel = 0xFFFFFFFFu;
-                if (w == w0) sel &= 0xFFFFFFFFu << (b.lo[0] & 31);
-                if (w == w1) sel &= 0xFFFFFFFFu >> (31 - (b.hi[0] & 31));
-                any |= __ldg(row + w) & sel;
-            }
+// Warp-cooperative test of one level: every lane has its own texel box (live lanes only); the (y, z) rows are taken over the
+// union of the lanes' ranges (a superset: still conservative), each lane loads one row word per word column, one OR
+// reduction per column, then every lane looks at its own x range in the reduced words.  The 32 cells of a warp are
+// neighbours in x, so their boxes overlap almost entirely: ~3 loads per lane instead of ~25.
+__device__ __forceinline__ bool warp_any_set(const uint32_t *__restrict__ m, const CodeLevel &L, const TexelBox &b, bool live) {
+    const uint32_t full = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const int ylo = __reduce_min_sync(full, live ? b.lo[1] : 0x7FFFFFFF), yhi = __reduce_max_sync(full, live ? b.hi[1] : -1);
+    const int zlo = __reduce_min_sync(full, live ? b.lo[2] : 0x7FFFFFFF), zhi = __reduce_max_sync(full, live ? b.hi[2] : -1);
+    const int wlo = __reduce_min_sync(full, live ? b.lo[0] >> 5 : 0x7FFFFFFF), whi = __reduce_max_sync(full, live ? b.hi[0] >> 5 : -1);
+    if (yhi < ylo) return false;                                      // no live lane
+    const int ny = yhi - ylo + 1, rows = ny * (zhi - zlo + 1);
+    bool any = false;
+    for (int w = wlo; w <= whi; w++) {
+        uint32_t acc = 0;
+        for (int r = lane; r < rows; r += 32) {
+            const int y = ylo + r % ny, z = zlo + r / ny;
+            acc |= __ldg(m + (uint32_t)(z * L.size + y) * (uint32_t)L.wpr + w);
         }
-    return any != 0;
+        acc = __reduce_or_sync(full, acc);
+        if (live && w >= (b.lo[0] >> 5) && w <= (b.hi[0] >> 5)) {
+            uint32_t sel = full;
+            if (w == (b.lo[0] >> 5)) sel &= full << (b.lo[0] & 31);
+            if (w == (b.hi[0] >> 5)) sel &= full >> (31 - (b.hi[0] & 31));
+            any = any || (acc & sel) != 0;
+        }
+    }
+    return any;
 }
 
-// One thread per cell.  Bit g of the cell's code: some step of group g, started anywhere inside the cell, can read a non-zero
-// texel.  The test is the footprint itself: the cell's box pushed along the cone by the group's height range (widened by
-// the variation of the light direction over the cell), converted to the texel range a trilinear lookup touches, against
-// the non-zero bits of the level(s) the group samples.  Conservative by construction, so skipping on a clear bit is exact.
+// One thread per cell, one warp per run of 32 cells along x.  Bit g of the cell's code: some step of group g, started
+// anywhere inside the cell, can read a non-zero texel.  The test is the footprint itself: the cell's box pushed along the
+// cone by the group's height range (widened by the variation of the light direction over the cell), converted to the texel
+// range a trilinear lookup touches, against the non-zero bits of the level(s) the group samples.  Conservative by
+// construction, so skipping on a clear bit is exact.
 __global__ void __launch_bounds__(256) need_code_kernel(const __grid_constant__ CodeArgs a) {
     const int G = a.G;
     const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = blockIdx.y * 8 + (threadIdx.x >> 5), iz = blockIdx.z;
-    if (ix >= G || iy >= G) return;
-    const uint32_t cell = ((uint32_t)iz * G + iy) * G + ix;
+    if (iy >= G) return;                                              // (whole warps)
+    bool live = ix < G;
+    const uint32_t cell = ((uint32_t)iz * G + iy) * G + min(ix, G - 1);
     const float invG = 1.0f / (float)G;
     if (a.worldBox) {
         // fragments start on the billboards' spheres: a cell that does not meet their bounding box is never looked up
@@ -195,9 +213,10 @@ __global__ void __launch_bounds__(256) need_code_kernel(const __grid_constant__ 
         for (int k = 0; k < 3; k++) {
             const float lo = unsortable(__ldg(a.worldBox + k)), hi = unsortable(__ldg(a.worldBox + 3 + k));
             const float c0 = a.b0[k] + ((float)ic[k] - 0.01f) * invG * a.range[k], c1 = a.b0[k] + ((float)ic[k] + 1.01f) * invG * a.range[k];
-            if (fmaxf(c0, c1) < lo || fminf(c0, c1) > hi) return;
+            if (fmaxf(c0, c1) < lo || fminf(c0, c1) > hi) live = false;
         }
     }
+    if (!__any_sync(0xFFFFFFFFu, live)) return;
     // half a cell, in normalized coordinates, with slack: the fast trace variant finds its cell with a point-sampled texture
     // fetch, whose fixed-point coordinate may land in the neighbouring cell within 1/256 of a cell border
     const float half = 0.5f * invG * (1.0f + 1.0f / 64.0f) + 1.0e-6f;
@@ -216,64 +235,57 @@ __global__ void __launch_bounds__(256) need_code_kernel(const __grid_constant__ 
     // or next to the cell gives no useful bound: every group stays needed there
     const float dmin = dist - hw;
     const uint32_t all = (1u << a.nGroups) - 1u;
-    if (!(dmin > 4.0f * hw) || !(dist > 0.0f)) {
+    const bool near = !(dmin > 4.0f * hw) || !(dist > 0.0f);
+    if (live && near) {
         a.code[cell] = (uint8_t)all;
         if (a.codeSurf) surf3Dwrite((unsigned char)0, a.codeSurf, ix, iy, iz);
-        return;
     }
-    const float invDist = 1.0f / dist, turn = (hw / dmin) * 1.01f;
+    live = live && !near;
+    if (!__any_sync(0xFFFFFFFFu, live)) return;
+    const float invDist = near ? 0.0f : 1.0f / dist, turn = near ? 0.0f : (hw / dmin) * 1.01f;
     float dir[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) dir[k] = toL[k] * invDist;
 
-    // range of sample positions of every group, and an early out on the union of the fine groups at a coarse level: a
-    // non-zero texel of level l has a non-zero ancestor up to three levels above it (255 -> 32 -> 4 -> 1 through
-    // (sum + 4) >> 3; floats never vanish), so an all-zero coarse range clears every group inside it at once
-    float pmin[kCodeGroups][3], pmax[kCodeGroups][3];
-    const CodeLevel &LC = a.lv[a.coarse];
-    int clo[3] = {1 << 30, 1 << 30, 1 << 30}, chi[3] = {-1, -1, -1};
-    uint32_t fineSet = 0;
-#pragma unroll
-    for (int g = 0; g < kCodeGroups; g++) {
-        if (g >= a.nGroups) break;
-        const CodeGroup &cg = a.g[g];
-        const float spread = cg.hMax * turn + 2.0e-5f;
+    // sample positions a group's steps can reach from inside the cell
+    auto reach = [&](float h0, float h1, float pmin[3], float pmax[3]) {
+        const float spread = h1 * turn + 2.0e-5f;
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            const float p0 = cg.hMin * dir[k], p1 = cg.hMax * dir[k];
-            pmin[g][k] = nc[k] - half + fminf(p0, p1) - spread;
-            pmax[g][k] = nc[k] + half + fmaxf(p0, p1) + spread;
+            const float p0 = h0 * dir[k], p1 = h1 * dir[k];
+            pmin[k] = nc[k] - half + fminf(p0, p1) - spread;
+            pmax[k] = nc[k] + half + fmaxf(p0, p1) + spread;
         }
-        if (cg.lv0 + cg.nLv - 1 <= a.coarse && a.coarse - cg.lv0 <= 3) {
-            fineSet |= 1u << g;
-            for (int j = 0; j < cg.nLv; j++) {                       // (the upper level's footprint is not the parents of the lower one's)
-                const TexelBox b = footprint(pmin[g], pmax[g], a.lv[cg.lv0 + j]);
-                const int sh = a.coarse - cg.lv0 - j;
-#pragma unroll
-                for (int k = 0; k < 3; k++) { clo[k] = min(clo[k], b.lo[k] >> sh); chi[k] = max(chi[k], b.hi[k] >> sh); }
-            }
-        }
-    }
-    uint32_t candidates = all;
-    if (fineSet) {
-        TexelBox cb;
-#pragma unroll
-        for (int k = 0; k < 3; k++) { cb.lo[k] = clo[k]; cb.hi[k] = min(chi[k], LC.size - 1); }
-        if (!any_set(a.coarse == 0 ? a.bits : a.nz + LC.off, LC, cb)) candidates &= ~fineSet;
+    };
+    // Early out for all the groups whose levels lie at or below a coarse level (at most three levels above their own): the
+    // coarse level's own trilinear footprint of everything those groups can reach contains the ancestors of every finer
+    // texel they can read, and a non-zero texel has non-zero ancestors up to three levels up (255 -> 32 -> 4 -> 1 through
+    // (sum + 4) >> 3; floats never vanish).  Nearly every cell leaves here.
+    uint32_t candidates = live ? all : 0u;
+    if (a.fineSet) {
+        float pmin[3], pmax[3];
+        reach(a.fineMin, a.fineMax, pmin, pmax);
+        const CodeLevel &LC = a.lv[a.coarse];
+        if (!warp_any_set(a.coarse == 0 ? a.bits : a.nz + LC.off, LC, footprint(pmin, pmax, LC), live)) candidates &= ~a.fineSet;
     }
     uint32_t bitsOut = 0;
     for (int g = 0; g < a.nGroups; g++) {
-        if (!((candidates >> g) & 1u)) continue;
+        const bool want = (candidates >> g) & 1u;
+        if (!__any_sync(0xFFFFFFFFu, want)) continue;
         const CodeGroup &cg = a.g[g];
+        float pmin[3], pmax[3];
+        reach(cg.hMin, cg.hMax, pmin, pmax);
         bool any = false;
-        for (int j = 0; j < cg.nLv && !any; j++) {
+        for (int j = 0; j < cg.nLv; j++) {
             const CodeLevel &L = a.lv[cg.lv0 + j];
-            any = any_set(cg.lv0 + j == 0 ? a.bits : a.nz + L.off, L, footprint(pmin[g], pmax[g], L));
+            any = warp_any_set(cg.lv0 + j == 0 ? a.bits : a.nz + L.off, L, footprint(pmin, pmax, L), want) || any;
         }
         if (any) bitsOut |= 1u << g;
     }
-    a.code[cell] = (uint8_t)bitsOut;
-    if (a.codeSurf) surf3Dwrite((unsigned char)(~bitsOut & all), a.codeSurf, ix, iy, iz);
+    if (live) {
+        a.code[cell] = (uint8_t)bitsOut;
+        if (a.codeSurf) surf3Dwrite((unsigned char)(~bitsOut & all), a.codeSurf, ix, iy, iz);
+    }
 }
 
 } // namespace
@@ -318,6 +330,12 @@ int launch_need_code(cudaStream_t st, const VolumeParams &vol, const TraceParams
         top = std::max(top, gr.level + a.g[g].nLv - 1);
     }
     a.coarse = std::min(std::min(std::max(top, 2), 3), vol.levels - 1);
+    a.fineSet = 0; a.fineMin = 1e30f; a.fineMax = 0.0f;
+    for (int g = 0; g < a.nGroups; g++)
+        if (a.g[g].lv0 + a.g[g].nLv - 1 <= a.coarse && a.coarse - a.g[g].lv0 <= 3) {
+            a.fineSet |= 1u << g;
+            a.fineMin = std::min(a.fineMin, a.g[g].hMin); a.fineMax = std::max(a.fineMax, a.g[g].hMax);
+        }
     uint32_t off[kMaxLevels] = {};
     skipmask_words(vol, off);
     for (int l = 0; l < vol.levels; l++) {
