@@ -412,16 +412,20 @@ class Runner:
         return st
 
 
-def tex_roofline(st, trace_ms, bil_peak):
-    """texture-pipe roofline of the trace kernel: every lookup charged in bilinear passes of the texture unit (noise tap on
-    the slice-pair texture 1, baked cone step 1, trilinear 2, mip-linear textureLod 4), against the measured ceiling"""
-    noise, baked = st.noiseSamples, st.bakedFetches
-    tri = st.filteredFetches - noise - baked               # trilinear-equivalents of the textureLod cone steps
-    passes = noise + baked + 2 * tri
+def tex_roofline(st, trace_ms, bil_peak, octaves=4):
+    """texture-pipe roofline of the trace kernel: every lookup the fast variant issues, charged in bilinear passes of the
+    texture unit (noise tap on a slice-pair texture 1 - a march step inside the combined-octave lattice takes 2 taps
+    instead of one per octave -, baked cone step 1, need-code lookup 1, trilinear 2, mip-linear textureLod 4), against the
+    measured ceiling"""
+    noise = st.noiseSamples - st.noiseLatticeSteps * (octaves - 2)
+    baked, code = st.bakedFetches, st.codeLookups
+    tri = st.filteredFetches - st.noiseSamples - baked     # trilinear-equivalents of the textureLod cone steps
+    passes = noise + baked + code + 2 * tri
     achieved = passes / (trace_ms * 1e-3) / 1e9
     return {"bound": "tex", "unit": "G bilinear passes/s", "achieved": achieved, "peak": bil_peak,
             "frac": achieved / bil_peak if bil_peak else None,
-            "passes_per_launch": passes, "noise_bilinear": noise, "baked_cone_bilinear": baked, "textureLod_trilinear_equiv": tri}
+            "passes_per_launch": passes, "noise_bilinear": noise, "noise_lattice_steps": st.noiseLatticeSteps, "baked_cone_bilinear": baked,
+            "need_code_lookups": code, "textureLod_trilinear_equiv": tri}
 
 
 def summarize(run, ms, ms_e2e, job_frames):
@@ -449,9 +453,12 @@ def main():
     from cloud_renderer_b200 import scene as sc
     dev = torch.device("cuda", local)
     stream = torch.cuda.Stream(dev)            # torch's default stream has handle 0, which the C-ABI reads as "create your own":
+    # L2 flush between steps: a fill of a buffer 10 % larger than the L2 (126 MB on B200), rounded up to a MiB
+    l2 = int(getattr(torch.cuda.get_device_properties(dev), "L2_cache_size", 0)) or (126 << 20)
+    flush_bytes = ((int(l2 * 1.1) >> 20) + 1) << 20
     torch.cuda.set_stream(stream)              # use one explicit stream for torch's events / flush / NCCL waits AND the library's kernels
     ctx = dict(torch=torch, dist=dist, pkg=pkg, sc=sc, world=world, rank=rank, local=local, dev=dev, stream=stream,
-               flush=torch.empty(256 << 20, dtype=torch.uint8, device=dev))
+               flush=torch.empty(flush_bytes, dtype=torch.uint8, device=dev))
 
     K, Wm = args.steps, args.warmup
     cfg = args.config
@@ -545,7 +552,7 @@ def main():
                              "time steps (C5: views) round-robin over ranks, volume replicated, no collective" if world > 1 else "single GPU"),
                 "transmittance_cutoff": args.cutoff, "sampler": args.sampler, "skip_empty_space": not args.no_skip,
                 "volume_format": args.volume_format,
-                "l2": "none (back to back)" if args.no_flush else "256 MiB fill between steps, inside the timed region",
+                "l2": "none (back to back)" if args.no_flush else f"{flush_bytes >> 20} MiB fill (1.1x the {l2 >> 20} MiB L2) between steps, inside the timed region",
                 "timing": "K frames enqueued back to back, one CUDA-event pair on the launching stream, max over ranks; the library overlaps the "
                           "light side of frame k+1 with the trace of frame k (see stages_ms for the serialised per-stage times)",
             },

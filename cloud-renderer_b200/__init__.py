@@ -54,7 +54,7 @@ class TraceParams(C.Structure):
 
 class TraceStats(C.Structure):
     _fields_ = [("fragments", u64), ("coneSamples", u64), ("noiseSamples", u64), ("binEntries", u64), ("coneSamplesSkipped", u64), ("filteredFetches", u64),
-                ("bakedFetches", u64)]
+                ("bakedFetches", u64), ("noiseLatticeSteps", u64), ("codeLookups", u64)]
 
 
 class Timings(C.Structure):

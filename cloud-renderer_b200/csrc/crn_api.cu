@@ -1829,6 +1829,7 @@ int crn_get_trace_stats(crn_ctx *c, crn_trace_stats *out) {
     out->binEntries = c->hCursors[5];
     out->coneSamplesSkipped = c->hStats[3];
     out->bakedFetches = c->hStats[5];
+    out->noiseLatticeSteps = c->hStats[6]; out->codeLookups = c->hStats[7];
     out->filteredFetches = c->hStats[4] + c->hStats[5] + c->hStats[2];      // textureLod cone fetches + baked cone fetches + noise taps
     return CRN_OK;
 }

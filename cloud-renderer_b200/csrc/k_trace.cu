@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_kernel(co
     }
     float C[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     float T = 1.0f;
-    unsigned long long nFrag = 0, nCone = 0, nNoise = 0, nSkip = 0, nFetch = 0, nBakedF = 0;
+    unsigned long long nFrag = 0, nCone = 0, nNoise = 0, nSkip = 0, nFetch = 0, nBakedF = 0, nLat = 0, nCode = 0;
 
     const uint32_t cnt = tp.active ? a.tileCnt[tile] : 0;
     const uint32_t off = cnt ? a.tileOff[tile] : 0;
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_kernel(co
                         light += saturatef(ng * 0.5f + 0.5f);
                         tx += dxs; tyy += dys; tz += dzs;
                         ux += dxs; uy += dys; uz += dzs;            // (sic) tex-space delta on the unit-sphere coord
-                        if (kStats) nNoise += tp.p.numOctaves;
+                        if (kStats) { nNoise += tp.p.numOctaves; if (__float_as_int(r1.w) & kRecInLattice) nLat++; }
                     }
                 }
                 const float c = tp.p.minNoiseColor + tp.p.noiseColorScale * light * inv;
@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_kernel(co
                     };
                     for (int b = 0; b < tp.nBaked; b++) bakedStep(b);
                 }
-                if (kStats && shade) nCone += tp.nSteps;
+                if (kStats && shade) { nCone += tp.nSteps; if (a.code && tp.nGroups > 0) nCode++; }
                 if (tp.p.doNoiseSample) { col[0] *= indirect; col[1] *= indirect; col[2] *= indirect; }
                 else col[0] = col[1] = col[2] = col[3] = indirect;
             }
@@ -471,6 +471,8 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_kernel(co
             nSkip += __shfl_down_sync(0xFFFFFFFFu, nSkip, s);
             nFetch += __shfl_down_sync(0xFFFFFFFFu, nFetch, s);
             nBakedF += __shfl_down_sync(0xFFFFFFFFu, nBakedF, s);
+            nLat += __shfl_down_sync(0xFFFFFFFFu, nLat, s);
+            nCode += __shfl_down_sync(0xFFFFFFFFu, nCode, s);
         }
         if (lane == 0) {
             if (nFrag) atomicAdd(&a.stats[0], nFrag);
@@ -479,6 +481,8 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_kernel(co
             if (nSkip) atomicAdd(&a.stats[3], nSkip);
             if (nFetch) atomicAdd(&a.stats[4], nFetch);
             if (nBakedF) atomicAdd(&a.stats[5], nBakedF);
+            if (nLat) atomicAdd(&a.stats[6], nLat);
+            if (nCode) atomicAdd(&a.stats[7], nCode);
         }
     }
 }

@@ -151,6 +151,8 @@ typedef struct crn_trace_stats {
     uint64_t coneSamplesSkipped; /* of coneSamples: proven zero by the empty-space masks, not fetched */
     uint64_t filteredFetches;  /* filtered lookups actually issued: noise taps (bilinear, slice pairs) + 1 or 2 trilinear per fetched textureLod cone sample + bakedFetches */
     uint64_t bakedFetches;     /* of filteredFetches: cone samples served by a baked step texture (one bilinear pass each) */
+    uint64_t noiseLatticeSteps; /* noise march steps of billboards inside the combined-octave noise lattice: the fast trace variant takes 2 lookups there (octave 0 + the pre-summed octaves) instead of numOctaves */
+    uint64_t codeLookups;      /* fragments whose need code the fast trace variant fetches through the texture unit (one point-sampled pass) */
 } crn_trace_stats;
 
 /* Stage timings of the most recent frame, milliseconds, measured with CUDA events on
