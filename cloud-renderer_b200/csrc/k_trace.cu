@@ -189,15 +189,19 @@ __device__ __forceinline__ bool sun_fragment(const TraceParams &tp, const ViewPa
 // kTex = false: explicit filtering (CRN_SAMPLER_EXPLICIT);  kTex = true: texture units (CRN_SAMPLER_TEXTURE)
 constexpr int kFastBaked = 16;        // the fast variant unrolls (and handles at most) this many baked steps (32^3 / 64^3 volumes bake all 16)
 // resident CTAs per SM the kernel is compiled for (register cap = 65536 / 64 / MINB).  Measured at C3 (trace ms):
-// 12: 4.82, 14: 4.73, 16: 4.39, 18: 4.36, 20: 4.52, 24: 4.60 -> 16 (64 registers, no spills in the fast variant)
+// round 1: 12: 4.82, 14: 4.73, 16: 4.39, 18: 4.36, 20: 4.52, 24: 4.60; with the noise lattice: 10: 2.73, 12: 2.74, 16: 2.49,
+// 20: 2.52; final kernel: 14: 2.31, 16: 2.22, 18: 2.19, 20: 2.24 -> 18 (56 registers) for the fast variant, 16 for the generic one
 #ifndef CRN_TRACE_MINB
-#define CRN_TRACE_MINB 16
+#define CRN_TRACE_MINB 18
+#endif
+#ifndef CRN_TRACE_GENERIC_MINB
+#define CRN_TRACE_GENERIC_MINB 16
 #endif
 constexpr int kTraceThreads = 64;     // 2 warp patches per CTA: measured best (256: 5.87 ms, 128: 5.83, 64: 5.79 at C3)
 
 // kGate: the paper variant's `if (sampleColor.a > 0)` on a second (occupancy) chain, CRN_VOLUME_RG8 only
 template <bool kTex, bool kStats, bool kGate>
-__global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_kernel(const __grid_constant__ TraceArgs a, const __grid_constant__ ViewParams cam,
+__global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_GENERIC_MINB) trace_kernel(const __grid_constant__ TraceArgs a, const __grid_constant__ ViewParams cam,
                                                     const __grid_constant__ TraceParams tp, const __grid_constant__ TexSet ts) {
     // a 16x16 tile is 8 warp patches; a CTA carries kTraceThreads/32 of them, so a slow patch holds up fewer warps
     constexpr int kWarps = kTraceThreads / 32, kSplit = 8 / kWarps;
