@@ -304,7 +304,8 @@ class Runner:
         self.r.set_billboards(self.base_pos, self.base_scale)
         t0 = time.perf_counter()
         i = 0
-        while time.perf_counter() - t0 < seconds:
+        # a slab exchange is a collective: every rank must take the SAME number of steps (a clock decides nothing there)
+        while (i < 24) if self.gather else (time.perf_counter() - t0 < seconds):
             self.step(i % len(self.frames), False, asynchronous=True)
             i += 1
             if i % 8 == 0:
@@ -448,7 +449,8 @@ def main():
     real_stdout = os.dup(1)
     os.dup2(2, 1)                      # NCCL / libraries may print to stdout; the JSON line goes to the real one
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=90))    # a hang ends the run, not the GPU budget
     pkg = entry.import_package()
     from cloud_renderer_b200 import scene as sc
     dev = torch.device("cuda", local)
