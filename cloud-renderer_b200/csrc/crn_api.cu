@@ -780,7 +780,8 @@ void build_trace_params(crn_ctx *c, const ViewParams &cam, TraceParams *tp) {
         p.height = 0.5f * (tp->steps[p.first].height + tp->steps[p.first + p.count - 1].height);
     }
     // need-code grid: cells of two voxels; only worth a kernel when some step is still fetched with textureLod
-    tp->codeDim = (c->tp.skipEmptySpace && tp->nGroups > 0 && c->tp.doConeTrace) ? std::max(16, D / 2) : 0;
+    // (at most 128^3 cells: the kernel's cost goes with the cell count, and a 512^3 volume's cones reach half as far in world units)
+    tp->codeDim = (c->tp.skipEmptySpace && tp->nGroups > 0 && c->tp.doConeTrace) ? std::max(16, std::min(D / 2, 128)) : 0;
     tp->codeDimF = (float)tp->codeDim;
     {   // derived constants of the fast variant
         FastConst &f = tp->f;
