@@ -935,6 +935,9 @@ int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
     }
     cudaStream_t st = c->stream, ls = c->lightStream;
     const bool useTex = c->tp.sampler == CRN_SAMPLER_TEXTURE;
+    int ownedTiles = 0;                                // tile rows this context traces (crn_set_tile_row_interleave): only they get CTAs
+    for (int ty = 0; ty < CS(c).binsC.tilesY; ty++)
+        if (ty % std::max(1, c->ilvCount) == c->ilvIndex) ownedTiles += CS(c).binsC.tilesX;
     // ---- trace set-up on the light stream: after this frame's voxelize (same stream), before the next frame's
     if (strict_order(c)) {                             // whatever the caller queued on its stream (slab exchange, crn_finish_mips)
         cudaEventRecord(c->evMainMark, st);
@@ -980,7 +983,7 @@ int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
     cudaStreamWaitEvent(c->copyStream, c->evBin[1], 0);
     cudaMemcpyAsync(c->hCursors + 4, CS(c).binsC.cursors, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->copyStream);
     cudaEventRecord(c->evCur[1], c->copyStream); c->curValid[1] = true;
-    c->launches += launch_tile_order(ax, CS(c).binsC, (uint32_t *)CS(c).tileOrder.p);
+    c->launches += launch_tile_order(ax, CS(c).binsC, (uint32_t *)CS(c).tileOrder.p, c->ilvIndex, std::max(1, c->ilvCount));
     if (c->timingOn) cudaEventRecord(c->evAuxT[2], ax);
     cudaEventRecord(c->evAuxDone, ax);
     // ---- need codes: inside the billboards' world box, which the camera-side prep kernel has just produced
@@ -999,7 +1002,7 @@ int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
                                 (const uint8_t *)c->chainA.p, (const int8_t *)c->noise.p, useTex ? &VS(c).ts : nullptr,
                                 tp.codeDim > 0 ? (const uint8_t *)VS(c).needCode.p : nullptr, (const uint32_t *)CS(c).tileOrder.p,
                                 img.p, format, dStats, tp.segCount > 1 ? (float4 *)c->segPartial.p : nullptr,
-                                tp.segCount > 1 ? (uint32_t *)c->segArrived.p : nullptr);
+                                tp.segCount > 1 ? (uint32_t *)c->segArrived.p : nullptr, ownedTiles);
     cudaEventRecord(VS(c).evFree, st); VS(c).freeValid = true;
     cudaEventRecord(CS(c).evFree, st); CS(c).freeValid = true;
     cudaEventRecord(c->evTraceEnd, st);

@@ -158,7 +158,7 @@ int launch_prep_sort(cudaStream_t st, const float *pos, const float *scale, int 
                      BoardRect *rectC, float *lbSorted, int32_t *drawOrder, void *sortTmp, const NoiseLat *lat = nullptr);
 size_t sort_tmp_bytes(int n);      // sortTmp must hold sort_tmp_bytes(n) + 16 bytes
 int launch_bin(cudaStream_t st, const BoardRect *rects, const int32_t *bounds, int n, int W, int H, Bins &b);
-int launch_tile_order(cudaStream_t st, const Bins &b, uint32_t *order);     // order[tilesX*tilesY]: longest lists first
+int launch_tile_order(cudaStream_t st, const Bins &b, uint32_t *order, int ilvIndex = 0, int ilvCount = 1);     // order[owned tiles]: longest lists first (owned: tile row % ilvCount == ilvIndex)
 const int32_t *sort_tmp_bounds(const void *sortTmp, int n, int pass);
 const uint32_t *sort_tmp_world_box(const void *sortTmp, int n);         // camera pass: sortable bits of the spheres' world bounding box   // rect bounds written by prep_kernel (pass 0 light, 1 camera)
 int launch_voxelize(cudaStream_t st, const ViewParams &light, const VolumeParams &vol, const float nearPlane[3],
@@ -195,7 +195,7 @@ int launch_finish_mips(cudaStream_t st, const VolumeParams &vol, uint8_t *chain,
 int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol, const TraceParams &tp,
                  const BoardRec *recs, const Bins &b, const uint32_t *bits, const uint8_t *chain,
                  const uint32_t *bitsA, const uint8_t *chainA, const int8_t *noise, const TexSet *ts, const uint8_t *needCode, const uint32_t *tileOrder, void *image,
-                 int format, unsigned long long *stats, float4 *segPartial, uint32_t *segArrived);
+                 int format, unsigned long long *stats, float4 *segPartial, uint32_t *segArrived, int ownedTiles);
 int launch_bake_steps(cudaStream_t st, const VolumeParams &vol, const uint32_t *bits, const uint8_t *chain, const BakeTex *tex, int nTex);
 int launch_need_code(cudaStream_t st, const VolumeParams &vol, const TraceParams &tp, const uint32_t *bits, const uint32_t *nz, const uint32_t *worldBox,
                      uint8_t *code, cudaSurfaceObject_t codeSurf);

@@ -199,18 +199,19 @@ __global__ void __launch_bounds__(kBinThreads) bin_kernel(BinArgs a) {
 // Longest-first launch order for the per-tile kernels: tiles are bucketed by log2 of their list length and
 // emitted from the longest bucket down, so the CTAs that walk hundreds of layers start first and the tail of
 // the grid is made of empty tiles (order inside a bucket is arbitrary; results do not depend on it).
-__global__ void __launch_bounds__(1024) tile_hist_kernel(const uint32_t *__restrict__ tileCnt, int tiles, uint32_t *gHist) {
+// (tile rows of another rank of an interleaved trace, crn_set_tile_row_interleave, are left out: the trace grid only holds owned tiles)
+__global__ void __launch_bounds__(1024) tile_hist_kernel(const uint32_t *__restrict__ tileCnt, int tiles, uint32_t *gHist, int tilesX, int ilvIndex, int ilvCount) {
     __shared__ uint32_t sHist[33];
     const int t = threadIdx.x, i = blockIdx.x * 1024 + t;
     if (t < 33) sHist[t] = 0;
     __syncthreads();
-    if (i < tiles) atomicAdd(&sHist[32 - __clz(tileCnt[i])], 1u);            // bucket 0: empty tile
+    if (i < tiles && (i / tilesX) % ilvCount == ilvIndex) atomicAdd(&sHist[32 - __clz(tileCnt[i])], 1u);            // bucket 0: empty tile
     __syncthreads();
     if (t < 33 && sHist[t]) atomicAdd(&gHist[t], sHist[t]);
 }
 
 __global__ void __launch_bounds__(1024) tile_scatter_kernel(const uint32_t *__restrict__ tileCnt, int tiles, const uint32_t *__restrict__ gHist,
-                                                            uint32_t *gCur, uint32_t *order) {
+                                                            uint32_t *gCur, uint32_t *order, int tilesX, int ilvIndex, int ilvCount) {
     __shared__ uint32_t sBase[33];
     const int t = threadIdx.x, i = blockIdx.x * 1024 + t;
     if (t == 0) {
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(1024) tile_scatter_kernel(const uint32_t *__re
     }
     __syncthreads();
     // warp-aggregated claim: one atomic per (warp, bucket) instead of one per tile
-    const int b = i < tiles ? 32 - __clz(tileCnt[i]) : 33;
+    const int b = (i < tiles && (i / tilesX) % ilvCount == ilvIndex) ? 32 - __clz(tileCnt[i]) : 33;
     const uint32_t peers = __match_any_sync(0xFFFFFFFFu, b);
     const int lane = t & 31, leader = __ffs(peers) - 1;
     uint32_t base = 0;
@@ -231,13 +232,13 @@ __global__ void __launch_bounds__(1024) tile_scatter_kernel(const uint32_t *__re
 } // namespace
 
 // scratch: 66 words (histogram + cursors) right after the order array
-int launch_tile_order(cudaStream_t st, const Bins &b, uint32_t *order) {
+int launch_tile_order(cudaStream_t st, const Bins &b, uint32_t *order, int ilvIndex, int ilvCount) {
     const int tiles = b.tilesX * b.tilesY;
     uint32_t *gHist = order + tiles, *gCur = gHist + 33;
     cudaMemsetAsync(gHist, 0, 66 * sizeof(uint32_t), st);
     const int grid = (tiles + 1023) / 1024;
-    tile_hist_kernel<<<grid, 1024, 0, st>>>(b.tileCnt, tiles, gHist);
-    tile_scatter_kernel<<<grid, 1024, 0, st>>>(b.tileCnt, tiles, gHist, gCur, order);
+    tile_hist_kernel<<<grid, 1024, 0, st>>>(b.tileCnt, tiles, gHist, b.tilesX, ilvIndex, ilvCount);
+    tile_scatter_kernel<<<grid, 1024, 0, st>>>(b.tileCnt, tiles, gHist, gCur, order, b.tilesX, ilvIndex, ilvCount);
     return 2;
 }
 

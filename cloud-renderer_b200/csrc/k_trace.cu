@@ -762,7 +762,7 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_fast_kern
 int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol, const TraceParams &tp,
                  const BoardRec *recs, const Bins &b, const uint32_t *bits, const uint8_t *chain,
                  const uint32_t *bitsA, const uint8_t *chainA, const int8_t *noise, const TexSet *ts, const uint8_t *needCode, const uint32_t *tileOrder, void *image,
-                 int format, unsigned long long *stats, float4 *segPartial, uint32_t *segArrived) {
+                 int format, unsigned long long *stats, float4 *segPartial, uint32_t *segArrived, int ownedTiles) {
     TraceArgs a;
     a.vol = vol;
     a.recs = recs;
@@ -780,7 +780,7 @@ int launch_trace(cudaStream_t st, const ViewParams &cam, const VolumeParams &vol
     a.invDim = 1.0f / (float)vol.dim;
     TexSet none{};
     const bool useTex = ts && ts->enabled && tp.p.sampler == CRN_SAMPLER_TEXTURE;
-    const int grid = b.tilesX * b.tilesY * (256 / kTraceThreads);
+    const int grid = ownedTiles * (256 / kTraceThreads);          // the tile order lists owned tiles only
     const bool gate = bitsA != nullptr;
     // the reference's configuration: see trace_fast_kernel
     // The fast variant takes floor() of the noise z coordinate by adding 1.5 * 2^23, valid for |z| < 2^22 texels.  z is
