@@ -96,6 +96,17 @@ class ClockSampler:
         except Exception:
             self.nvml = None
 
+    def resume(self):
+        """sample from now on (the timed legs); pause() suspends between them"""
+        self.active = True
+        if not getattr(self, "started", False):
+            self.started = True
+            self.start()
+
+    def pause(self):
+        self.active = False
+        return None
+
     def start(self):
         if self.nvml:
             self.samples, self.reasons = [], 0
@@ -113,6 +124,9 @@ class ClockSampler:
     def _poll(self):
         n = self.nvml
         while not self.stop_flag:
+            if not getattr(self, "active", True):
+                time.sleep(0.0005)
+                continue
             try:
                 self.samples.append(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
                 self.reasons |= n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
@@ -136,7 +150,8 @@ class ClockSampler:
             except Exception:
                 mx = None
             return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": mx,
-                    "reasons": sorted(k for k, bit in names.items() if self.reasons & bit), "samples": len(self.samples), "source": "nvml, 2 ms poll"}
+                    "reasons": sorted(k for k, bit in names.items() if self.reasons & bit), "samples": len(self.samples),
+                    "source": "nvml, polled from a thread during the two timed legs (resident + e2e)"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -361,7 +376,7 @@ class Runner:
         r.wait_images()
         self.barrier()
         if sampler:
-            sampler.start()
+            sampler.resume()
         l0 = r.launch_count()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
@@ -372,7 +387,7 @@ class Runner:
         r.wait_images()                                    # host leg: every image has landed in host memory; both: pools checked
         b.record(stream)
         self.barrier()
-        clocks = sampler.stop() if sampler else None
+        clocks = sampler.pause() if sampler else None
         ms = self._max_over_ranks(a.elapsed_time(b))
         launches = r.launch_count() - l0
         if self.ctx["world"] > 1:
@@ -469,8 +484,10 @@ def main():
     run = Runner(ctx, cfg, K, Wm, args, mode)
     sampler = ClockSampler(local) if rank == 0 and not os.environ.get("BENCH_NO_SMI") else None
     run.prewarm()
-    ms, launches, clocks = run.timed(False, sampler)
-    ms_e2e, _, _ = run.timed(True)
+    ms, launches, _ = run.timed(False, sampler)
+    ms_e2e, _, clocks = run.timed(True, sampler)         # one sampler over BOTH timed legs (an NVML query takes milliseconds)
+    if sampler:
+        clocks = sampler.stop()
     stage, serial_ms = run.stages()
     st = run.stats()
     D, L, N, Wd, Ht = sc.CONFIGS[cfg]
