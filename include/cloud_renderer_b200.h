@@ -322,7 +322,9 @@ int crn_get_launch_count(crn_ctx *ctx, uint64_t *count);
  * 3 global atomicOr (RED) on a 2 MB set, 4 shared-memory atomicOr, 5 FFMA issue,
  * 6 tex2DLayered bilinear RGBA8 32x32x32 (the noise texture's layout), 7 tex2DLayered bilinear RG16 (baked cone
  * steps), 8 the same RG8, 9 RGBA8 with f16x2 return, 10 tex3D trilinear R16, 11/12 tex3DLod on a mipmapped R8 256^3
- * at LOD 4.5 / 2.5 (mip-linear: four bilinear passes), 13 tex2DLayered bilinear RG16F. */
+ * at LOD 4.5 / 2.5 (mip-linear: four bilinear passes), 13 tex2DLayered bilinear RG16F, 14 tex3D with z on slice centres,
+ * 15-18 tex2DLayered bilinear RGBA16_SNORM / RGBA8_SNORM 161x161x160 and tex3D RG16_SNORM 161^3 with strided (L1-missing)
+ * coordinates: the combined-octave noise lattice's format and access pattern. */
 int crn_microbench(int device, int32_t which, double *giga_ops_per_s);
 
 /* library identification: "cloud-renderer_b200 <version> sm_100a" */
