@@ -840,3 +840,83 @@ def test_fast_generic_baked_and_textureLod_paths_agree(name, pkg, scenes, orc):
     print(f"{name}: fast vs generic {pf:.1f} dB, baked vs textureLod {pb:.1f} dB, lattice vs per-octave {pl:.1f} dB")
     assert pf >= 80.0 and pb >= 60.0 and pl >= 80.0
     assert not np.array_equal(imgs["lattice"], imgs["fast"]), "the lattice route was not taken"
+
+
+def _lattice_steps(r, pkg):
+    """march steps the last frame took from the combined-octave noise lattice (crn_trace_stats)"""
+    r.set_stats(True)
+    r.cone_trace(fmt=pkg.IMAGE_RGBA32F)
+    st = r.trace_stats()
+    r.set_stats(False)
+    return st.noiseLatticeSteps, st.noiseSamples
+
+
+@pytest.mark.parametrize("case", ["default", "wind_time", "even_freq", "wind_y", "five_freq"])
+def test_noise_lattice_qualification(case, pkg, scenes, orc):
+    """k_noiselat.cu pre-sums octaves 1..3 only when that is exact: freqStep an odd integer and no wind offset on octaves 1
+    and 2.  Octave 0's own offset (windVel.x * runTime) never disqualifies it: that octave stays a lookup of its own.  Whatever
+    the route, the image meets the oracle."""
+    s = steady_state(scenes.make_scene("small"), orc)
+    s.tp.sampler = pkg.SAMPLER_TEXTURE
+    expect = True
+    if case == "wind_time":
+        s.tp.runTime = 7.3                                  # octave 0 shifted by 0.073 uv = 63 lattice cells and a fraction
+    elif case == "even_freq":
+        s.tp.freqStep, expect = 2.0, False                  # octave-1 texel centres fall between octave-3 ones
+    elif case == "wind_y":
+        s.tp.windVel[1], s.tp.runTime, expect = 0.02, 3.0, False     # octaveOffsets[1] != 0
+    elif case == "five_freq":
+        s.tp.freqStep = 5.0                                 # odd: qualifies (K = 32 * 125 lattice units per uv unit) unless the window is too large
+        expect = None
+    r = pkg.Renderer(0)
+    r.set_scene(s); r.voxelize()
+    img = r.cone_trace(fmt=pkg.IMAGE_RGBA32F).copy()
+    lat, noise = _lattice_steps(r, pkg)
+    r.close()
+    _, _, l0 = orc.voxelize(s, want_posmap=False)
+    ref, _, _ = orc.cone_trace(s, orc.mips(l0, s.vol.levels), want_u8=False)
+    p = psnr(img, ref)
+    print(f"{case}: {lat} of {noise // 4} march steps from the lattice, PSNR {p:.1f} dB, max err {np.abs(img - ref).max():.2e}")
+    assert p >= 45.0
+    if expect is True:       # (the reference-radii scene's largest billboards reach past the 512 MB window cap: most, not all)
+        assert lat * 4 > 0.5 * noise, "most billboards of this scene lie inside the lattice window"
+    elif expect is False:
+        assert lat == 0, "the lattice must not be used for these parameters"
+
+
+def test_noise_lattice_window_fallback(pkg, scenes, orc):
+    """Billboards whose noise march leaves the baked window take the per-octave lookups, the others the lattice, inside ONE
+    frame: offsets three times the volume's half extent (the window is capped at 2.5x), device-resident source (the host
+    does not know the extent: volume box + 20 %).  Both mixes meet the oracle and each other."""
+    import os
+    s = scenes.make_scene("small")
+    s.board_pos = (s.board_pos * 3.0).astype(np.float32)
+    s = steady_state(s, orc)
+    s.tp.sampler = pkg.SAMPLER_TEXTURE
+    _, _, l0 = orc.voxelize(s, want_posmap=False)
+    ref, _, _ = orc.cone_trace(s, orc.mips(l0, s.vol.levels), want_u8=False)
+    imgs, fracs = {}, {}
+    try:
+        for route in ("host", "device", "off"):
+            if route == "off":
+                os.environ["CRN_NO_LATTICE"] = "1"
+            r = pkg.Renderer(0)
+            r.set_scene(s)
+            if route == "device":
+                import torch
+                dp, ds = torch.from_numpy(s.board_pos).cuda(), torch.from_numpy(s.board_scale).cuda()
+                r.set_billboards(dp, ds)
+                torch.cuda.synchronize()
+            r.voxelize()
+            imgs[route] = r.cone_trace(fmt=pkg.IMAGE_RGBA32F).copy()
+            lat, noise = _lattice_steps(r, pkg)
+            fracs[route] = lat * 4 / max(noise, 1)
+            r.close()
+    finally:
+        os.environ.pop("CRN_NO_LATTICE", None)
+    for k, im in imgs.items():
+        p = psnr(im, ref)
+        print(f"window fallback / {k}: {100 * fracs[k]:.1f} % of the march steps from the lattice, PSNR {p:.1f} dB")
+        assert p >= 45.0
+    assert fracs["off"] == 0.0 and 0.0 < fracs["device"] < 1.0 and fracs["device"] <= fracs["host"]
+    assert psnr(imgs["host"], imgs["off"]) >= 80.0 and psnr(imgs["device"], imgs["off"]) >= 80.0
