@@ -1,7 +1,7 @@
 """Small frames of every code path (both samplers, all volume formats, a Z-slab + crn_finish_mips, device-side
 generation + animation, pipelined frames) for
     compute-sanitizer --tool memcheck|racecheck python profiles/sanitizer_check.py
-Round 1 result on B200: memcheck 0 errors, racecheck 0 hazards (profiles/r01_sanitizer.txt)."""
+Round 1 result on B200: memcheck 0 errors, racecheck 0 hazards (profiles/r01_sanitizer.txt); round 2: profiles/r02_sanitizer.txt."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -18,6 +18,15 @@ for name, fmt in (("tiny", 0), ("small", 0), ("small", 1)):
     r.set_z_slab(0, 16); r.voxelize(); r.finish_mips(min(5, s.vol.levels)) if s.vol.levels > 5 else None
     print(name, fmt, img.mean())
     r.close()
+# 128^3 volume, fill radii: fine cone steps + need-code texture + baked steps + noise lattice + segmented tile lists
+s = sc.make_scene("C2", boards=600, size=(640, 360))
+s.tp.sampler = 1
+r = pkg.Renderer(0)
+r.set_scene(s)
+for k in range(2):
+    r.voxelize(); img = r.cone_trace()
+print("C2crop", img.mean())
+r.close()
 # paper variant (interior march, second chain, gated trace) and device-side generation / animation, pipelined frames
 s = sc.make_scene("small")
 s.vol.format = 2
