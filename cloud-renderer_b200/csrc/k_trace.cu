@@ -537,15 +537,18 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_fast_kern
     // 2x2-pixel quads: the texture unit works on groups of four consecutive lanes, and a disc edge leaves fewer
     // partially filled 2x2 blocks than 4x1 strips (measured at C3: trace 3.35 -> 3.30 ms)
     const int lx = (lane & 1) | ((lane >> 1) & 6), ly = ((lane >> 1) & 1) | ((lane >> 3) & 2);
-    const int px = tx * kTile + (warp & 1) * 8 + lx;
-    const int py = ty * kTile + (warp >> 1) * 4 + ly;
-    if (tp.ilvCount > 1 && (ty % tp.ilvCount) != tp.ilvIndex) return;
-    const bool valid = px < cam.W && py < cam.H && py >= tp.row0 && py < tp.row1;
-    if (!kSeg && __all_sync(0xFFFFFFFFu, !valid)) return;           // (segmented: every thread stays for the barrier below)
-
-    const float ndcx = ((float)px + 0.5f) / (float)cam.W * 2.0f - 1.0f;
-    const float ndcy = ((float)py + 0.5f) / (float)cam.H * 2.0f - 1.0f;
-    const float xs = ndcx * tp.f.invP0, ys = ndcy * tp.f.invP5;        // view-space x, y of the pixel ray at unit depth
+    // (the pixel's coordinates are recomputed after the list walk: only xs, ys and `valid` stay live through it)
+    const int pxOf = (warp & 1) * 8 + lx, pyOf = (warp >> 1) * 4 + ly;
+    bool valid;
+    float xs, ys;                                                       // view-space x, y of the pixel ray at unit depth
+    {
+        const int px = tx * kTile + pxOf, py = ty * kTile + pyOf;
+        if (tp.ilvCount > 1 && (ty % tp.ilvCount) != tp.ilvIndex) return;
+        valid = px < cam.W && py < cam.H && py >= tp.row0 && py < tp.row1;
+        if (!kSeg && __all_sync(0xFFFFFFFFu, !valid)) return;       // (segmented: every thread stays for the barrier below)
+        xs = (((float)px + 0.5f) / (float)cam.W * 2.0f - 1.0f) * tp.f.invP0;
+        ys = (((float)py + 0.5f) / (float)cam.H * 2.0f - 1.0f) * tp.f.invP5;
+    }
 
     float Cg = 0.0f, Ca = 0.0f, T = 1.0f;
     const uint32_t cnt = a.tileCnt[tile];
@@ -558,10 +561,10 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_fast_kern
     const uint32_t eBegin = kSeg ? (uint32_t)((uint64_t)cnt * seg / nSeg) : 0u;
     const uint32_t eEnd = kSeg ? (uint32_t)((uint64_t)cnt * (seg + 1) / nSeg) : cnt;
 
-    for (uint32_t e = eBegin; e < eEnd; e++) {
+    for (const uint32_t *lp = list + eBegin, *const le = list + eEnd; lp < le; lp++) {
         const bool live = valid && T > cutoff;
         if (__all_sync(0xFFFFFFFFu, !live)) break;                      // early ray termination, whole patch
-        const uint32_t k = __ldg(list + e);
+        const uint32_t k = __ldg(lp);
         const float4 r0 = __ldg(reinterpret_cast<const float4 *>(&a.recs[k].cx));
         const float4 r1 = __ldg(reinterpret_cast<const float4 *>(&a.recs[k].xv));
         const float radius = r0.w;
@@ -732,6 +735,9 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_fast_kern
     }
 
     if (valid) {
+        const int px = (tile % a.tilesX) * kTile + pxOf, py = (tile / a.tilesX) * kTile + pyOf;
+        const float ndcx = ((float)px + 0.5f) / (float)cam.W * 2.0f - 1.0f;
+        const float ndcy = ((float)py + 0.5f) / (float)cam.H * 2.0f - 1.0f;
         // background = clear colour, then the sun pass blended over it
         float bg[4] = {tp.bg[0], tp.bg[1], tp.bg[2], tp.bg[3]};
         if (tp.p.drawSun) {
