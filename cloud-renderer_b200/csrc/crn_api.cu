@@ -813,7 +813,9 @@ int ensure_noise_lattice(crn_ctx *c, const ViewParams &cam, TraceParams &tp) {
     NoiseLat &L = tp.lat;
     L.on = 0;
     const crn_trace_params &p = c->tp;
-    if (c->noLattice || p.sampler != CRN_SAMPLER_TEXTURE || !p.doNoiseSample || p.numOctaves != 4 || c->noiseDim <= 0) return CRN_OK;
+    // (only the fast trace variant reads it: the same conditions as launch_trace's choice, k_trace.cu)
+    if (c->noLattice || p.sampler != CRN_SAMPLER_TEXTURE || !p.doNoiseSample || p.numOctaves != 4 || c->noiseDim != 32 || !p.doConeTrace || p.showQuad ||
+        p.quantizeFramebuffer || cam.ortho || c->vol.format == CRN_VOLUME_RG8 || getenv("CRN_NO_FAST")) return CRN_OK;   // (stats frames keep it: they report what the fast variant does)
     const float fs = p.freqStep;
     if (!(fs >= 1.0f && fs <= 9.0f) || fs != floorf(fs) || ((int)fs & 1) == 0) return CRN_OK;
     if (!(p.adjustSize > 0.0f) || tp.octaveOffsets[1] != 0.0f || tp.octaveOffsets[2] != 0.0f) return CRN_OK;
