@@ -926,8 +926,11 @@ int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
         // measured trace ms at 1 / 2 / 4 segments: C1 (3600 tiles) 0.244 / 0.188 / 0.165, C2 (8160) 0.807 / 0.715 / 0.632,
         // C3 (32400) 3.015 / 2.955 / 3.086, C4 (129600) 9.46 / 10.12 / 10.65; a rank of an interleaved trace owns 1/count of the tiles
         const size_t active = tiles / (size_t)std::max(1, c->ilvCount);
-        // final kernel: C1 0.280 / 0.185 / 0.143, C2 0.669 / 0.504 / 0.473, C3 2.173 / 2.180 / 2.324
-        tp.segCount = active <= 16384 ? 4 : active <= 24576 ? 2 : 1;
+        // final kernel: C1 0.280 / 0.185 / 0.143, C2 0.669 / 0.504 / 0.473, C3 2.173 / 2.180 / 2.324.  Stand-alone, C3 does not care
+        // between 1 and 2 — but PIPELINED frames do: with the lists cut in two the CTAs live half as long, the high-priority
+        // set-up kernels and the read-back of the neighbouring frames get their slots sooner: 380 -> 392 frames/s resident,
+        // 347 -> 388 end to end (bench.py, segments 1 / 2 / 3 / 4: 380 / 392 / 383 / 377 and 347 / 388 / 381 / 372)
+        tp.segCount = active <= 16384 ? 4 : active <= 65536 ? 2 : 1;
         if (c->segOverride >= 1) tp.segCount = std::min(c->segOverride, 16);
         tp.segMin = 6;
         if (tp.segCount > 1) {
