@@ -930,7 +930,8 @@ int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
         // between 1 and 2 — but PIPELINED frames do: with the lists cut in two the CTAs live half as long, the high-priority
         // set-up kernels and the read-back of the neighbouring frames get their slots sooner: 380 -> 392 frames/s resident,
         // 347 -> 388 end to end (bench.py, segments 1 / 2 / 3 / 4: 380 / 392 / 383 / 377 and 347 / 388 / 381 / 372)
-        tp.segCount = active <= 16384 ? 4 : active <= 65536 ? 2 : 1;
+        // C2 pipelined: 2 / 4 / 6 segments 1685 / 1631 / 1531 frames/s; C1: 2 / 4 / 8 -> 3885 / 4564 / 3674; C4 (129600 tiles): 1 / 2 -> 128.5 / 122.9
+        tp.segCount = (active <= 4096 || (c->ilvCount > 1 && active <= 16384)) ? 4 : active <= 65536 ? 2 : 1;
         if (c->segOverride >= 1) tp.segCount = std::min(c->segOverride, 16);
         tp.segMin = 6;
         if (tp.segCount > 1) {
