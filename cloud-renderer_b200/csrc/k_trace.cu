@@ -197,7 +197,10 @@ constexpr int kFastBaked = 16;        // the fast variant unrolls (and handles a
 #ifndef CRN_TRACE_GENERIC_MINB
 #define CRN_TRACE_GENERIC_MINB 16
 #endif
-constexpr int kTraceThreads = 64;     // 2 warp patches per CTA: measured best (256: 5.87 ms, 128: 5.83, 64: 5.79 at C3)
+#ifndef CRN_TRACE_THREADS
+#define CRN_TRACE_THREADS 64
+#endif
+constexpr int kTraceThreads = CRN_TRACE_THREADS;     // 2 warp patches per CTA: measured best (256: 5.87 ms, 128: 5.83, 64: 5.79 at C3)
 
 // kGate: the paper variant's `if (sampleColor.a > 0)` on a second (occupancy) chain, CRN_VOLUME_RG8 only
 template <bool kTex, bool kStats, bool kGate>
