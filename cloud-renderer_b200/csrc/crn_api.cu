@@ -933,7 +933,7 @@ int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
         // C2 pipelined: 2 / 4 / 6 segments 1685 / 1631 / 1531 frames/s; C1: 2 / 4 / 8 -> 3885 / 4564 / 3674; C4 (129600 tiles): 1 / 2 -> 128.5 / 122.9
         tp.segCount = (active <= 4096 || (c->ilvCount > 1 && active <= 16384)) ? 4 : active <= 65536 ? 2 : 1;
         if (c->segOverride >= 1) tp.segCount = std::min(c->segOverride, 16);
-        tp.segMin = 6;
+        tp.segMin = 6; tp.segMax = 1024;
         if (tp.segCount > 1) {
             if ((r = reserve(c, c->segPartial, tiles * tp.segCount * 256 * sizeof(float4)))) return r;
             if ((r = reserve(c, c->segArrived, tiles * 4 * sizeof(uint32_t)))) return r;      // zeroed by reserve, re-armed by the kernel

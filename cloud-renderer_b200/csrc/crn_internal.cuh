@@ -128,7 +128,7 @@ struct TraceParams {
     int32_t noiseMask;                // noiseDim - 1 if noiseDim is a power of two, else -1
     int32_t nFine;                    // steps[0..nFine) are fetched with textureLod (grouped for the empty-space test)
     int32_t nBaked;                   // baked[0..nBaked) are the remaining steps, in step order
-    int32_t segCount, segMin;         // small frames: tile lists of >= segCount * segMin entries are cut into segCount depth segments (1: off)
+    int32_t segCount, segMin, segMax; // tile lists of segCount * segMin .. segMax entries are cut into segCount depth segments (1: off)
     int32_t codeDim;                  // cells per axis of the need-code grid (0: no empty-space skipping)
     float codeDimF;
     FastConst f;

@@ -559,7 +559,9 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_MINB) trace_fast_kern
     const float cutoff = tp.p.transmittanceCutoff;
     const float rx = cam.nrm[0], ry = cam.nrm[1], rz = cam.nrm[2];     // viewRay (res/conetrace_frag.glsl:138)
     // this CTA's share of the list: short lists are not cut (segment 0 takes them whole, the other CTAs leave)
-    const int nSeg = (kSeg && cnt >= (uint32_t)(S * tp.segMin)) ? S : 1;
+    // ... and neither are very long ones: hundreds of layers of large billboards end in the early ray termination, which a
+    // later segment cannot see (reference radii at C3: ~4700 entries per tile, 7.8 ms uncut against 12.3 ms cut in two)
+    const int nSeg = (kSeg && cnt >= (uint32_t)(S * tp.segMin) && cnt <= (uint32_t)tp.segMax) ? S : 1;
     if (kSeg && seg >= nSeg) return;
     const uint32_t eBegin = kSeg ? (uint32_t)((uint64_t)cnt * seg / nSeg) : 0u;
     const uint32_t eEnd = kSeg ? (uint32_t)((uint64_t)cnt * (seg + 1) / nSeg) : cnt;
