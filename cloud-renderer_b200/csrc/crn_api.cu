@@ -212,6 +212,7 @@ struct crn_ctx {
     int nBakePlan = 0;
     DevBuf segPartial, segArrived;       // small frames: per-segment partial composites of the cut tile lists (k_trace.cu)
     int segOverride = -1;                // CRN_TRACE_SEGMENTS=n: force the segment count (experiments)
+    int segMaxOverride = -1;             // CRN_TRACE_SEGMAX=n: longest tile list that is still cut (experiments)
     uint64_t volumeGen = 0;              // bumped whenever the chain changes (voxelize, finish_mips)
     uint64_t boardsGen = 0;              // bumped whenever the billboard arrays change
     bool lastTraceExplicit = false;      // the last trace read the bits / the chain directly (explicit sampler)
@@ -932,8 +933,12 @@ int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
         // 347 -> 388 end to end (bench.py, segments 1 / 2 / 3 / 4: 380 / 392 / 383 / 377 and 347 / 388 / 381 / 372)
         // C2 pipelined: 2 / 4 / 6 segments 1685 / 1631 / 1531 frames/s; C1: 2 / 4 / 8 -> 3885 / 4564 / 3674; C4 (129600 tiles): 1 / 2 -> 128.5 / 122.9
         tp.segCount = (active <= 4096 || (c->ilvCount > 1 && active <= 16384)) ? 4 : active <= 65536 ? 2 : 1;
+        // Frames whose lists are very long on average (the camera-side bin entries of the last frame whose cursors have been
+        // read back: reference radii at C3 hold 430 entries per tile of the WHOLE frame, the fill radii 23) gain nothing from
+        // segments — their lists are over the cut limit anyway — and pay for the doubled grid: 90 against 96 frames/s
+        if (c->hCursors && (size_t)c->hCursors[5] > 128 * tiles) tp.segCount = 1;
         if (c->segOverride >= 1) tp.segCount = std::min(c->segOverride, 16);
-        tp.segMin = 6; tp.segMax = 1024;
+        tp.segMin = 6; tp.segMax = c->segMaxOverride > 0 ? c->segMaxOverride : 1024;
         if (tp.segCount > 1) {
             if ((r = reserve(c, c->segPartial, tiles * tp.segCount * 256 * sizeof(float4)))) return r;
             if ((r = reserve(c, c->segArrived, tiles * 4 * sizeof(uint32_t)))) return r;      // zeroed by reserve, re-armed by the kernel
@@ -1096,6 +1101,7 @@ int crn_create(int device, void *stream, crn_ctx **out) {
     if (const char *nb = getenv("CRN_NO_BAKE")) c->noBake = atoi(nb) != 0;
     if (const char *nl = getenv("CRN_NO_LATTICE")) c->noLattice = atoi(nl) != 0;
     if (const char *sg = getenv("CRN_TRACE_SEGMENTS")) c->segOverride = atoi(sg);
+    if (const char *sm = getenv("CRN_TRACE_SEGMAX")) c->segMaxOverride = atoi(sm);
     if (const char *pm = getenv("CRN_BIN_POOL_MIN")) { const long v = atol(pm); if (v > 0) c->poolMin = (size_t)v; }
     if ((e = cudaGetLastError()) != cudaSuccess) {
         crn_destroy(c);
