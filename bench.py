@@ -465,7 +465,7 @@ def main():
     os.dup2(2, 1)                      # NCCL / libraries may print to stdout; the JSON line goes to the real one
     if world > 1:
         import datetime
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=90))    # a hang ends the run, not the GPU budget
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=300))   # a hang ends the run within minutes (the rendezvous of cold processes shares this limit)
     pkg = entry.import_package()
     from cloud_renderer_b200 import scene as sc
     dev = torch.device("cuda", local)
