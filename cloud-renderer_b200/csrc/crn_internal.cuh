@@ -15,7 +15,10 @@ namespace crn {
 // geometry of the two tilings
 // ----------------------------------------------------------------------------------------
 constexpr int kTile = 16;            // fine tile edge in pixels: one 256-thread CTA, 8 warps of 8x4
-constexpr int kCoarse = 4;           // coarse tile = kCoarse x kCoarse fine tiles (64 px)
+#ifndef CRN_COARSE
+#define CRN_COARSE 4
+#endif
+constexpr int kCoarse = CRN_COARSE;  // coarse tile = kCoarse x kCoarse fine tiles (64 px)
 constexpr int kMaxConeSteps = 128;   // vctSteps upper bound (reference UI slider tops out far lower)
 constexpr int kMaxLevels = 16;
 constexpr int kMaxOctaves = 8;
