@@ -62,13 +62,13 @@ __device__ __forceinline__ NodeAxis node_axis(int k, int shift, int N) {
 }
 
 // kFmt: 0 = R8 chain level (>= 1), 1 = R32F chain level (>= 1), 2 = the 1-bit level 0
+// the bilinear (x, y) part of a node's trilinear sample on texel plane z: four loads
 template <int kFmt>
-__device__ __forceinline__ float node_sample(const uint32_t *__restrict__ bits, const uint8_t *__restrict__ lvl, int N, int shift, int kx, int ky, int kz) {
-    const NodeAxis X = node_axis(kx, shift, N), Y = node_axis(ky, shift, N), Z = node_axis(kz, shift, N);
-    float c[8];
+__device__ __forceinline__ float plane_sample(const uint32_t *__restrict__ bits, const uint8_t *__restrict__ lvl, int N, const NodeAxis &X, const NodeAxis &Y, int z) {
+    float c[4];
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const uint32_t row = (uint32_t)(((q & 2) ? Z.i1 : Z.i0) * N + ((q & 1) ? Y.i1 : Y.i0));
+    for (int q = 0; q < 2; q++) {
+        const uint32_t row = (uint32_t)(z * N + (q ? Y.i1 : Y.i0));
         if (kFmt == 2) {
             const uint32_t *r = bits + row * (uint32_t)(N >> 5);
             c[2 * q] = (float)((__ldg(r + (X.i0 >> 5)) >> (X.i0 & 31)) & 1u);
@@ -81,17 +81,39 @@ __device__ __forceinline__ float node_sample(const uint32_t *__restrict__ bits, 
             c[2 * q] = (float)__ldg(r + X.i0); c[2 * q + 1] = (float)__ldg(r + X.i1);
         }
     }
-    const float x00 = fmaf(X.w, c[1] - c[0], c[0]), x10 = fmaf(X.w, c[3] - c[2], c[2]);
-    const float x01 = fmaf(X.w, c[5] - c[4], c[4]), x11 = fmaf(X.w, c[7] - c[6], c[6]);
-    const float y0 = fmaf(Y.w, x10 - x00, x00), y1 = fmaf(Y.w, x11 - x01, x01);
-    const float v = fmaf(Z.w, y1 - y0, y0);
-    return kFmt == 0 ? v * (1.0f / 255.0f) : v;
+    const float x0 = fmaf(X.w, c[1] - c[0], c[0]), x1 = fmaf(X.w, c[3] - c[2], c[2]);
+    return fmaf(Y.w, x1 - x0, x0);
 }
 
-// One thread per (x, y) and run of kBakeRun layers (kBakeRun + 1 node evaluations for kBakeRun texels).  Layer k holds
-// (B(x,y,k), B(x,y,k+1) - B(x,y,k)) as SNORM16 codes: the trace kernel's z blend is one FMA, and because the step is the
-// difference of the quantised planes, layer k + its step is exactly layer k+1.
-constexpr int kBakeRun = 4;
+// A column of nodes (x, y, k0..) of one level: consecutive nodes share their texel planes (a new plane every 2 nodes of the
+// lower level, every 4 of the upper one), so the two planes of the current node are kept and only a new one is fetched.
+template <int kFmt>
+struct ColumnSampler {
+    const uint32_t *bits;
+    const uint8_t *lvl;
+    int N, shift;
+    NodeAxis X, Y;
+    int z0 = -1, z1 = -1;
+    float p0 = 0.0f, p1 = 0.0f;
+    __device__ __forceinline__ float at(int k) {
+        const NodeAxis Z = node_axis(k, shift, N);
+        if (Z.i0 != z0) {
+            if (Z.i0 == z1) { z0 = z1; p0 = p1; }
+            else { z0 = Z.i0; p0 = plane_sample<kFmt>(bits, lvl, N, X, Y, z0); }
+        }
+        if (Z.i1 != z1) {
+            z1 = Z.i1;
+            p1 = z1 == z0 ? p0 : plane_sample<kFmt>(bits, lvl, N, X, Y, z1);
+        }
+        const float v = fmaf(Z.w, p1 - p0, p0);
+        return kFmt == 0 ? v * (1.0f / 255.0f) : v;
+    }
+};
+
+// One thread per (x, y) and run of kBakeRun layers (kBakeRun + 1 node evaluations for kBakeRun texels, ~4 loads per
+// layer).  Layer k holds (B(x,y,k), B(x,y,k+1) - B(x,y,k)) as SNORM16 codes: the trace kernel's z blend is one FMA, and
+// because the step is the difference of the quantised planes, layer k + its step is exactly layer k+1.
+constexpr int kBakeRun = 16;
 template <bool kF32>
 __global__ void __launch_bounds__(256) bake_steps_kernel(const __grid_constant__ BakeArgs a) {
     const BakeGroup &g = a.g[blockIdx.z];
@@ -101,16 +123,17 @@ __global__ void __launch_bounds__(256) bake_steps_kernel(const __grid_constant__
     const int yr = blockIdx.y * 8 + (threadIdx.x >> 5);              // y + n * run
     if (x >= n || yr >= n * runs) return;
     const int y = yr % n, k0 = (yr / n) * kBakeRun;
+    ColumnSampler<2> lo0{a.bits, nullptr, g.NL, 1, node_axis(x, 1, g.NL), node_axis(y, 1, g.NL)};
+    ColumnSampler<kF32 ? 1 : 0> lo{nullptr, a.chain + g.offL, g.NL, 1, node_axis(x, 1, g.NL), node_axis(y, 1, g.NL)};
+    ColumnSampler<kF32 ? 1 : 0> up{nullptr, a.chain + g.offU, max(g.NU, 1), 2, node_axis(x, 2, max(g.NU, 1)), node_axis(y, 2, max(g.NU, 1))};
     int prev[kMaxBakedTex];
     for (int k = k0; k <= min(k0 + kBakeRun, n - 1); k++) {
-        float lo, hi = 0.0f;
-        if (g.level0 == 0) lo = node_sample<2>(a.bits, nullptr, g.NL, 1, x, y, k);
-        else lo = node_sample<kF32 ? 1 : 0>(nullptr, a.chain + g.offL, g.NL, 1, x, y, k);
-        if (g.NU) hi = node_sample<kF32 ? 1 : 0>(nullptr, a.chain + g.offU, g.NU, 2, x, y, k);
+        const float vlo = g.level0 == 0 ? lo0.at(k) : lo.at(k);
+        const float vhi = g.NU ? up.at(k) : 0.0f;
 #pragma unroll
         for (int t = 0; t < kMaxBakedTex; t++) {
             if (t < g.count) {
-                const float v = g.frac[t] > 0.0f ? fmaf(g.frac[t], hi - lo, lo) : lo;
+                const float v = g.frac[t] > 0.0f ? fmaf(g.frac[t], vhi - vlo, vlo) : vlo;
                 const int q = (int)__float2uint_rn(__saturatef(v) * 32767.0f);
                 if (k > k0) surf2DLayeredwrite(make_short2((short)prev[t], (short)(q - prev[t])), g.surf[t], x * 4, y, k - 1);
                 prev[t] = q;
