@@ -198,14 +198,16 @@ __device__ __forceinline__ bool warp_any_set(const uint32_t *__restrict__ m, con
     const int zlo = __reduce_min_sync(full, live ? b.lo[2] : 0x7FFFFFFF), zhi = __reduce_max_sync(full, live ? b.hi[2] : -1);
     const int wlo = __reduce_min_sync(full, live ? b.lo[0] >> 5 : 0x7FFFFFFF), whi = __reduce_max_sync(full, live ? b.hi[0] >> 5 : -1);
     if (yhi < ylo) return false;                                      // no live lane
-    const int ny = yhi - ylo + 1, rows = ny * (zhi - zlo + 1);
+    // lanes as an 8 (y) x 4 (z) patch of rows, stepped over the range (no integer division: the kernel is issue-bound)
+    const int ly = lane & 7, lz = lane >> 3;
     bool any = false;
     for (int w = wlo; w <= whi; w++) {
         uint32_t acc = 0;
-        for (int r = lane; r < rows; r += 32) {
-            const int y = ylo + r % ny, z = zlo + r / ny;
-            acc |= __ldg(m + (uint32_t)(z * L.size + y) * (uint32_t)L.wpr + w);
-        }
+        for (int zb = zlo; zb <= zhi; zb += 4)
+            for (int yb = ylo; yb <= yhi; yb += 8) {
+                const int y = yb + ly, z = zb + lz;
+                if (y <= yhi && z <= zhi) acc |= __ldg(m + (uint32_t)(z * L.size + y) * (uint32_t)L.wpr + w);
+            }
         acc = __reduce_or_sync(full, acc);
         if (live && w >= (b.lo[0] >> 5) && w <= (b.hi[0] >> 5)) {
             uint32_t sel = full;
