@@ -932,7 +932,8 @@ int enqueue_trace(crn_ctx *c, int format, DevBuf *target = nullptr) {
         // set-up kernels and the read-back of the neighbouring frames get their slots sooner: 380 -> 392 frames/s resident,
         // 347 -> 388 end to end (bench.py, segments 1 / 2 / 3 / 4: 380 / 392 / 383 / 377 and 347 / 388 / 381 / 372)
         // C2 pipelined: 2 / 4 / 6 segments 1685 / 1631 / 1531 frames/s; C1: 2 / 4 / 8 -> 3885 / 4564 / 3674; C4 (129600 tiles): 1 / 2 -> 128.5 / 122.9
-        tp.segCount = (active <= 4096 || (c->ilvCount > 1 && active <= 16384)) ? 4 : active <= 65536 ? 2 : 1;
+        // (C4 on two GPUs, 64800 owned tiles: 1 / 2 segments -> 228 / 220 frames/s)
+        tp.segCount = (active <= 4096 || (c->ilvCount > 1 && active <= 16384)) ? 4 : active <= 49152 ? 2 : 1;
         // Frames whose lists are very long on average (the camera-side bin entries of the last frame whose cursors have been
         // read back: reference radii at C3 hold 430 entries per tile of the WHOLE frame, the fill radii 23) gain nothing from
         // segments — their lists are over the cut limit anyway — and pay for the doubled grid: 90 against 96 frames/s
