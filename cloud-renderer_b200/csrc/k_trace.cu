@@ -30,7 +30,8 @@
 // precomputed on the host (TraceParams::steps).  With the texture sampler the coarse steps read
 // per-frame baked step textures (k_conebake.cu: one bilinear pass + a z blend instead of a mip-linear
 // 3D fetch, exact); the remaining fine steps are grouped, and a group whose bit in the need-code grid
-// (k_conebake.cu, from the conservative empty-space masks of k_skipmask.cu) is clear is skipped exactly.
+// (k_conebake.cu: the group's texel footprint against the non-zero bit volumes of k_skipmask.cu) is clear is skipped
+// exactly.  noise3D's octaves 1..3 come pre-summed from the combined-octave lattice (k_noiselat.cu, exact) in the fast variant.
 #include "crn_internal.cuh"
 
 #include <cstdlib>
@@ -504,8 +505,15 @@ __global__ void __launch_bounds__(kTraceThreads, CRN_TRACE_GENERIC_MINB) trace_k
 //   * colour is grey in every mode of conetrace_frag.glsl, so ONE colour accumulator + alpha;
 //   * the noise march runs along the view ray, a kernel constant perpendicular to the billboard plane:
 //     texture coordinate = QA + s1 * ray, |unitTex|^2 = |o|^2 / r^2 + s2^2 with two running scalars;
-//   * background (clear colour + sun disc) is evaluated after the list walk, not carried through it.
-// Same fragments, same lookups, same order of composition as the generic kernel.
+//   * background (clear colour + sun disc) is evaluated after the list walk, not carried through it;
+//   * billboards flagged by the prep kernel (k_prep_sort.cu: the whole march stays inside the lattice window) take TWO
+//     lookups per march step — octave 0 from the noise texture's RGBA16 copy, octaves 1..3 from the combined-octave lattice
+//     (k_noiselat.cu) — with all six lookup coordinates as running sums; the others one lookup per octave;
+//   * every slice-pair texel holds (plane, step to the next plane), so a z blend is one FMA per channel, and the noise
+//     value is carried at half scale (the textures store v / 2), which turns saturate(ng * 0.5 + 0.5) into one FADD.SAT;
+//   * the need code comes from one point-sampled fetch of a 3D texture of skip bits.
+// Same fragments and the same order of composition as the generic kernel; the lookups are the reference's own or exact
+// re-tabulations of them.
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float fma_sat(float a, float b, float c) {
     float d;
@@ -523,7 +531,8 @@ __device__ __forceinline__ float4 tex_layer4(unsigned long long tex, int layer, 
 
 // NB: number of baked cone steps (compile-time: no predication of the unused slots).
 // kSeg: small frames (1280x720: a few thousand tiles) do not fill 148 SMs and are bound by the ONE warp that walks the
-// longest list.  There the list of a tile is cut into tp.segCount contiguous depth segments, each composited on its own
+// longest list; and on mid-sized frames (C3) shorter-lived CTAs let the next frame's set-up kernels and the read-back in
+// sooner.  There the list of a tile is cut into tp.segCount contiguous depth segments, each composited on its own
 // by a separate CTA into (C_s, T_s); the last CTA to arrive merges them front to back: C = C_0 + T_0 C_1 + T_0 T_1 C_2 ...
 // Same fragments, same order; the sum is re-associated (differences of a few ulp), and the early ray termination only
 // sees its own segment's transmittance (still bounded by the cutoff).
